@@ -1,0 +1,118 @@
+// Host-side launch interface of the sm_100a kernels (internal C++; the public C-ABI is
+// include/gitb200.h, implemented in api.cu on top of these).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
+
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual, bf16 operands, fp32 accumulation in TMEM.
+struct GemmArgs {
+  const bf16* A = nullptr;  // row-major [M, K], leading dimension lda (elements, multiple of 8)
+  int lda = 0;
+  const bf16* W = nullptr;  // row-major [N, K] (the nn.Linear layout), leading dimension ldw
+  int ldw = 0;
+  int M = 0, N = 0, K = 0;        // N % 128 == 0, K % 8 == 0
+  const float* bias = nullptr;    // [N] fp32, optional
+  const bf16* residual = nullptr; // optional addend, leading dimension ldr
+  int ldr = 0;
+  int res_periodic = 0;  // 1: residual row = (r % gin) + goff (positional-embedding table), 0: output row
+  int act = ACT_NONE;
+  bf16* out = nullptr;  // optional bf16 output, leading dimension ldo
+  int ldo = 0;
+  float* out_f32 = nullptr;  // optional fp32 output, leading dimension ldo32
+  int ldo32 = 0;
+  // Output row remap: out_row = (r / gin) * gout + (r % gin) + goff when gin > 0 (used to leave a
+  // gap for the CLS row of every frame in the patch-embedding GEMM).
+  int gin = 0, gout = 0, goff = 0;
+};
+// force_bn: 0 = heuristic, 128 or 256 = tile width override (tests / tuning).
+cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn = 0);
+const char* gemm_last_error();
+
+// out[r,:] = LN(x[r,:]) * gamma + beta (+ addend[((r / add_group) % add_period), :]); fp32 statistics.
+struct LayerNormArgs {
+  const bf16* x = nullptr;
+  int ldx = 0;
+  int rows = 0, cols = 0;  // cols % 256 == 0 or cols == 768/1024; handled generically for cols % 8 == 0, cols <= 4096
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  const float* addend = nullptr;  // optional [add_period, cols] fp32 (temporal embedding)
+  int add_group = 1, add_period = 1;
+  bf16* out = nullptr;
+  int ldo = 0;
+  float* out_f32 = nullptr;  // optional fp32 copy
+  int ldo32 = 0;
+};
+cudaError_t layernorm_bf16(const LayerNormArgs& a, cudaStream_t stream);
+
+// frames fp32 NCHW [n_frames, 3, res, res] -> patches bf16 [n_frames * grid * grid, kpad], k = c*p*p + ky*p + kx
+cudaError_t im2col_patches(const float* frames, int n_frames, int res, int patch, int kpad, bf16* out,
+                           cudaStream_t stream);
+// x[f*T + 0, :] = cls[:] + pos[0, :]   (bf16 residual stream)
+cudaError_t write_cls_rows(const float* cls, const bf16* pos, int n_frames, int T, int width, bf16* x,
+                           cudaStream_t stream);
+
+// Bidirectional self-attention over fixed-length groups of rows (ViT frames: len 197/257; decoder
+// visual pass: len Nv).  qkv: [rows, 3*H*64] bf16 laid out [q | k | v], out: [rows, H*64] bf16.
+cudaError_t attention_groups(const bf16* qkv, int ld_qkv, bf16* out, int ldo, int n_groups, int group_len,
+                             int heads, float scale, cudaStream_t stream);
+
+// Text rows attending to the visual keys of their clip plus their causal text prefix.
+struct TextAttnArgs {
+  const bf16* q = nullptr;  // [n_rows, ldq] : query of text row r (first H*64 columns used)
+  int ldq = 0;
+  int n_clips = 0, rows_per_clip = 0;  // row r belongs to clip r / rows_per_clip
+  int heads = 0;
+  const bf16* vis_kv = nullptr;  // this layer's visual K|V: [n_clips * Nv, ld_vis], K at col k_off, V at col v_off
+  int ld_vis = 0, k_off = 0, v_off = 0, Nv = 0;
+  const bf16* txt_kv = nullptr;  // this layer's text K|V: [max_pos][n_rows][2*H*64]  (K then V)
+  const int* anc = nullptr;      // [n_rows, anc_ld]: slot of row r's ancestor at text position s (null = r)
+  int anc_ld = 0;
+  const int* n_text = nullptr;   // [n_rows] number of visible text keys (pos+1); null = n_text_const
+  int n_text_const = 0;
+  float scale = 0.125f;
+  bf16* out = nullptr;  // [n_rows, ldo]
+  int ldo = 0;
+  float* partial = nullptr;  // workspace: [n_rows * heads * splits * (64 + 2)] fp32
+  int splits = 1;
+};
+cudaError_t text_attention(const TextAttnArgs& a, cudaStream_t stream);
+
+// words[tok] + positions[pos] -> LN(eps) -> out bf16
+cudaError_t embed_text(const int* tokens, const int* positions, int n_rows, const bf16* words, const bf16* pos_table,
+                       const float* gamma, const float* beta, float eps, int width, bf16* out, cudaStream_t stream);
+
+// Scatter this step's K|V (columns [H*64, 3*H*64) of qkv) into the text KV plane at position `pos[r]`.
+cudaError_t store_text_kv(const bf16* qkv, int ld_qkv, int n_rows, int kv_width, const int* pos, int pos_const,
+                          bf16* txt_kv, cudaStream_t stream);
+
+// Beam / greedy search state, all device resident (semantics: reference model.py:479-678).
+struct SearchState {
+  int n_clips, nb, cand, V, ldl, max_len, eos, n_keep;
+  float length_penalty;
+  int* tokens;        // [n_rows, max_len]   current partial captions (input_ids)
+  int* tokens_tmp;    // [n_rows, max_len]
+  float* beam_scores; // [n_rows]
+  int* done;          // [n_clips]
+  int* anc;           // [n_rows, max_len] ancestor slot per text position
+  int* anc_tmp;
+  int* cur_tok;       // [n_rows] token fed to the next step
+  // hypotheses: per clip up to n_keep (+1 scratch)
+  float* hyp_score;   // [n_clips, n_keep + 1]
+  int* hyp_len;       // [n_clips, n_keep + 1]
+  int* hyp_tok;       // [n_clips, n_keep + 1, max_len]
+  int* hyp_count;     // [n_clips]
+  float* worst;       // [n_clips]
+  int reorder_cache;  // 0 = reference behaviour (cache rows never re-indexed), 1 = re-index by parent
+};
+// One search step: log-softmax over logits [n_rows, ldl] (fp32), + beam score, top-(cand) per clip,
+// then the reference's candidate walk; cur_len = current caption length before this step.
+cudaError_t search_step(const SearchState& s, const float* logits, int cur_len, cudaStream_t stream);
+cudaError_t search_init(const SearchState& s, int sos, cudaStream_t stream);
+// decoded [n_clips, n_keep, max_len] (eos padded), logprobs [n_clips, n_keep]
+cudaError_t search_finalize(const SearchState& s, int* decoded, float* logprobs, cudaStream_t stream);
