@@ -1,0 +1,11 @@
+"""Importable alias of the package directory `real-time-video-captioning_b200/` (its name is not a valid
+Python identifier): ``import gitb200`` == importlib.import_module("real-time-video-captioning_b200")."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module("real-time-video-captioning_b200")
+sys.modules[__name__] = _pkg

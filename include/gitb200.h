@@ -1,0 +1,144 @@
+/*
+ * gitb200 -- C ABI of the B200-native GIT captioning hot path.
+ *
+ * The reference (farazali7/real-time-video-captioning) has no FFI: its boundary for this path is the
+ * Python class surface of /root/reference/src/models/model.py.  Each entry point below names the
+ * reference interface whose arithmetic it replaces; the Python mirror in
+ * real-time-video-captioning_b200/model.py binds them with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative
+ * gitb200_status, never throws; `gitb200_last_error` gives the message.  Pointers named *_dev are
+ * device pointers on the context's GPU, *_host are host pointers.  All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and is asynchronous unless stated.
+ * One context per GPU; a context is not thread-safe.  There is no CPU fallback: without a usable
+ * sm_100 device every compute call fails with GITB200_ERR_CUDA.
+ */
+#ifndef GITB200_H_
+#define GITB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gitb200_ctx gitb200_ctx;
+
+typedef enum {
+  GITB200_OK = 0,
+  GITB200_ERR_INVALID = -1,  /* bad argument / unsupported shape */
+  GITB200_ERR_CUDA = -2,     /* CUDA runtime or driver error (message has the detail) */
+  GITB200_ERR_STATE = -3,    /* call order violated (weights not finalised, no visual features, ...) */
+  GITB200_ERR_MISSING = -4   /* a required weight was never loaded */
+} gitb200_status;
+
+/* Model hyper-parameters: get_git_model(tokenizer, param), model.py:681-718. */
+typedef struct {
+  int vit_width, vit_layers, vit_heads, patch, resolution; /* CLIPViT_B_16: 768,12,12,16,224; CLIPViT_L_14: 1024,24,16,14,224 */
+  int hidden, dec_layers, dec_heads, ffn;                   /* 768, 6, 12, 3072            (model.py:690-693) */
+  int vocab, max_positions;                                 /* 30522, 1024                 (model.py:689,694) */
+  int num_image_with_embedding;                             /* param['num_image_with_embedding'] (model.py:368) */
+  float vit_ln_eps, proj_ln_eps, embed_ln_eps, bert_ln_eps; /* 1e-5, 1e-5, 1e-8, 1e-12 */
+  int sos, eos;                                             /* tokenizer.cls_token_id / sep_token_id (model.py:363-364) */
+} gitb200_config;
+
+/* GeneratorWithBeamSearchV2(...) + search(...) arguments, model.py:702-708 and :479-480. */
+typedef struct {
+  int beam_size;          /* 4  (model.py:706) */
+  int max_steps;          /* 15 (model.py:704): captions hold at most max_steps tokens incl. SOS */
+  int per_node_beam_size; /* 2  (upstream default) */
+  int num_keep_best;      /* 1  (model.py:479) */
+  float length_penalty;   /* 0.6 (model.py:707) */
+  int reorder_cache;      /* 0 = reference behaviour: decoder cache rows are NOT re-indexed after a beam
+                             re-order (model.py:623-634 is commented out); 1 = re-index by parent beam */
+} gitb200_search_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int gitb200_create(const gitb200_config* cfg, int device, gitb200_ctx** out);
+void gitb200_destroy(gitb200_ctx* ctx);
+/* Message of the last failure on this context (ctx may be NULL for create failures). */
+const char* gitb200_last_error(const gitb200_ctx* ctx);
+/* Library build info, e.g. "gitb200 0.1 sm_100a". */
+const char* gitb200_version(void);
+
+/* ---- weights: load_state_dict(self.model, ckpt['model']), model.py:736-738 -------------------
+ * `name` is the upstream state-dict key (image_encoder.conv1.weight, textual.transformer.encoder.
+ * layer.0.attention.self.query.weight, img_temperal_embedding.0, ...); `data` is fp32, host or device.
+ * Unknown names are ignored (upstream's loader is tolerant); finalize repacks everything once:
+ * bf16 K-major matrices, fused decoder QKV, vocabulary padded to a multiple of 256. */
+int gitb200_load_weight(gitb200_ctx* ctx, const char* name, const float* data, int ndim, const int64_t* shape);
+int gitb200_finalize_weights(gitb200_ctx* ctx);
+
+/* Pre-size every workspace and the KV cache (optional; calls grow them on demand). */
+int gitb200_reserve(gitb200_ctx* ctx, int max_clips, int max_frames, int max_rows_per_clip, int max_text_len);
+
+/* Geometry helpers. */
+int gitb200_tokens_per_frame(const gitb200_ctx* ctx); /* T = (resolution/patch)^2 + 1 */
+int gitb200_logits_ld(const gitb200_ctx* ctx);        /* leading dimension of every logits buffer (vocab rounded up to 256) */
+
+/* ---- image encoder: self.image_encoder(frames) + temporal embeddings + concat, model.py:378-382 -
+ * frames_dev: fp32 [n_clips, n_frames, 3, R, R].  Frames beyond num_image_with_embedding are dropped
+ * (zip truncation, model.py:380).  Keeps the bf16 visual features inside the context for the calls
+ * below and, if visual_features_dev != NULL, also writes them as fp32 [n_clips, F'*T, Dv]. */
+int gitb200_encode(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames, float* visual_features_dev,
+                   void* stream);
+/* Use caller-provided visual features (infer(batch, visual_features, ...), model.py:426). fp32 [n_clips, nv, Dv]. */
+int gitb200_set_visual_features(gitb200_ctx* ctx, const float* visual_features_dev, int n_clips, int nv, void* stream);
+
+/* ---- caption search: infer + GeneratorWithBeamSearchV2.search, model.py:426-462, :479-678 -----
+ * Runs on the context's current visual features.  tokens_dev: int32 [n_clips, num_keep_best, max_steps]
+ * (eos padded, SOS first); logprobs_dev: fp32 [n_clips, num_keep_best]; logits_dev (optional): fp32
+ * [max_steps-1, n_clips*beam_size, logits_ld] = the per-step scores the reference copies to the host at
+ * model.py:521 (kept on the device here). */
+int gitb200_decode(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev,
+                   float* logits_dev, void* stream);
+/* encode + decode. */
+int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
+                    const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
+                    void* stream);
+/* Same with HOST buffers (frames_host should be pinned for full PCIe speed): chunks of `chunk_clips`
+ * clips are copied host->device on a side stream while the previous chunk computes; tokens and
+ * logprobs are copied back; returns after everything has completed (synchronous). */
+int gitb200_caption_host(gitb200_ctx* ctx, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
+                         const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host);
+
+/* ---- teacher-forced logits: forward_one_custom, model.py:371-424 ------------------------------
+ * tokens_dev: int32 [n_clips, L].  If frames_dev == NULL the current visual features are used.
+ * logits_dev: fp32 [n_clips*L, logits_ld].  hidden_states_dev (optional): fp32
+ * [n_clips, dec_layers+1, nv+L, hidden] (the 7 stacked hidden states of model.py:419-423).
+ * visual_features_dev (optional): fp32 [n_clips, nv, Dv]. */
+int gitb200_forward_logits(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
+                           const int32_t* tokens_dev, int L, float* logits_dev, float* hidden_states_dev,
+                           float* visual_features_dev, void* stream);
+
+/* ---- step-wise decoding: CaptioningModel.decoding_step bound at model.py:442-445 --------------
+ * For callers that drive their own search loop through the generic `step(input_ids)` callable.
+ * begin: runs the decoder over the visual tokens (the first-call branch of decoding_step) for
+ * n_clips * rows_per_clip rows; step: feeds one token per row at text position `pos` and writes
+ * fp32 logits [rows, logits_ld]; reorder: optional cache re-index by beam_idx (int32 [rows]). */
+int gitb200_decode_begin(gitb200_ctx* ctx, int rows_per_clip, void* stream);
+int gitb200_decode_step(gitb200_ctx* ctx, const int32_t* tokens_dev, int pos, float* logits_dev, void* stream);
+int gitb200_decode_reorder(gitb200_ctx* ctx, const int32_t* beam_idx_dev, int pos, void* stream);
+
+/* ---- single operators (used by the parity tests; same kernels the pipeline launches) ---------- */
+/* out = act(A[M,K] * W[N,K]^T + bias) + residual; bf16 in/out (uint16 storage), fp32 bias. act: 0 none,
+ * 1 QuickGELU, 2 erf-GELU.  tile_n: 0 auto, 128 or 256. */
+int gitb200_op_gemm(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev,
+                    const void* residual_dev, int act, void* out_bf16_dev, float* out_f32_dev, int tile_n,
+                    void* stream);
+int gitb200_op_layernorm(const void* x_dev, int rows, int cols, const float* gamma_dev, const float* beta_dev,
+                         float eps, void* out_bf16_dev, void* stream);
+/* qkv: bf16 [n_groups*group_len, 3*heads*64] -> out bf16 [n_groups*group_len, heads*64] */
+int gitb200_op_attention_groups(const void* qkv_dev, void* out_dev, int n_groups, int group_len, int heads,
+                                float scale, void* stream);
+/* Search on a pre-computed score sequence: logits_dev fp32 [max_steps-1, n_clips*beam, ld]. */
+int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, int sos, int eos,
+                      const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, void* stream);
+
+/* Number of kernels this library has launched since the last call with reset != 0 (bench.py's gpu_launches). */
+long long gitb200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GITB200_H_ */

@@ -1,0 +1,904 @@
+// C-ABI (include/gitb200.h) and the host-side engine of the captioning path: weight repacking,
+// workspace / KV-cache management in HBM, and the launch sequences for
+//   encode  (CLIP ViT over every frame + temporal embeddings)          -- model.py:378-382
+//   visual pass of the prefix-LM decoder (fills the visual K/V cache)  -- first call of decoding_step
+//   decode steps + device-side beam / greedy search                    -- model.py:426-462, :479-678
+//   teacher-forced logits (forward_one_custom)                         -- model.py:371-424
+//
+// HBM layout (all activations bf16, row-major, rows = tokens):
+//   ViT:      x/ln [n_clips*F*T, W], qkv [.., 3W], attn [.., W], mlp [.., 4W]
+//   decoder:  hv [n_clips*Nv, H] visual hidden states; kv[l] [n_clips*Nv, 3H] = this layer's q|k|v of the
+//             visual tokens -- columns [H, 3H) ARE the visual K/V cache that every decode step of every
+//             beam of the clip reads (pages = one clip's contiguous Nv rows, shared by all beams);
+//             txt_kv[l] [max_len][rows][2H] text K/V cache, one slot per beam row and position, re-ordered
+//             through the ancestor table instead of being copied.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gitb200.h"
+#include "kernels.h"
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches += n; }
+
+namespace {
+
+std::string g_create_err;
+
+struct DevF32 {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto d : shape) n *= (size_t)d;
+    return n;
+  }
+};
+
+struct VitLayer {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc1, *b_fc2;
+  bf16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+};
+struct DecLayer {
+  float *b_qkv, *b_out, *lna_g, *lna_b, *b_fc1, *b_fc2, *lno_g, *lno_b;
+  bf16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+};
+
+template <typename T>
+struct Buf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+}  // namespace
+
+struct gitb200_ctx {
+  gitb200_config cfg;
+  int device = 0;
+  std::string err;
+  bool finalized = false;
+  std::map<std::string, DevF32> raw;  // staged fp32 weights (freed by finalize)
+  std::vector<void*> weight_allocs;
+
+  // geometry
+  int T = 0, kpad = 0, vocab_pad = 0, n_temporal = 0;
+
+  // repacked weights
+  bf16 *w_patch = nullptr, *pos_bf16 = nullptr;
+  float *cls = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+  float* temporal = nullptr;  // [n_temporal, W]
+  std::vector<VitLayer> vit;
+  bf16* w_proj = nullptr;
+  float *b_proj = nullptr, *lnp_g = nullptr, *lnp_b = nullptr;
+  float *words_f32 = nullptr, *pos_f32 = nullptr, *lne_g = nullptr, *lne_b = nullptr;
+  std::vector<DecLayer> dec;
+  bf16* w_vocab = nullptr;
+  float* b_vocab = nullptr;
+
+  // workspaces
+  Buf<bf16> patches, x, lnb, qkv, attn, mlp, vf, hv, hvb, hvc, vattn, vmlp;
+  std::vector<Buf<bf16>> kv;      // per decoder layer: [n_clips*Nv, 3H]
+  std::vector<Buf<bf16>> txt_kv;  // per decoder layer: [max_len][rows][2H]
+  Buf<bf16> tx, tq, ta, tb, tc, tf;
+  Buf<float> logits, partial, vf_in_f32;
+  Buf<int> ibuf;       // search ints
+  Buf<double> dbuf;    // search doubles
+  Buf<float> fbuf;     // search floats
+  Buf<int> pos_arr, ntext_arr, tok_arr;
+  Buf<float> stage[2];  // host-path frame staging
+  Buf<int> out_tok;
+  Buf<float> out_lp;
+  cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+  // current state
+  int cur_clips = 0, cur_nv = 0;     // visual features held in vf
+  int step_rows_per_clip = 0;        // step-wise decoding state
+  bool visual_pass_done = false;
+  int visual_pass_full = 0;
+  int anc_parity = 0;
+  bool step_anc_used = false;
+};
+
+namespace {
+
+int fail(gitb200_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_err = buf;
+  return code;
+}
+
+#define CUDA_OK(c, expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t e_ = (expr);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      return fail(c, GITB200_ERR_CUDA, "%s failed: %s [%s] (%s:%d)", #expr, cudaGetErrorString(e_),        \
+                  gemm_last_error(), __FILE__, __LINE__);                                                  \
+  } while (0)
+
+template <typename T>
+int ensure(gitb200_ctx* c, Buf<T>& b, size_t n) {
+  if (b.cap >= n) return 0;
+  if (b.p) CUDA_OK(c, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  CUDA_OK(c, cudaMalloc(&b.p, n * sizeof(T)));
+  b.cap = n;
+  return 0;
+}
+#define ENSURE(c, b, n)                   \
+  do {                                    \
+    int r_ = ensure(c, b, (size_t)(n));   \
+    if (r_) return r_;                    \
+  } while (0)
+
+template <typename T>
+int walloc(gitb200_ctx* c, T** p, size_t n) {
+  CUDA_OK(c, cudaMalloc(p, n * sizeof(T)));
+  c->weight_allocs.push_back(*p);
+  return 0;
+}
+
+const DevF32* find(gitb200_ctx* c, const std::string& name) {
+  auto it = c->raw.find(name);
+  return it == c->raw.end() ? nullptr : &it->second;
+}
+
+// fp32 [rows, cols] -> bf16 [dst_rows, dst_cols] zero padded
+int to_bf16(gitb200_ctx* c, const std::string& name, int rows, int cols, int dst_rows, int dst_cols, bf16** out) {
+  const DevF32* w = find(c, name);
+  if (!w) return fail(c, GITB200_ERR_MISSING, "missing weight %s", name.c_str());
+  if (w->numel() != (size_t)rows * cols)
+    return fail(c, GITB200_ERR_INVALID, "weight %s has %zu elements, expected %d x %d", name.c_str(), w->numel(), rows, cols);
+  int r = walloc(c, out, (size_t)dst_rows * dst_cols);
+  if (r) return r;
+  CUDA_OK(c, cast_f32_to_bf16(w->p, rows, cols, cols, *out, dst_cols, dst_rows, dst_cols, 0));
+  return 0;
+}
+// fp32 vector copy (optionally zero padded)
+int to_f32(gitb200_ctx* c, const std::string& name, size_t n, size_t n_pad, float** out) {
+  const DevF32* w = find(c, name);
+  if (!w) return fail(c, GITB200_ERR_MISSING, "missing weight %s", name.c_str());
+  if (w->numel() != n) return fail(c, GITB200_ERR_INVALID, "weight %s has %zu elements, expected %zu", name.c_str(), w->numel(), n);
+  int r = walloc(c, out, n_pad);
+  if (r) return r;
+  if (n_pad > n) CUDA_OK(c, cudaMemset(*out, 0, n_pad * sizeof(float)));
+  CUDA_OK(c, cudaMemcpy(*out, w->p, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  return 0;
+}
+#define TRY(expr)          \
+  do {                     \
+    int r_ = (expr);       \
+    if (r_) return r_;     \
+  } while (0)
+
+int gemm(gitb200_ctx* c, const GemmArgs& g, cudaStream_t s) {
+  CUDA_OK(c, gemm_bf16(g, s, 0));
+  return 0;
+}
+
+GemmArgs linear(const bf16* A, int lda, const bf16* W, int K, int M, int N, const float* bias, bf16* out, int ldo) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = out; g.ldo = ldo;
+  return g;
+}
+
+int ln(gitb200_ctx* c, const bf16* x, int rows, int cols, const float* g, const float* b, float eps, bf16* out,
+       cudaStream_t s, const float* addend = nullptr, int add_group = 1, int add_period = 1, float* out32 = nullptr) {
+  LayerNormArgs a;
+  a.x = x; a.ldx = cols; a.rows = rows; a.cols = cols; a.gamma = g; a.beta = b; a.eps = eps; a.out = out; a.ldo = cols;
+  a.addend = addend; a.add_group = add_group; a.add_period = add_period; a.out_f32 = out32; a.ldo32 = cols;
+  CUDA_OK(c, layernorm_bf16(a, s));
+  return 0;
+}
+
+// ------------------------------------------------------------------ encode
+int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s) {
+  const gitb200_config& k = c->cfg;
+  const int W = k.vit_width, T = c->T, G = k.resolution / k.patch;
+  // zip() truncation of model.py:380: frames beyond the temporal-embedding list are dropped
+  const int F = (k.num_image_with_embedding > 0 && n_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : n_frames;
+  const int rows = n_clips * F * T;
+  const int prow = n_clips * F * G * G;
+  ENSURE(c, c->patches, (size_t)prow * c->kpad);
+  ENSURE(c, c->x, (size_t)rows * W);
+  ENSURE(c, c->lnb, (size_t)rows * W);
+  ENSURE(c, c->qkv, (size_t)rows * 3 * W);
+  ENSURE(c, c->attn, (size_t)rows * W);
+  ENSURE(c, c->mlp, (size_t)rows * 4 * W);
+  ENSURE(c, c->vf, (size_t)rows * W);
+
+  const size_t frame_elems = (size_t)3 * k.resolution * k.resolution;
+  if (F == n_frames) {
+    CUDA_OK(c, im2col_patches(frames, n_clips * F, k.resolution, k.patch, c->kpad, c->patches.p, s));
+  } else {
+    for (int i = 0; i < n_clips; ++i)
+      CUDA_OK(c, im2col_patches(frames + (size_t)i * n_frames * frame_elems, F, k.resolution, k.patch, c->kpad,
+                                c->patches.p + (size_t)i * F * G * G * c->kpad, s));
+  }
+  // patch embedding (conv1 as GEMM) + positional embedding, rows shifted to leave the CLS slot of every frame
+  {
+    GemmArgs g = linear(c->patches.p, c->kpad, c->w_patch, c->kpad, prow, W, nullptr, c->x.p, W);
+    g.residual = c->pos_bf16; g.ldr = W; g.res_periodic = 1; g.gin = G * G; g.gout = T; g.goff = 1;
+    TRY(gemm(c, g, s));
+  }
+  CUDA_OK(c, write_cls_rows(c->cls, c->pos_bf16, n_clips * F, T, W, c->x.p, s));
+  // ln_pre (in place semantics: x <- ln_pre(x)); the residual stream starts from the normalised tokens
+  TRY(ln(c, c->x.p, rows, W, c->ln_pre_g, c->ln_pre_b, k.vit_ln_eps, c->lnb.p, s));
+  std::swap(c->x.p, c->lnb.p);
+  std::swap(c->x.cap, c->lnb.cap);
+  const float scale = 1.0f / sqrtf((float)(W / k.vit_heads));
+  for (int l = 0; l < k.vit_layers; ++l) {
+    const VitLayer& L = c->vit[l];
+    TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
+    TRY(gemm(c, linear(c->lnb.p, W, L.w_qkv, W, rows, 3 * W, L.b_qkv, c->qkv.p, 3 * W), s));
+    CUDA_OK(c, attention_groups(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
+    {
+      GemmArgs g = linear(c->attn.p, W, L.w_out, W, rows, W, L.b_out, c->x.p, W);
+      g.residual = c->x.p; g.ldr = W;  // x += out_proj(attn): each element is read then written by one thread
+      TRY(gemm(c, g, s));
+    }
+    TRY(ln(c, c->x.p, rows, W, L.ln2_g, L.ln2_b, k.vit_ln_eps, c->lnb.p, s));
+    {
+      GemmArgs g = linear(c->lnb.p, W, L.w_fc1, W, rows, 4 * W, L.b_fc1, c->mlp.p, 4 * W);
+      g.act = ACT_QUICK_GELU;
+      TRY(gemm(c, g, s));
+    }
+    {
+      GemmArgs g = linear(c->mlp.p, 4 * W, L.w_fc2, 4 * W, rows, W, L.b_fc2, c->x.p, W);
+      g.residual = c->x.p; g.ldr = W;
+      TRY(gemm(c, g, s));
+    }
+  }
+  // ln_post on all tokens + temporal embedding of the frame (frame index = (row / T) % F)
+  TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, c->vf.p, s,
+         k.num_image_with_embedding > 0 ? c->temporal : nullptr, T, F));
+  c->cur_clips = n_clips;
+  c->cur_nv = F * T;
+  c->visual_pass_done = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------ decoder over the visual tokens
+// full_last: also run attention/FFN of the last layer on the visual rows (needed only for hidden-state output)
+int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_text, cudaStream_t s) {
+  const gitb200_config& k = c->cfg;
+  const int H = k.hidden, Nv = c->cur_nv, B = c->cur_clips, M = B * Nv;
+  if (B <= 0 || Nv <= 0) return fail(c, GITB200_ERR_STATE, "no visual features: call gitb200_encode or gitb200_set_visual_features first");
+  ENSURE(c, c->hv, (size_t)M * H);
+  ENSURE(c, c->hvb, (size_t)M * H);
+  ENSURE(c, c->hvc, (size_t)M * H);
+  ENSURE(c, c->vattn, (size_t)M * H);
+  ENSURE(c, c->vmlp, (size_t)M * k.ffn);
+  if ((int)c->kv.size() != k.dec_layers) c->kv.resize(k.dec_layers);
+  for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->kv[l], (size_t)M * 3 * H);
+
+  auto emit_hidden = [&](int idx) -> int {
+    if (!hidden_out) return 0;
+    // hidden_out: [B, layers+1, Nv+L, H]; visual rows of clip b, state idx
+    const size_t per_state = (size_t)(Nv + L_text) * H;
+    for (int b = 0; b < B; ++b)
+      CUDA_OK(c, cast_bf16_to_f32(c->hv.p + (size_t)b * Nv * H, Nv, H, H,
+                                  hidden_out + ((size_t)b * (k.dec_layers + 1) + idx) * per_state, H, s));
+    return 0;
+  };
+
+  // visual_projection = Linear + LayerNorm
+  TRY(gemm(c, linear(c->vf.p, k.vit_width, c->w_proj, k.vit_width, M, H, c->b_proj, c->hvb.p, H), s));
+  TRY(ln(c, c->hvb.p, M, H, c->lnp_g, c->lnp_b, k.proj_ln_eps, c->hv.p, s));
+  TRY(emit_hidden(0));
+  const float scale = 1.0f / sqrtf((float)(H / k.dec_heads));
+  for (int l = 0; l < k.dec_layers; ++l) {
+    const DecLayer& L = c->dec[l];
+    const bool full = (l + 1 < k.dec_layers) || full_last;
+    if (full) {
+      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv, H, M, 3 * H, L.b_qkv, c->kv[l].p, 3 * H), s));
+    } else {
+      // last layer: only K and V of the visual tokens are ever read again
+      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv + (size_t)H * H, H, M, 2 * H, L.b_qkv + H, c->kv[l].p + H, 3 * H), s));
+      break;
+    }
+    CUDA_OK(c, attention_groups(c->kv[l].p, 3 * H, c->vattn.p, H, B, Nv, k.dec_heads, scale, s));
+    {
+      GemmArgs g = linear(c->vattn.p, H, L.w_out, H, M, H, L.b_out, c->hvb.p, H);
+      g.residual = c->hv.p; g.ldr = H;
+      TRY(gemm(c, g, s));
+    }
+    TRY(ln(c, c->hvb.p, M, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->hvc.p, s));
+    {
+      GemmArgs g = linear(c->hvc.p, H, L.w_fc1, H, M, k.ffn, L.b_fc1, c->vmlp.p, k.ffn);
+      g.act = ACT_GELU_ERF;
+      TRY(gemm(c, g, s));
+    }
+    {
+      GemmArgs g = linear(c->vmlp.p, k.ffn, L.w_fc2, k.ffn, M, H, L.b_fc2, c->hvb.p, H);
+      g.residual = c->hvc.p; g.ldr = H;
+      TRY(gemm(c, g, s));
+    }
+    TRY(ln(c, c->hvb.p, M, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->hv.p, s));
+    TRY(emit_hidden(l + 1));
+  }
+  c->visual_pass_done = true;
+  c->visual_pass_full = full_last ? 1 : 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ text rows through the decoder
+struct TextPass {
+  int n_clips, rows_per_clip, max_len;
+  const int* tokens;     // [rows]
+  const int* positions;  // [rows] or nullptr -> pos_const
+  int pos_const;
+  const int* n_text;     // [rows] or nullptr -> n_text_const
+  int n_text_const;
+  const int* anc;        // ancestor table or nullptr
+  int slot_div, n_slots, slot_is_clip;
+  float* logits;         // [rows, vocab_pad]
+  float* hidden_out;     // optional fp32 [B, layers+1, Nv+L, H] (text rows written)
+};
+
+int ensure_text(gitb200_ctx* c, int rows, int n_slots, int max_len) {
+  const gitb200_config& k = c->cfg;
+  const int H = k.hidden;
+  ENSURE(c, c->tx, (size_t)rows * H);
+  ENSURE(c, c->tq, (size_t)rows * 3 * H);
+  ENSURE(c, c->ta, (size_t)rows * H);
+  ENSURE(c, c->tb, (size_t)rows * H);
+  ENSURE(c, c->tc, (size_t)rows * H);
+  ENSURE(c, c->tf, (size_t)rows * k.ffn);
+  if ((int)c->txt_kv.size() != k.dec_layers) c->txt_kv.resize(k.dec_layers);
+  for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->txt_kv[l], (size_t)max_len * n_slots * 2 * H);
+  return 0;
+}
+
+int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
+  const gitb200_config& k = c->cfg;
+  const int H = k.hidden, rows = t.n_clips * t.rows_per_clip, Nv = c->cur_nv;
+  const float scale = 1.0f / sqrtf((float)(H / k.dec_heads));
+  // split the visual keys over several CTAs when there are too few (clip, head) pairs to fill 148 SMs
+  const int chunks = (t.rows_per_clip + 3) / 4;
+  int splits = (2 * 148 + t.n_clips * chunks * k.dec_heads - 1) / (t.n_clips * chunks * k.dec_heads);
+  if (splits > 16) splits = 16;
+  while (splits > 1 && Nv / splits < 64) --splits;
+  if (splits < 1) splits = 1;
+  if (splits > 1) ENSURE(c, c->partial, text_attention_workspace_floats(rows, k.dec_heads, splits));
+
+  auto emit_hidden = [&](int idx) -> int {
+    if (!t.hidden_out) return 0;
+    const int L = t.rows_per_clip;
+    const size_t per_state = (size_t)(Nv + L) * H;
+    for (int b = 0; b < t.n_clips; ++b)
+      CUDA_OK(c, cast_bf16_to_f32(c->tx.p + (size_t)b * L * H, L, H, H,
+                                  t.hidden_out + ((size_t)b * (k.dec_layers + 1) + idx) * per_state + (size_t)Nv * H, H, s));
+    return 0;
+  };
+
+  CUDA_OK(c, embed_text(t.tokens, t.positions, t.pos_const, rows, c->words_f32, c->pos_f32, c->lne_g, c->lne_b,
+                        k.embed_ln_eps, H, c->tx.p, s));
+  TRY(emit_hidden(0));
+  for (int l = 0; l < k.dec_layers; ++l) {
+    const DecLayer& L = c->dec[l];
+    TRY(gemm(c, linear(c->tx.p, H, L.w_qkv, H, rows, 3 * H, L.b_qkv, c->tq.p, 3 * H), s));
+    CUDA_OK(c, store_text_kv(c->tq.p, 3 * H, rows, 2 * H, H, t.positions, t.pos_const, t.slot_div, t.n_slots,
+                             c->txt_kv[l].p, s));
+    TextAttnArgs a;
+    a.q = c->tq.p; a.ldq = 3 * H; a.n_clips = t.n_clips; a.rows_per_clip = t.rows_per_clip; a.heads = k.dec_heads;
+    a.vis_kv = c->kv[l].p; a.ld_vis = 3 * H; a.k_off = H; a.v_off = 2 * H; a.Nv = Nv;
+    a.txt_kv = c->txt_kv[l].p; a.txt_slots = t.n_slots; a.text_slot_is_clip = t.slot_is_clip;
+    a.anc = t.anc; a.anc_ld = t.max_len; a.n_text = t.n_text; a.n_text_const = t.n_text_const;
+    a.scale = scale; a.out = c->ta.p; a.ldo = H; a.partial = c->partial.p; a.splits = splits;
+    CUDA_OK(c, text_attention(a, s));
+    {
+      GemmArgs g = linear(c->ta.p, H, L.w_out, H, rows, H, L.b_out, c->tb.p, H);
+      g.residual = c->tx.p; g.ldr = H;
+      TRY(gemm(c, g, s));
+    }
+    TRY(ln(c, c->tb.p, rows, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->tc.p, s));
+    {
+      GemmArgs g = linear(c->tc.p, H, L.w_fc1, H, rows, k.ffn, L.b_fc1, c->tf.p, k.ffn);
+      g.act = ACT_GELU_ERF;
+      TRY(gemm(c, g, s));
+    }
+    {
+      GemmArgs g = linear(c->tf.p, k.ffn, L.w_fc2, k.ffn, rows, H, L.b_fc2, c->tb.p, H);
+      g.residual = c->tc.p; g.ldr = H;
+      TRY(gemm(c, g, s));
+    }
+    TRY(ln(c, c->tb.p, rows, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->tx.p, s));
+    TRY(emit_hidden(l + 1));
+  }
+  {
+    GemmArgs g = linear(c->tx.p, H, c->w_vocab, H, rows, c->vocab_pad, c->b_vocab, nullptr, 0);
+    g.out_f32 = t.logits; g.ldo32 = c->vocab_pad;
+    TRY(gemm(c, g, s));
+  }
+  return 0;
+}
+
+int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unused, int eos, const gitb200_search_params& sp,
+                      SearchState* st) {
+  (void)sos_unused;
+  const int nb = sp.beam_size, rows = n_clips * nb, ml = sp.max_steps, nk = sp.num_keep_best;
+  if (nb < 1 || nb > 8 || sp.per_node_beam_size < 1 || nb * sp.per_node_beam_size > 16 || nk < 1 || nk > 15 || ml < 2)
+    return fail(c, GITB200_ERR_INVALID, "unsupported search parameters (beam %d, per-node %d, keep %d, max_steps %d)", nb,
+                sp.per_node_beam_size, nk, ml);
+  const size_t n_int = (size_t)rows * ml * 4 + (size_t)n_clips * 2 + rows + (size_t)n_clips * (nk + 1) * (1 + ml);
+  ENSURE(c, c->ibuf, n_int);
+  ENSURE(c, c->dbuf, (size_t)n_clips * (nk + 2));
+  ENSURE(c, c->fbuf, (size_t)rows);
+  int* ip = c->ibuf.p;
+  st->n_clips = n_clips; st->nb = nb; st->cand = nb * sp.per_node_beam_size; st->V = V; st->ldl = ldl; st->max_len = ml;
+  st->eos = eos; st->n_keep = nk; st->length_penalty = sp.length_penalty; st->reorder_cache = sp.reorder_cache;
+  st->tokens = ip; ip += (size_t)rows * ml;
+  st->tokens_tmp = ip; ip += (size_t)rows * ml;
+  st->anc = ip; ip += (size_t)rows * ml;
+  st->anc_tmp = ip; ip += (size_t)rows * ml;
+  st->done = ip; ip += n_clips;
+  st->hyp_count = ip; ip += n_clips;
+  st->cur_tok = ip; ip += rows;
+  st->hyp_len = ip; ip += (size_t)n_clips * (nk + 1);
+  st->hyp_tok = ip;
+  st->hyp_score = c->dbuf.p;
+  st->worst = c->dbuf.p + (size_t)n_clips * (nk + 1);
+  st->beam_scores = c->fbuf.p;
+  return 0;
+}
+
+int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_out, float* logprobs_out, float* logits_out,
+               cudaStream_t s) {
+  const gitb200_config& k = c->cfg;
+  const int B = c->cur_clips, nb = sp.beam_size, rows = B * nb;
+  if (sp.max_steps > k.max_positions) return fail(c, GITB200_ERR_INVALID, "max_steps %d exceeds the %d text positions", sp.max_steps, k.max_positions);
+  SearchState st;
+  TRY(make_search_state(c, B, k.vocab, c->vocab_pad, k.sos, k.eos, sp, &st));
+  if (!c->visual_pass_done) TRY(run_visual_pass(c, false, nullptr, 0, s));
+  TRY(ensure_text(c, rows, rows, sp.max_steps));
+  if (!logits_out) ENSURE(c, c->logits, (size_t)rows * c->vocab_pad);
+  CUDA_OK(c, search_init(st, k.sos, s));
+  int parity = 0;
+  for (int t = 0; t + 1 < sp.max_steps; ++t) {  // model.py:518: while cur_len < max_length, cur_len = t + 1
+    TextPass tp;
+    tp.n_clips = B; tp.rows_per_clip = nb; tp.max_len = sp.max_steps;
+    tp.tokens = st.cur_tok; tp.positions = nullptr; tp.pos_const = t;
+    tp.n_text = nullptr; tp.n_text_const = t + 1;
+    tp.anc = sp.reorder_cache ? (parity ? st.anc_tmp : st.anc) : nullptr;
+    tp.slot_div = 1; tp.n_slots = rows; tp.slot_is_clip = 0;
+    tp.logits = logits_out ? logits_out + (size_t)t * rows * c->vocab_pad : c->logits.p;
+    tp.hidden_out = nullptr;
+    TRY(run_text_pass(c, tp, s));
+    CUDA_OK(c, search_step(st, tp.logits, t + 1, parity, s));
+    parity ^= 1;
+  }
+  CUDA_OK(c, search_finalize(st, tokens_out, logprobs_out, s));
+  return 0;
+}
+
+}  // namespace
+
+// ==================================================================== C ABI
+extern "C" {
+
+const char* gitb200_version(void) { return "gitb200 0.1 (sm_100a: tcgen05/TMEM GEMM + TMA, CUDA 12.9)"; }
+
+long long gitb200_launch_count(int reset) {
+  const long long v = g_launches.load();
+  if (reset) g_launches = 0;
+  return v;
+}
+
+const char* gitb200_last_error(const gitb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int gitb200_create(const gitb200_config* cfg, int device, gitb200_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, GITB200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(nullptr, GITB200_ERR_CUDA, "no CUDA device available (%s): gitb200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(nullptr, GITB200_ERR_INVALID, "device %d out of range (%d devices)", device, n_dev);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, GITB200_ERR_CUDA, "device %d is sm_%d%d; gitb200 kernels are built for sm_100a only", device, prop.major, prop.minor);
+  if (cfg->vit_width % 256 != 0 || cfg->vit_width / cfg->vit_heads != 64 || cfg->hidden != 768 || cfg->hidden / cfg->dec_heads != 64 ||
+      cfg->ffn % 256 != 0 || cfg->resolution % cfg->patch != 0 || cfg->vit_layers < 1 || cfg->dec_layers < 1 ||
+      (cfg->vit_width != 768 && cfg->vit_width != 1024))
+    return fail(nullptr, GITB200_ERR_INVALID, "unsupported model geometry (need head dim 64, hidden 768, ViT width 768 or 1024)");
+  gitb200_ctx* c = new gitb200_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  const int G = cfg->resolution / cfg->patch;
+  c->T = G * G + 1;
+  c->kpad = ((3 * cfg->patch * cfg->patch + 63) / 64) * 64;
+  c->vocab_pad = ((cfg->vocab + 255) / 256) * 256;
+  c->n_temporal = cfg->num_image_with_embedding;
+  *out = c;
+  return GITB200_OK;
+}
+
+void gitb200_destroy(gitb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->raw) cudaFree(kv.second.p);
+  for (void* p : c->weight_allocs) cudaFree(p);
+  auto fr = [](auto& b) { if (b.p) cudaFree(b.p); };
+  fr(c->patches); fr(c->x); fr(c->lnb); fr(c->qkv); fr(c->attn); fr(c->mlp); fr(c->vf); fr(c->hv); fr(c->hvb); fr(c->hvc);
+  fr(c->vattn); fr(c->vmlp);
+  for (auto& b : c->kv) fr(b);
+  for (auto& b : c->txt_kv) fr(b);
+  fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
+  fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
+  fr(c->out_tok); fr(c->out_lp);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  delete c;
+}
+
+int gitb200_load_weight(gitb200_ctx* c, const char* name, const float* data, int ndim, const int64_t* shape) {
+  if (!c || !name || !data || ndim < 0 || ndim > 8) return fail(c, GITB200_ERR_INVALID, "bad load_weight argument");
+  if (c->finalized) return fail(c, GITB200_ERR_STATE, "weights already finalised");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  DevF32 w;
+  for (int i = 0; i < ndim; ++i) w.shape.push_back(shape[i]);
+  const size_t n = w.numel();
+  if (n == 0) return fail(c, GITB200_ERR_INVALID, "empty weight %s", name);
+  auto it = c->raw.find(name);
+  if (it != c->raw.end()) {
+    cudaFree(it->second.p);
+    c->raw.erase(it);
+  }
+  CUDA_OK(c, cudaMalloc(&w.p, n * sizeof(float)));
+  CUDA_OK(c, cudaMemcpy(w.p, data, n * sizeof(float), cudaMemcpyDefault));
+  c->raw[name] = w;
+  return GITB200_OK;
+}
+
+int gitb200_finalize_weights(gitb200_ctx* c) {
+  if (!c) return GITB200_ERR_INVALID;
+  if (c->finalized) return GITB200_OK;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const gitb200_config& k = c->cfg;
+  const int W = k.vit_width, H = k.hidden, P = k.patch, T = c->T;
+  const std::string ie = "image_encoder.";
+  TRY(to_bf16(c, ie + "conv1.weight", W, 3 * P * P, W, c->kpad, &c->w_patch));
+  TRY(to_f32(c, ie + "class_embedding", W, W, &c->cls));
+  TRY(to_bf16(c, ie + "positional_embedding", T, W, T, W, &c->pos_bf16));
+  TRY(to_f32(c, ie + "ln_pre.weight", W, W, &c->ln_pre_g));
+  TRY(to_f32(c, ie + "ln_pre.bias", W, W, &c->ln_pre_b));
+  TRY(to_f32(c, ie + "ln_post.weight", W, W, &c->ln_post_g));
+  TRY(to_f32(c, ie + "ln_post.bias", W, W, &c->ln_post_b));
+  c->vit.resize(k.vit_layers);
+  for (int l = 0; l < k.vit_layers; ++l) {
+    const std::string b = ie + "transformer.resblocks." + std::to_string(l) + ".";
+    VitLayer& L = c->vit[l];
+    TRY(to_f32(c, b + "ln_1.weight", W, W, &L.ln1_g));
+    TRY(to_f32(c, b + "ln_1.bias", W, W, &L.ln1_b));
+    TRY(to_bf16(c, b + "attn.in_proj_weight", 3 * W, W, 3 * W, W, &L.w_qkv));
+    TRY(to_f32(c, b + "attn.in_proj_bias", 3 * W, 3 * W, &L.b_qkv));
+    TRY(to_bf16(c, b + "attn.out_proj.weight", W, W, W, W, &L.w_out));
+    TRY(to_f32(c, b + "attn.out_proj.bias", W, W, &L.b_out));
+    TRY(to_f32(c, b + "ln_2.weight", W, W, &L.ln2_g));
+    TRY(to_f32(c, b + "ln_2.bias", W, W, &L.ln2_b));
+    TRY(to_bf16(c, b + "mlp.c_fc.weight", 4 * W, W, 4 * W, W, &L.w_fc1));
+    TRY(to_f32(c, b + "mlp.c_fc.bias", 4 * W, 4 * W, &L.b_fc1));
+    TRY(to_bf16(c, b + "mlp.c_proj.weight", W, 4 * W, W, 4 * W, &L.w_fc2));
+    TRY(to_f32(c, b + "mlp.c_proj.bias", W, W, &L.b_fc2));
+  }
+  if (c->n_temporal > 0) {
+    TRY(walloc(c, &c->temporal, (size_t)c->n_temporal * W));
+    for (int i = 0; i < c->n_temporal; ++i) {
+      const DevF32* w = find(c, "img_temperal_embedding." + std::to_string(i));
+      if (!w) return fail(c, GITB200_ERR_MISSING, "missing weight img_temperal_embedding.%d", i);
+      if (w->numel() != (size_t)W) return fail(c, GITB200_ERR_INVALID, "img_temperal_embedding.%d has %zu elements", i, w->numel());
+      CUDA_OK(c, cudaMemcpy(c->temporal + (size_t)i * W, w->p, W * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+  }
+  const std::string tx = "textual.";
+  TRY(to_bf16(c, tx + "visual_projection.0.weight", H, W, H, W, &c->w_proj));
+  TRY(to_f32(c, tx + "visual_projection.0.bias", H, H, &c->b_proj));
+  TRY(to_f32(c, tx + "visual_projection.1.weight", H, H, &c->lnp_g));
+  TRY(to_f32(c, tx + "visual_projection.1.bias", H, H, &c->lnp_b));
+  TRY(to_f32(c, tx + "embedding.words.weight", (size_t)k.vocab * H, (size_t)k.vocab * H, &c->words_f32));
+  TRY(to_f32(c, tx + "embedding.positions.weight", (size_t)k.max_positions * H, (size_t)k.max_positions * H, &c->pos_f32));
+  TRY(to_f32(c, tx + "embedding.layer_norm.weight", H, H, &c->lne_g));
+  TRY(to_f32(c, tx + "embedding.layer_norm.bias", H, H, &c->lne_b));
+  c->dec.resize(k.dec_layers);
+  for (int l = 0; l < k.dec_layers; ++l) {
+    const std::string b = tx + "transformer.encoder.layer." + std::to_string(l) + ".";
+    DecLayer& L = c->dec[l];
+    // fused q|k|v projection
+    TRY(walloc(c, &L.w_qkv, (size_t)3 * H * H));
+    TRY(walloc(c, &L.b_qkv, (size_t)3 * H));
+    const char* names[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      const DevF32* w = find(c, b + "attention.self." + names[j] + ".weight");
+      const DevF32* bi = find(c, b + "attention.self." + names[j] + ".bias");
+      if (!w || !bi) return fail(c, GITB200_ERR_MISSING, "missing weight %sattention.self.%s.*", b.c_str(), names[j]);
+      if (w->numel() != (size_t)H * H || bi->numel() != (size_t)H) return fail(c, GITB200_ERR_INVALID, "bad shape for %sattention.self.%s", b.c_str(), names[j]);
+      CUDA_OK(c, cast_f32_to_bf16(w->p, H, H, H, L.w_qkv + (size_t)j * H * H, H, H, H, 0));
+      CUDA_OK(c, cudaMemcpy(L.b_qkv + (size_t)j * H, bi->p, H * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    TRY(to_bf16(c, b + "attention.output.dense.weight", H, H, H, H, &L.w_out));
+    TRY(to_f32(c, b + "attention.output.dense.bias", H, H, &L.b_out));
+    TRY(to_f32(c, b + "attention.output.LayerNorm.weight", H, H, &L.lna_g));
+    TRY(to_f32(c, b + "attention.output.LayerNorm.bias", H, H, &L.lna_b));
+    TRY(to_bf16(c, b + "intermediate.dense.weight", k.ffn, H, k.ffn, H, &L.w_fc1));
+    TRY(to_f32(c, b + "intermediate.dense.bias", k.ffn, k.ffn, &L.b_fc1));
+    TRY(to_bf16(c, b + "output.dense.weight", H, k.ffn, H, k.ffn, &L.w_fc2));
+    TRY(to_f32(c, b + "output.dense.bias", H, H, &L.b_fc2));
+    TRY(to_f32(c, b + "output.LayerNorm.weight", H, H, &L.lno_g));
+    TRY(to_f32(c, b + "output.LayerNorm.bias", H, H, &L.lno_b));
+  }
+  // vocabulary head: upstream ties output.weight to embedding.words.weight; accept either
+  const std::string ow = find(c, tx + "output.weight") ? tx + "output.weight" : tx + "embedding.words.weight";
+  TRY(to_bf16(c, ow, k.vocab, H, c->vocab_pad, H, &c->w_vocab));
+  if (find(c, tx + "output.bias")) {
+    TRY(to_f32(c, tx + "output.bias", k.vocab, c->vocab_pad, &c->b_vocab));
+  } else {
+    TRY(walloc(c, &c->b_vocab, (size_t)c->vocab_pad));
+    CUDA_OK(c, cudaMemset(c->b_vocab, 0, c->vocab_pad * sizeof(float)));
+  }
+  CUDA_OK(c, cudaDeviceSynchronize());
+  for (auto& kv : c->raw) cudaFree(kv.second.p);
+  c->raw.clear();
+  c->finalized = true;
+  return GITB200_OK;
+}
+
+int gitb200_tokens_per_frame(const gitb200_ctx* c) { return c ? c->T : 0; }
+int gitb200_logits_ld(const gitb200_ctx* c) { return c ? c->vocab_pad : 0; }
+
+int gitb200_reserve(gitb200_ctx* c, int max_clips, int max_frames, int max_rows_per_clip, int max_text_len) {
+  if (!c || max_clips < 1 || max_frames < 1 || max_rows_per_clip < 1 || max_text_len < 1) return fail(c, GITB200_ERR_INVALID, "bad reserve argument");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const gitb200_config& k = c->cfg;
+  const int F = (k.num_image_with_embedding > 0 && max_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : max_frames;
+  const int W = k.vit_width, H = k.hidden, G = k.resolution / k.patch;
+  const size_t rows = (size_t)max_clips * F * c->T;
+  ENSURE(c, c->patches, (size_t)max_clips * F * G * G * c->kpad);
+  ENSURE(c, c->x, rows * W);
+  ENSURE(c, c->lnb, rows * W);
+  ENSURE(c, c->qkv, rows * 3 * W);
+  ENSURE(c, c->attn, rows * W);
+  ENSURE(c, c->mlp, rows * 4 * W);
+  ENSURE(c, c->vf, rows * W);
+  ENSURE(c, c->hv, rows * H);
+  ENSURE(c, c->hvb, rows * H);
+  ENSURE(c, c->hvc, rows * H);
+  ENSURE(c, c->vattn, rows * H);
+  ENSURE(c, c->vmlp, rows * k.ffn);
+  c->kv.resize(k.dec_layers);
+  for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->kv[l], rows * 3 * H);
+  const int trows = max_clips * max_rows_per_clip;
+  TRY(ensure_text(c, trows, trows, max_text_len));
+  ENSURE(c, c->logits, (size_t)trows * c->vocab_pad);
+  return GITB200_OK;
+}
+
+int gitb200_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, float* vf_out, void* stream) {
+  if (!c || !frames || n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad encode argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(run_encode(c, frames, n_clips, n_frames, s));
+  if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
+  return GITB200_OK;
+}
+
+int gitb200_set_visual_features(gitb200_ctx* c, const float* vf, int n_clips, int nv, void* stream) {
+  if (!c || !vf || n_clips < 1 || nv < 1) return fail(c, GITB200_ERR_INVALID, "bad set_visual_features argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const int W = c->cfg.vit_width;
+  ENSURE(c, c->vf, (size_t)n_clips * nv * W);
+  CUDA_OK(c, cast_f32_to_bf16(vf, n_clips * nv, W, W, c->vf.p, W, n_clips * nv, W, (cudaStream_t)stream));
+  c->cur_clips = n_clips;
+  c->cur_nv = nv;
+  c->visual_pass_done = false;
+  return GITB200_OK;
+}
+
+int gitb200_decode(gitb200_ctx* c, const gitb200_search_params* sp, int32_t* tokens, float* logprobs, float* logits, void* stream) {
+  if (!c || !sp || !tokens || !logprobs) return fail(c, GITB200_ERR_INVALID, "bad decode argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  if (c->cur_clips <= 0) return fail(c, GITB200_ERR_STATE, "no visual features: call gitb200_encode or gitb200_set_visual_features first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  return run_decode(c, *sp, tokens, logprobs, logits, (cudaStream_t)stream);
+}
+
+int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, const gitb200_search_params* sp,
+                    int32_t* tokens, float* logprobs, float* logits, void* stream) {
+  int r = gitb200_encode(c, frames, n_clips, n_frames, nullptr, stream);
+  if (r) return r;
+  return gitb200_decode(c, sp, tokens, logprobs, logits, stream);
+}
+
+int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
+                         const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host) {
+  if (!c || !frames_host || !sp || !tokens_host || !logprobs_host || n_clips < 1 || n_frames < 1)
+    return fail(c, GITB200_ERR_INVALID, "bad caption_host argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
+  const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
+  const int per_clip_tok = sp->num_keep_best * sp->max_steps;
+  if (!c->copy_stream) {
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  // the legacy default stream would serialise with the copy stream; compute runs on a private one
+  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  cudaStream_t comp = c->comp_stream;
+  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
+  ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
+  ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
+  const int n_chunks = (n_clips + chunk_clips - 1) / chunk_clips;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int b = ch & 1;
+    const int c0 = ch * chunk_clips;
+    const int nc = (n_clips - c0) < chunk_clips ? (n_clips - c0) : chunk_clips;
+    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
+    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)c0 * clip_elems, (size_t)nc * clip_elems * sizeof(float),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
+    int r = gitb200_caption(c, c->stage[b].p, nc, n_frames, sp, c->out_tok.p + (size_t)c0 * per_clip_tok,
+                            c->out_lp.p + (size_t)c0 * sp->num_keep_best, nullptr, comp);
+    if (r) return r;
+    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+  }
+  CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
+  CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
+  CUDA_OK(c, cudaStreamSynchronize(comp));
+  return GITB200_OK;
+}
+
+int gitb200_forward_logits(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, const int32_t* tokens, int L,
+                           float* logits, float* hidden, float* vf_out, void* stream) {
+  if (!c || !tokens || !logits || L < 1) return fail(c, GITB200_ERR_INVALID, "bad forward_logits argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  if (L > c->cfg.max_positions) return fail(c, GITB200_ERR_INVALID, "caption length %d exceeds %d positions", L, c->cfg.max_positions);
+  CUDA_OK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (frames) {
+    if (n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad forward_logits argument");
+    TRY(run_encode(c, frames, n_clips, n_frames, s));
+  }
+  if (c->cur_clips <= 0) return fail(c, GITB200_ERR_STATE, "no visual features");
+  const int B = c->cur_clips, rows = B * L, W = c->cfg.vit_width;
+  if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, B * c->cur_nv, W, W, vf_out, W, s));
+  const bool want_full = hidden != nullptr;
+  if (!c->visual_pass_done || (want_full && !c->visual_pass_full) || hidden) TRY(run_visual_pass(c, want_full, hidden, L, s));
+  TRY(ensure_text(c, rows, B, L));
+  ENSURE(c, c->pos_arr, rows);
+  ENSURE(c, c->ntext_arr, rows);
+  CUDA_OK(c, fill_positions(c->pos_arr.p, c->ntext_arr.p, rows, L, s));
+  TextPass tp;
+  tp.n_clips = B; tp.rows_per_clip = L; tp.max_len = L;
+  tp.tokens = tokens; tp.positions = c->pos_arr.p; tp.pos_const = 0;
+  tp.n_text = c->ntext_arr.p; tp.n_text_const = 0; tp.anc = nullptr;
+  tp.slot_div = L; tp.n_slots = B; tp.slot_is_clip = 1;
+  tp.logits = logits; tp.hidden_out = hidden;
+  return run_text_pass(c, tp, s);
+}
+
+int gitb200_decode_begin(gitb200_ctx* c, int rows_per_clip, void* stream) {
+  if (!c || rows_per_clip < 1) return fail(c, GITB200_ERR_INVALID, "bad decode_begin argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!c->visual_pass_done) TRY(run_visual_pass(c, false, nullptr, 0, s));
+  const int rows = c->cur_clips * rows_per_clip, ml = c->cfg.max_positions < 64 ? c->cfg.max_positions : 64;
+  TRY(ensure_text(c, rows, rows, ml));
+  ENSURE(c, c->ibuf, (size_t)rows * ml * 2);
+  c->step_rows_per_clip = rows_per_clip;
+  c->anc_parity = 0;
+  c->step_anc_used = false;
+  return GITB200_OK;
+}
+
+int gitb200_decode_step(gitb200_ctx* c, const int32_t* tokens, int pos, float* logits, void* stream) {
+  if (!c || !tokens || !logits || pos < 0) return fail(c, GITB200_ERR_INVALID, "bad decode_step argument");
+  if (c->step_rows_per_clip < 1 || !c->visual_pass_done) return fail(c, GITB200_ERR_STATE, "call gitb200_decode_begin first");
+  const int ml = c->cfg.max_positions < 64 ? c->cfg.max_positions : 64;
+  if (pos >= ml) return fail(c, GITB200_ERR_INVALID, "step-wise decoding supports up to %d text positions", ml);
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const int rows = c->cur_clips * c->step_rows_per_clip;
+  TextPass tp;
+  tp.n_clips = c->cur_clips; tp.rows_per_clip = c->step_rows_per_clip; tp.max_len = ml;
+  tp.tokens = tokens; tp.positions = nullptr; tp.pos_const = pos; tp.n_text = nullptr; tp.n_text_const = pos + 1;
+  tp.anc = c->step_anc_used ? c->ibuf.p + (size_t)c->anc_parity * rows * ml : nullptr;
+  tp.slot_div = 1; tp.n_slots = rows; tp.slot_is_clip = 0; tp.logits = logits; tp.hidden_out = nullptr;
+  return run_text_pass(c, tp, (cudaStream_t)stream);
+}
+
+int gitb200_decode_reorder(gitb200_ctx* c, const int32_t* beam_idx, int pos, void* stream) {
+  if (!c || !beam_idx || pos < 0) return fail(c, GITB200_ERR_INVALID, "bad decode_reorder argument");
+  if (c->step_rows_per_clip < 1) return fail(c, GITB200_ERR_STATE, "call gitb200_decode_begin first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const int rows = c->cur_clips * c->step_rows_per_clip, ml = c->cfg.max_positions < 64 ? c->cfg.max_positions : 64;
+  int* a0 = c->ibuf.p + (size_t)c->anc_parity * rows * ml;
+  int* a1 = c->ibuf.p + (size_t)(c->anc_parity ^ 1) * rows * ml;
+  CUDA_OK(c, anc_reorder(c->step_anc_used ? a0 : nullptr, a1, beam_idx, rows, ml, pos, (cudaStream_t)stream));
+  c->anc_parity ^= 1;
+  c->step_anc_used = true;
+  return GITB200_OK;
+}
+
+// ---- single operators
+int gitb200_op_gemm(const void* a, const void* w, int M, int N, int K, const float* bias, const void* residual, int act,
+                    void* out_bf16, float* out_f32, int tile_n, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)a; g.lda = K; g.W = (const bf16*)w; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.residual = (const bf16*)residual; g.ldr = N; g.act = act; g.out = (bf16*)out_bf16; g.ldo = N; g.out_f32 = out_f32; g.ldo32 = N;
+  cudaError_t e = gemm_bf16(g, (cudaStream_t)stream, tile_n);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "gemm: %s [%s]", cudaGetErrorString(e), gemm_last_error());
+  return GITB200_OK;
+}
+
+int gitb200_op_layernorm(const void* x, int rows, int cols, const float* gamma, const float* beta, float eps, void* out, void* stream) {
+  LayerNormArgs a;
+  a.x = (const bf16*)x; a.ldx = cols; a.rows = rows; a.cols = cols; a.gamma = gamma; a.beta = beta; a.eps = eps; a.out = (bf16*)out; a.ldo = cols;
+  cudaError_t e = layernorm_bf16(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "layernorm: %s", cudaGetErrorString(e));
+  return GITB200_OK;
+}
+
+int gitb200_op_attention_groups(const void* qkv, void* out, int n_groups, int group_len, int heads, float scale, void* stream) {
+  cudaError_t e = attention_groups((const bf16*)qkv, 3 * heads * 64, (bf16*)out, heads * 64, n_groups, group_len, heads, scale, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "attention_groups: %s", cudaGetErrorString(e));
+  return GITB200_OK;
+}
+
+int gitb200_op_search(const float* logits, int ld, int vocab, int n_clips, int sos, int eos, const gitb200_search_params* sp,
+                      int32_t* tokens, float* logprobs, void* stream) {
+  if (!logits || !sp || !tokens || !logprobs || n_clips < 1) return fail(nullptr, GITB200_ERR_INVALID, "bad op_search argument");
+  gitb200_ctx tmp;  // scratch owner for the search buffers
+  cudaGetDevice(&tmp.device);
+  SearchState st;
+  int r = make_search_state(&tmp, n_clips, vocab, ld, sos, eos, *sp, &st);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  if (!r) {
+    const int rows = n_clips * sp->beam_size;
+    e = search_init(st, sos, s);
+    int parity = 0;
+    for (int t = 0; e == cudaSuccess && t + 1 < sp->max_steps; ++t) {
+      e = search_step(st, logits + (size_t)t * rows * ld, t + 1, parity, s);
+      parity ^= 1;
+    }
+    if (e == cudaSuccess) e = search_finalize(st, tokens, logprobs, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  if (tmp.ibuf.p) cudaFree(tmp.ibuf.p);
+  if (tmp.dbuf.p) cudaFree(tmp.dbuf.p);
+  if (tmp.fbuf.p) cudaFree(tmp.fbuf.p);
+  if (r) return fail(nullptr, r, "%s", tmp.err.c_str());
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "search: %s", cudaGetErrorString(e));
+  return GITB200_OK;
+}
+
+}  // extern "C"

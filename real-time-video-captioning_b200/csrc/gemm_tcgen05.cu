@@ -208,7 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint4* r4 = reinterpret_cast<const uint4*>(ep.residual + (size_t)rrow * ep.ldr + col);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(r4 + i);
+              const uint4 u = r4[i];  // plain load: `out` may alias `residual` (in-place residual update)
               const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
               f[8 * i + 0] += a0.x;
               f[8 * i + 1] += a0.y;
@@ -354,6 +354,7 @@ cudaError_t launch(const GemmArgs& a, const Epilogue& ep, cudaStream_t stream) {
   const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, a.M, a.N, a.K, ep);
+  note_launch();
   return cudaGetLastError();
 }
 

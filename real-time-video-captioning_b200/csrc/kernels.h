@@ -9,6 +9,9 @@ typedef __nv_bfloat16 bf16;
 
 enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
 
+// every host wrapper below reports the kernels it enqueues (gitb200_launch_count)
+void note_launch(int n = 1);
+
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias) + residual, bf16 operands, fp32 accumulation in TMEM.
 struct GemmArgs {
   const bf16* A = nullptr;  // row-major [M, K], leading dimension lda (elements, multiple of 8)
@@ -70,8 +73,10 @@ struct TextAttnArgs {
   int heads = 0;
   const bf16* vis_kv = nullptr;  // this layer's visual K|V: [n_clips * Nv, ld_vis], K at col k_off, V at col v_off
   int ld_vis = 0, k_off = 0, v_off = 0, Nv = 0;
-  const bf16* txt_kv = nullptr;  // this layer's text K|V: [max_pos][n_rows][2*H*64]  (K then V)
-  const int* anc = nullptr;      // [n_rows, anc_ld]: slot of row r's ancestor at text position s (null = r)
+  const bf16* txt_kv = nullptr;  // this layer's text K|V plane: [max_pos][txt_slots][2*H*64]  (K then V)
+  int txt_slots = 0;             // slots per position: n_rows (decode: one per beam row) or n_clips (teacher forcing)
+  int text_slot_is_clip = 0;     // 1: every text key of row r lives in slot (r / rows_per_clip)  (teacher forcing)
+  const int* anc = nullptr;      // [n_rows, anc_ld]: slot of row r's ancestor at text position s < n_text-1 (null = r)
   int anc_ld = 0;
   const int* n_text = nullptr;   // [n_rows] number of visible text keys (pos+1); null = n_text_const
   int n_text_const = 0;
@@ -82,14 +87,21 @@ struct TextAttnArgs {
   int splits = 1;
 };
 cudaError_t text_attention(const TextAttnArgs& a, cudaStream_t stream);
+size_t text_attention_workspace_floats(int n_rows, int heads, int splits);
 
-// words[tok] + positions[pos] -> LN(eps) -> out bf16
-cudaError_t embed_text(const int* tokens, const int* positions, int n_rows, const bf16* words, const bf16* pos_table,
-                       const float* gamma, const float* beta, float eps, int width, bf16* out, cudaStream_t stream);
+// words[tok] + positions[pos] -> LN(eps) -> out bf16   (fp32 tables; positions == nullptr -> pos_const)
+cudaError_t embed_text(const int* tokens, const int* positions, int pos_const, int n_rows, const float* words,
+                       const float* pos_table, const float* gamma, const float* beta, float eps, int width, bf16* out,
+                       cudaStream_t stream);
 
-// Scatter this step's K|V (columns [H*64, 3*H*64) of qkv) into the text KV plane at position `pos[r]`.
-cudaError_t store_text_kv(const bf16* qkv, int ld_qkv, int n_rows, int kv_width, const int* pos, int pos_const,
-                          bf16* txt_kv, cudaStream_t stream);
+// Scatter this step's K|V (columns [q_width, q_width + kv_width) of qkv) into the text KV plane:
+// txt_kv[(pos(r) * n_slots + r / slot_div) * kv_width + c];  pos(r) = pos ? pos[r] : pos_const.
+cudaError_t store_text_kv(const bf16* qkv, int ld_qkv, int n_rows, int kv_width, int q_width, const int* pos,
+                          int pos_const, int slot_div, int n_slots, bf16* txt_kv, cudaStream_t stream);
+
+cudaError_t cast_f32_to_bf16(const float* src, int rows, int cols, int lds, bf16* dst, int ldd, int dst_rows,
+                             int dst_cols, cudaStream_t stream);
+cudaError_t cast_bf16_to_f32(const bf16* src, int rows, int cols, int lds, float* dst, int ldd, cudaStream_t stream);
 
 // Beam / greedy search state, all device resident (semantics: reference model.py:479-678).
 struct SearchState {
@@ -103,16 +115,23 @@ struct SearchState {
   int* anc_tmp;
   int* cur_tok;       // [n_rows] token fed to the next step
   // hypotheses: per clip up to n_keep (+1 scratch)
-  float* hyp_score;   // [n_clips, n_keep + 1]
+  double* hyp_score;  // [n_clips, n_keep + 1]  (Python float arithmetic in the reference -> double)
   int* hyp_len;       // [n_clips, n_keep + 1]
   int* hyp_tok;       // [n_clips, n_keep + 1, max_len]
   int* hyp_count;     // [n_clips]
-  float* worst;       // [n_clips]
+  double* worst;      // [n_clips]
   int reorder_cache;  // 0 = reference behaviour (cache rows never re-indexed), 1 = re-index by parent
 };
 // One search step: log-softmax over logits [n_rows, ldl] (fp32), + beam score, top-(cand) per clip,
 // then the reference's candidate walk; cur_len = current caption length before this step.
-cudaError_t search_step(const SearchState& s, const float* logits, int cur_len, cudaStream_t stream);
+// parity: which of the (tokens, tokens_tmp) / (anc, anc_tmp) pairs currently holds the live state
+// (0: tokens/anc are read and *_tmp written; 1: the reverse).  The caller flips it after every step.
+cudaError_t search_step(const SearchState& s, const float* logits, int cur_len, int parity, cudaStream_t stream);
 cudaError_t search_init(const SearchState& s, int sos, cudaStream_t stream);
 // decoded [n_clips, n_keep, max_len] (eos padded), logprobs [n_clips, n_keep]
 cudaError_t search_finalize(const SearchState& s, int* decoded, float* logprobs, cudaStream_t stream);
+
+// pos[r] = r % L, n_text[r] = r % L + 1 (teacher-forced text rows)
+cudaError_t fill_positions(int* pos, int* n_text, int rows, int L, cudaStream_t stream);
+// Step-wise decoding cache re-index: out[r][s] = in ? in[beam_idx[r]][s] : beam_idx[r] for s < pos; out[r][pos] = beam_idx[r].
+cudaError_t anc_reorder(const int* anc_in, int* anc_out, const int* beam_idx, int rows, int ld, int pos, cudaStream_t stream);

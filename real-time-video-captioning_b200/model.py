@@ -1,0 +1,594 @@
+"""Drop-in Python surface of the reference's GIT captioning path (/root/reference/src/models/model.py).
+
+Same names, constructor arguments, return structures and error behaviour as the reference classes
+(`get_git_model` :681, `GenerativeImageTextModel` :343, `GeneratorWithBeamSearchV2` :465,
+`GenerativeImageTextTeacher` :721), but every tensor operation of the path runs in libgitb200.so
+(hand-written sm_100a kernels) through the C ABI of include/gitb200.h.  The nn.Module tree below only
+*holds* the parameters under the upstream state-dict key names so that ``load_state_dict``,
+``.parameters()``, ``.eval()`` and ``.to()`` behave as callers expect; none of these modules has a torch
+forward, and there is no CPU path: without a B200 and the built library every forward raises.
+
+Differences from the reference, all deliberate:
+  * clips are batched: one call encodes and captions every clip of ``x`` (the reference loops clip by clip,
+    model.py:752-759, :765-770);
+  * the decoder keeps a true K/V cache (the upstream cache stores layer inputs and re-projects K,V every
+    step) and visual K/V are shared by all beams of a clip;
+  * the search loop and its bookkeeping run on the device; ``logits_dict`` is materialised on the host only
+    when it is read.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import VIT_CONFIGS, Engine, SearchConfig, make_config
+
+VOCAB_SIZE = 30522  # model.py:689
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter containers (upstream module tree; no torch forward on purpose)
+# ----------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("gitb200 parameter containers have no torch forward; call the model, it runs on the "
+                           "CUDA library")
+
+
+class _Affine(_Holder):
+    """weight (+bias) container: Linear [out,in], LayerNorm [n], Conv2d [out,in,k,k]."""
+
+    def __init__(self, w_shape: Sequence[int], bias: bool = True, ln: bool = False, std: float = 0.02):
+        super().__init__()
+        w = torch.ones(*w_shape) if ln else torch.randn(*w_shape) * std
+        self.weight = nn.Parameter(w)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(w_shape[0]))
+
+
+class _MHA(_Holder):
+    def __init__(self, width: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.randn(3 * width, width) * width ** -0.5)
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * width))
+        self.out_proj = _Affine((width, width), std=width ** -0.5)
+
+
+class _MLP(_Holder):
+    def __init__(self, width: int):
+        super().__init__()
+        self.c_fc = _Affine((4 * width, width), std=width ** -0.5)
+        self.c_proj = _Affine((width, 4 * width), std=(4 * width) ** -0.5)
+
+
+class ResidualAttentionBlock(_Holder):
+    """image_encoder.transformer.resblocks[i] (attested at model.py:847)."""
+
+    def __init__(self, width: int):
+        super().__init__()
+        self.ln_1 = _Affine((width,), ln=True)
+        self.attn = _MHA(width)
+        self.ln_2 = _Affine((width,), ln=True)
+        self.mlp = _MLP(width)
+
+
+class _Transformer(_Holder):
+    def __init__(self, width: int, layers: int):
+        super().__init__()
+        self.resblocks = nn.ModuleList([ResidualAttentionBlock(width) for _ in range(layers)])
+
+
+class CLIPVisionTower(_Holder):
+    """Parameters of upstream get_image_encoder(image_encoder_type, input_resolution) (model.py:682-685)."""
+
+    def __init__(self, image_encoder_type: str = "CLIPViT_B_16", input_resolution: int = 224):
+        super().__init__()
+        v = VIT_CONFIGS[image_encoder_type]
+        w, p = v["width"], v["patch"]
+        self.image_encoder_type, self.input_resolution = image_encoder_type, input_resolution
+        self.conv1 = _Affine((w, 3, p, p), bias=False, std=(3 * p * p) ** -0.5)
+        self.class_embedding = nn.Parameter(torch.randn(w) * w ** -0.5)
+        self.positional_embedding = nn.Parameter(torch.randn((input_resolution // p) ** 2 + 1, w) * w ** -0.5)
+        self.ln_pre = _Affine((w,), ln=True)
+        self.transformer = _Transformer(w, v["layers"])
+        self.ln_post = _Affine((w,), ln=True)
+
+
+class _SelfAttention(_Holder):
+    def __init__(self, h):
+        super().__init__()
+        self.query, self.key, self.value = _Affine((h, h)), _Affine((h, h)), _Affine((h, h))
+
+
+class _AttnOutput(_Holder):
+    def __init__(self, h_in, h):
+        super().__init__()
+        self.dense = _Affine((h, h_in))
+        self.LayerNorm = _Affine((h,), ln=True)
+
+
+class _Attention(_Holder):
+    def __init__(self, h):
+        super().__init__()
+        self.self = _SelfAttention(h)
+        self.output = _AttnOutput(h, h)
+
+
+class _Intermediate(_Holder):
+    def __init__(self, h, f):
+        super().__init__()
+        self.dense = _Affine((f, h))
+
+
+class BertLayer(_Holder):
+    """textual.transformer.encoder.layer[i] (``.output`` attested at model.py:857)."""
+
+    def __init__(self, h, f):
+        super().__init__()
+        self.attention = _Attention(h)
+        self.intermediate = _Intermediate(h, f)
+        self.output = _AttnOutput(f, h)
+
+
+class _BertEncoder(_Holder):
+    def __init__(self, h, f, layers):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(h, f) for _ in range(layers)])
+
+
+class _BertEncoderAsDecoder(_Holder):
+    def __init__(self, h, f, layers):
+        super().__init__()
+        self.encoder = _BertEncoder(h, f, layers)
+
+
+class _Embedding(_Holder):
+    def __init__(self, vocab, h, max_len):
+        super().__init__()
+        self.words = _Affine((vocab, h), bias=False)
+        self.positions = _Affine((max_len, h), bias=False)
+        self.layer_norm = _Affine((h,), ln=True)
+
+
+class TransformerDecoderTextualHead(_Holder):
+    """Parameters of the upstream text head built at model.py:687-700 (argument names kept)."""
+
+    def __init__(self, visual_feature_size=768, vocab_size=VOCAB_SIZE, hidden_size=768, num_layers=6, attention_heads=12,
+                 feedforward_size=3072, max_caption_length=1024, mask_future_positions=True, padding_idx=0,
+                 decoder_type="bert_en", output_hidden_states=True, visual_projection_type="linearLn"):
+        super().__init__()
+        if decoder_type != "bert_en" or visual_projection_type != "linearLn" or not mask_future_positions:
+            raise NotImplementedError("only decoder_type='bert_en', visual_projection_type='linearLn', causal text")
+        self.visual_feature_size, self.vocab_size, self.hidden_size = visual_feature_size, vocab_size, hidden_size
+        self.num_layers, self.attention_heads, self.feedforward_size = num_layers, attention_heads, feedforward_size
+        self.max_caption_length, self.output_hidden_states = max_caption_length, output_hidden_states
+        self.visual_projection = nn.ModuleList([_Affine((hidden_size, visual_feature_size), std=visual_feature_size ** -0.5),
+                                                _Affine((hidden_size,), ln=True)])
+        self.embedding = _Embedding(vocab_size, hidden_size, max_caption_length)
+        self.transformer = _BertEncoderAsDecoder(hidden_size, feedforward_size, num_layers)
+        self.output = _Affine((vocab_size, hidden_size))
+        self.output.weight = self.embedding.words.weight  # upstream ties the vocabulary head to the word embedding
+
+
+# ----------------------------------------------------------------------------------------------
+# search
+# ----------------------------------------------------------------------------------------------
+class BeamHypotheses:
+    """Upstream BeamHypotheses (constructed at model.py:503): n-best list with length-normalised scores."""
+
+    def __init__(self, n_hyp, max_length, length_penalty, early_stopping):
+        self.max_length = max_length - 1
+        self.length_penalty, self.early_stopping, self.n_hyp = length_penalty, early_stopping, n_hyp
+        self.hyp, self.worst_score = [], 1e9
+
+    def __len__(self):
+        return len(self.hyp)
+
+    def add(self, hyp, sum_logprobs):
+        score = sum_logprobs / len(hyp) ** self.length_penalty
+        if len(self) < self.n_hyp or score > self.worst_score:
+            self.hyp.append((score, hyp))
+            if len(self) > self.n_hyp:
+                ranked = sorted((s, i) for i, (s, _) in enumerate(self.hyp))
+                del self.hyp[ranked[0][1]]
+                self.worst_score = ranked[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs):
+        if len(self) < self.n_hyp:
+            return False
+        if self.early_stopping:
+            return True
+        return self.worst_score >= best_sum_logprobs / self.max_length ** self.length_penalty
+
+
+class LazyLogits(Sequence):
+    """``logits_dict`` of the reference (model.py:521: a list over steps of a list over beam rows of
+    np.ndarray[V]) backed by the device buffer the decode kernels wrote; copied to the host on first read."""
+
+    def __init__(self, dev: torch.Tensor, vocab: int):
+        self._dev, self._vocab, self._host = dev, vocab, None
+
+    def device_tensor(self) -> torch.Tensor:
+        """[steps, rows, V] view on the device (no copy)."""
+        return self._dev[:, :, : self._vocab]
+
+    def _materialise(self):
+        if self._host is None:
+            self._host = self.device_tensor().cpu().numpy()
+        return self._host
+
+    def __len__(self):
+        return self._dev.shape[0]
+
+    def __getitem__(self, i):
+        h = self._materialise()
+        if isinstance(i, slice):
+            return [list(step) for step in h[i]]
+        return list(h[i])
+
+
+class GeneratorWithBeamSearchV2:
+    """model.py:465-678.  ``search`` keeps the reference's generic contract -- any ``step`` callable mapping
+    input_ids [B*beams, len] to scores [B*beams, V] -- with the control flow on the host; when the model
+    recognises its own decoder it bypasses this loop for the fused device-side search (same semantics)."""
+
+    def __init__(self, eos_index, max_steps, beam_size, length_penalty, per_node_beam_size=2, repetition_penalty=1.0,
+                 temperature=1.0):
+        self._eos_index, self.max_steps, self.beam_size = eos_index, max_steps, beam_size
+        self.length_penalty, self.per_node_beam_size = length_penalty, per_node_beam_size
+        self.repetition_penalty, self.temperature = repetition_penalty, temperature
+
+    def search_config(self, num_keep_best=1, reorder_cache=False) -> SearchConfig:
+        return SearchConfig(self.beam_size, self.max_steps, self.length_penalty, self.per_node_beam_size, num_keep_best,
+                            reorder_cache)
+
+    def search(self, input_ids, step: Callable, num_keep_best=1, do_sample=False, top_k=None, top_p=None,
+               num_return_sequences=1):
+        if do_sample:
+            raise NotImplementedError("sampling branch (model.py:532-554) is not used by the reference path")
+        if num_return_sequences != 1:
+            input_ids = input_ids[:, None, :].expand(input_ids.shape[0], num_return_sequences, input_ids.shape[1])
+            input_ids = input_ids.reshape(-1, input_ids.shape[-1])
+        batch_size, cur_len = input_ids.shape
+        nb, eos, max_length = self.beam_size, self._eos_index, self.max_steps
+        input_ids = input_ids.unsqueeze(1).expand(batch_size, nb, cur_len).contiguous().view(batch_size * nb, cur_len)
+        hyps = [BeamHypotheses(num_keep_best, max_length, self.length_penalty, early_stopping=False) for _ in range(batch_size)]
+        beam_scores = torch.zeros((batch_size, nb), dtype=torch.float, device=input_ids.device)
+        beam_scores[:, 1:] = -1e9
+        beam_scores = beam_scores.view(-1)
+        done = [False] * batch_size
+        saved_logits = []
+        while cur_len < max_length:
+            scores = step(input_ids)
+            vocab = scores.shape[-1]
+            saved_logits.append([r.detach().cpu().numpy() for r in scores])
+            if self.repetition_penalty != 1.0:
+                for i in range(batch_size * nb):
+                    for tok in set(input_ids[i].tolist()):
+                        scores[i, tok] = scores[i, tok] * self.repetition_penalty if scores[i, tok] < 0 else scores[i, tok] / self.repetition_penalty
+            lp = torch.log_softmax(scores, dim=-1) + beam_scores[:, None]
+            next_scores, next_words = torch.topk(lp.view(batch_size, nb * vocab), self.per_node_beam_size * nb, dim=1,
+                                                 largest=True, sorted=True)
+            ns_host, nw_host = next_scores.tolist(), next_words.tolist()  # one transfer per step, not one per candidate
+            nxt = []
+            for b in range(batch_size):
+                done[b] = done[b] or hyps[b].is_done(max(ns_host[b]))
+                if done[b]:
+                    nxt.extend([(0, eos, 0)] * nb)
+                    continue
+                beam = []
+                for idx, score in zip(nw_host[b], ns_host[b]):
+                    beam_id, word = idx // vocab, idx % vocab
+                    if word == eos or cur_len + 1 == max_length:
+                        hyps[b].add(input_ids[b * nb + beam_id, :cur_len].clone(), score)
+                    else:
+                        beam.append((score, word, b * nb + beam_id))
+                    if len(beam) == nb:
+                        break
+                assert len(beam) == (0 if cur_len + 1 == max_length else nb)
+                nxt.extend(beam if beam else [(0, eos, 0)] * nb)
+            beam_scores = beam_scores.new_tensor([x[0] for x in nxt])
+            beam_words = input_ids.new_tensor([x[1] for x in nxt])
+            beam_idx = input_ids.new_tensor([x[2] for x in nxt])
+            input_ids = torch.cat([input_ids[beam_idx, :], beam_words.unsqueeze(1)], dim=-1)
+            cur_len += 1
+            if all(done):
+                break
+        tgt_len = torch.ones(batch_size, num_keep_best, dtype=torch.long)
+        logprobs = torch.full((batch_size, num_keep_best), -1e5, dtype=torch.float, device=input_ids.device)
+        decoded = input_ids.new_full((batch_size, num_keep_best, max_length), eos)
+        for i, h in enumerate(hyps):
+            order = torch.topk(torch.tensor([x[0] for x in h.hyp]), min(num_keep_best, len(h.hyp)), largest=True)[1]
+            for j, hi in enumerate(order.tolist()):
+                conf, best = h.hyp[hi]
+                logprobs[i, j] = conf
+                tgt_len[i, j] = len(best) + 1
+                decoded[i, j, : len(best)] = best
+                decoded[i, j, len(best)] = eos
+        if num_keep_best == 1:
+            decoded = decoded.squeeze(dim=1)
+        return decoded, logprobs, saved_logits
+
+
+# ----------------------------------------------------------------------------------------------
+# the model
+# ----------------------------------------------------------------------------------------------
+class GenerativeImageTextModel(nn.Module):
+    """model.py:343-462 (subclass of upstream CaptioningModel), executing on a gitb200 Engine."""
+
+    def __init__(self, image_encoder, text_decoder, decoder, tokenizer, param):
+        super().__init__()
+        self.image_encoder = image_encoder
+        self.textual = text_decoder
+        self.decoder = decoder
+        self.tokenizer = tokenizer
+        self.param = dict(param)
+        self.sos_index = tokenizer.cls_token_id      # model.py:363
+        self.eos_index = tokenizer.sep_token_id      # model.py:364
+        self.use_history_for_infer = True            # model.py:366
+        self.num_image_with_embedding = param.get("num_image_with_embedding")  # model.py:368
+        self.pooling_images = None
+        self.prev_encoded_layers = None
+        width = VIT_CONFIGS[image_encoder.image_encoder_type]["width"]
+        self.img_temperal_embedding = nn.ParameterList(
+            [nn.Parameter(torch.zeros(1, 1, width)) for _ in range(self.num_image_with_embedding or 0)])
+        self._engine: Optional[Engine] = None
+        self._engine_stale = True
+        self._vf_token = None          # visual-feature tensor currently resident in the engine
+        self._step_pos = 0
+        self.cache_reorder = "reference"  # or "correct" 
+
+    # ---- engine plumbing
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        sd = dict(state_dict)
+        if "textual.output.weight" not in sd and "textual.embedding.words.weight" in sd:
+            sd["textual.output.weight"] = sd["textual.embedding.words.weight"]
+        if "textual.output.weight" in sd and "textual.embedding.words.weight" in sd and \
+                sd["textual.output.weight"] is not sd["textual.embedding.words.weight"] and \
+                not torch.equal(sd["textual.output.weight"], sd["textual.embedding.words.weight"]):
+            # untied head (not produced by upstream, used by the parity tests): break the tie before copying
+            self.textual.output.weight = nn.Parameter(torch.empty_like(self.textual.embedding.words.weight))
+        sd.pop("image_encoder.proj", None)  # present in CLIP checkpoints, unused with output_grid=True
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self._engine_stale = True
+        return out
+
+    def _apply(self, fn, *a, **k):
+        self._engine_stale = True
+        return super()._apply(fn, *a, **k)
+
+    def engine(self) -> Engine:
+        if self._engine is None or self._engine_stale:
+            p = next(self.parameters())
+            if not p.is_cuda:
+                raise RuntimeError("GenerativeImageTextModel runs only on a CUDA device (B200): call .to('cuda') first; "
+                                   "there is no CPU path")
+            if self._engine is None or self._engine.device != p.device:
+                cfg = make_config(self.param, self.sos_index, self.eos_index, vocab=self.textual.vocab_size,
+                                  hidden=self.textual.hidden_size, layers=self.textual.num_layers,
+                                  heads=self.textual.attention_heads, ffn=self.textual.feedforward_size,
+                                  max_positions=self.textual.max_caption_length)
+                self._engine = Engine(cfg, p.device.index or 0)
+            else:
+                cfg = self._engine.cfg
+                self._engine.close()
+                self._engine = Engine(cfg, p.device.index or 0)
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_stale = False
+            self._vf_token = None
+        return self._engine
+
+    @staticmethod
+    def _stack_frames(images) -> torch.Tensor:
+        """batch['image']: list of F tensors [B,3,H,W] (the reference passes B == 1) -> [B,F,3,H,W]."""
+        if not isinstance(images, (list, tuple)):
+            raise NotImplementedError("single-image input (no temporal embedding) is not part of the clip path")
+        return torch.stack([im if im.dim() == 4 else im.unsqueeze(0) for im in images], dim=1).float()
+
+    # ---- forward paths
+    @torch.no_grad()
+    def forward_one_custom(self, batch, return_info=False):
+        """model.py:371-424: (logits [B,L,V], visual_features [B,Nv,Dv], hidden_states [7,Nv+L,H] for B == 1)."""
+        if "context" in batch:
+            raise NotImplementedError("'context' inputs are not used by the reference path")
+        has_image = "image" in batch
+        assert has_image, "text-only forward is not part of the captioning path"
+        if self.pooling_images is not None:
+            raise NotImplementedError
+        eng = self.engine()
+        frames = self._stack_frames(batch["image"]).to(eng.device)
+        tokens = batch["caption_tokens"]
+        logits, vf, hidden = eng.forward_logits(frames, tokens, want_hidden=True, want_features=True)
+        self._vf_token = None
+        hidden_states = hidden[0] if hidden.shape[0] == 1 else hidden  # reference squeezes the batch dim (B == 1)
+        return logits, vf, hidden_states
+
+    def forward(self, batch):
+        """Eval-mode CaptioningModel.forward (model.py:768): encode the clip(s), then ``infer``."""
+        if self.training:
+            raise NotImplementedError("the GIT teacher is frozen (model.py:741-745); training forward is out of scope")
+        with torch.no_grad():
+            eng = self.engine()
+            frames = self._stack_frames(batch["image"]).to(eng.device)
+            vf = eng.encode(frames, want_features=True)
+            self._vf_token = vf
+            return self.infer(batch, vf, None)
+
+    def decoding_step(self, visual_features, visual_features_valid, bi_valid_mask_caption, partial_captions):
+        """Upstream CaptioningModel.decoding_step with use_history_for_infer: scores of the last position."""
+        eng = self.engine()
+        B = visual_features.shape[0]
+        rows = partial_captions.shape[0]
+        if self.prev_encoded_layers is None:
+            if self._vf_token is not visual_features:
+                eng.set_visual_features(visual_features.to(eng.device))
+                self._vf_token = visual_features
+            eng.decode_begin(rows // B)
+            for p in range(partial_captions.shape[1] - 1):  # prefix tokens fill the cache
+                eng.decode_step(partial_captions[:, p], p)
+            self.prev_encoded_layers = ("gitb200-kv-cache", rows)
+        pos = partial_captions.shape[1] - 1
+        return eng.decode_step(partial_captions[:, pos], pos).float()
+
+    def infer(self, batch, visual_features, visual_features_valid, search_param=None):
+        """model.py:426-462."""
+        batch_size = visual_features.size(0)
+        search_param = dict(search_param or {})
+        eng = self.engine()
+        fast = (isinstance(self.decoder, GeneratorWithBeamSearchV2) and "prefix" not in batch
+                and not search_param.get("do_sample", False) and search_param.get("num_return_sequences", 1) == 1
+                and self.decoder.repetition_penalty == 1.0 and visual_features_valid is None)
+        self.prev_encoded_layers = None
+        if fast:
+            if self._vf_token is not visual_features:
+                eng.set_visual_features(visual_features.to(eng.device))
+                self._vf_token = visual_features
+            sc = self.decoder.search_config(search_param.get("num_keep_best", 1), self.cache_reorder == "correct")
+            tokens, logprobs, logits = eng.decode(batch_size, sc, save_logits=True)
+            predicted = tokens.long()
+            if sc.num_keep_best == 1:
+                predicted = predicted.squeeze(1)
+            logits_dict = LazyLogits(logits, eng.cfg.vocab)
+        else:
+            if "prefix" not in batch:
+                start = torch.full((batch_size, 1), self.sos_index, dtype=torch.long, device=eng.device)
+            else:
+                assert len(batch["prefix"]) == 1, "not supported"
+                start = batch["prefix"].long().to(eng.device)
+            step = functools.partial(self.decoding_step, visual_features, visual_features_valid,
+                                     batch.get("bi_valid_mask_caption"))
+            predicted, logprobs, logits_dict = self.decoder.search(start, step, **search_param)
+            if "prefix" in batch:
+                predicted = predicted[:, start.shape[1]:]
+        return {"predictions": predicted, "logprobs": logprobs, "logits_dict": logits_dict,
+                "visual_features": visual_features}
+
+
+def get_git_model(tokenizer, param):
+    """model.py:681-718 (random-initialised parameters; load a checkpoint with load_state_dict)."""
+    image_encoder = CLIPVisionTower(param.get("image_encoder_type", "CLIPViT_B_16"),
+                                    input_resolution=param.get("test_crop_size", 224))
+    text_decoder = TransformerDecoderTextualHead(
+        visual_feature_size=param.get("visual_feature_size", 768), vocab_size=VOCAB_SIZE, hidden_size=768, num_layers=6,
+        attention_heads=12, feedforward_size=768 * 4, max_caption_length=1024, mask_future_positions=True, padding_idx=0,
+        decoder_type="bert_en", output_hidden_states=True, visual_projection_type="linearLn")
+    decoder = GeneratorWithBeamSearchV2(eos_index=tokenizer.sep_token_id, max_steps=15, beam_size=4, length_penalty=0.6)
+    return GenerativeImageTextModel(image_encoder, text_decoder, decoder=decoder, tokenizer=tokenizer, param=param)
+
+
+# ----------------------------------------------------------------------------------------------
+# teacher wrapper
+# ----------------------------------------------------------------------------------------------
+class SyntheticTokenizer:
+    """Stand-in for BertTokenizer('bert-base-uncased') when its vocabulary file is not available (offline):
+    same special ids (CLS 101, SEP 102, PAD 0), ``decode`` renders token ids as words ``t<id>``."""
+    cls_token_id, sep_token_id, pad_token_id = 101, 102, 0
+    vocab_size = VOCAB_SIZE
+
+    def decode(self, ids, skip_special_tokens=True):
+        special = {self.cls_token_id, self.sep_token_id, self.pad_token_id}
+        return " ".join(f"t{int(i)}" for i in ids if not (skip_special_tokens and int(i) in special))
+
+
+def _load_tokenizer():
+    try:
+        from transformers import BertTokenizer
+        tok = BertTokenizer.from_pretrained("bert-base-uncased", do_lower_case=True)
+        if tok.cls_token_id == 101 and tok.sep_token_id == 102 and len(tok) >= VOCAB_SIZE:
+            return tok
+    except Exception:
+        pass
+    return SyntheticTokenizer()  # offline images return a 5-token stub vocabulary
+
+
+class GenerativeImageTextTeacher(nn.Module):
+    """model.py:721-793.  ``forward`` / ``forward_output_logits`` keep the reference's per-clip return
+    structures but run all clips of ``x`` as one batch on the GPU."""
+
+    def __init__(self, param_path: Optional[str] = None, pretrained_weights: Optional[str] = None, *, param: Optional[dict] = None,
+                 tokenizer=None, state_dict=None, device="cuda"):
+        super().__init__()
+        self.tokenizer = tokenizer or _load_tokenizer()
+        if param is None:
+            import yaml
+            with open(param_path) as fh:
+                param = yaml.safe_load(fh)
+        self.param = param
+        self.model = get_git_model(self.tokenizer, self.param)
+        if pretrained_weights is not None:
+            ckpt = torch.load(pretrained_weights, map_location="cpu")["model"]      # model.py:736-737
+            self.model.load_state_dict(ckpt, strict=False)                           # upstream loader is tolerant
+        elif state_dict is not None:
+            self.model.load_state_dict(state_dict, strict=False)
+        for p in self.model.parameters():                                            # model.py:741-742
+            p.requires_grad = False
+        self.model.eval()                                                            # model.py:745
+        self.model.to(device)
+
+    @classmethod
+    def from_random_init(cls, param: dict, state_dict=None, device="cuda", tokenizer=None):
+        """Benchmark / parity constructor: no checkpoint file, no YAML."""
+        return cls(param=param, state_dict=state_dict, device=device, tokenizer=tokenizer or SyntheticTokenizer())
+
+    @torch.no_grad()
+    def forward_output_logits(self, x, y):
+        """model.py:747-760: lists (one entry per clip) of logits [1,L,V], visual features [1,Nv,Dv],
+        hidden states [7,Nv+L,H]."""
+        eng = self.model.engine()
+        frames = x.to(eng.device).float()
+        logits, vf, hidden = eng.forward_logits(frames, y, want_hidden=True, want_features=True)
+        n = frames.shape[0]
+        return [logits[i:i + 1] for i in range(n)], [vf[i:i + 1] for i in range(n)], [hidden[i] for i in range(n)]
+
+    @torch.no_grad()
+    def forward(self, x):
+        """model.py:762-793: one result dict per clip with predictions / logprobs / logits_dict / visual_features /
+        output / cap."""
+        m = self.model
+        eng = m.engine()
+        frames = x.to(eng.device).float()
+        n = frames.shape[0]
+        nb = m.decoder.beam_size
+        res = m({"image": [frames[:, f] for f in range(frames.shape[1])]})
+        all_logits = res["logits_dict"].device_tensor()                   # [steps, n*nb, V]
+        out = []
+        for i in range(n):
+            pred = res["predictions"][i:i + 1]
+            cap = self.tokenizer.decode(pred[0].tolist(), skip_special_tokens=True)                # :771
+            k = min(len(cap.split(" ")), all_logits.shape[0])                                       # :772
+            dist = all_logits[:k, i * nb:(i + 1) * nb]                                              # :776  [k, nb, V]
+            words = pred[0, 1:k + 1].to(dist.device)                                                # :780
+            idx = torch.gather(dist, 2, words[:, None, None].expand(-1, nb, -1)).squeeze(-1).argmax(dim=1)   # :784
+            picked = torch.gather(dist, 1, idx[:, None, None].expand(-1, -1, dist.shape[-1])).squeeze(1)[None]  # :787
+            out.append({"predictions": pred, "logprobs": res["logprobs"][i:i + 1],
+                        "logits_dict": LazyLogits(res["logits_dict"]._dev[:, i * nb:(i + 1) * nb], eng.cfg.vocab),
+                        "visual_features": res["visual_features"][i:i + 1], "output": picked, "cap": cap})
+        return out
+
+    # ---- the generate facade the reference's scripts call on their model (inference.py:51, real_time_inference.py:58)
+    @torch.no_grad()
+    def greedy_decode(self, src, max_len: int):
+        """[B,F,3,H,W] -> LongTensor [B, <= max_len+1] starting with CLS (StudentCandidateV1.greedy_decode contract,
+        model.py:156-187): beam 1 over the GIT decoder."""
+        return self._generate(src, max_len, 1)
+
+    @torch.no_grad()
+    def beam_search(self, src, max_len: int, k: int = 4):
+        return self._generate(src, max_len, k)
+
+    def _generate(self, src, max_len, k):
+        eng = self.model.engine()
+        frames = src.to(eng.device).float()
+        eng.encode(frames, want_features=False)
+        self.model._vf_token = None
+        sc = SearchConfig(beam_size=k, max_steps=max_len + 1, length_penalty=self.model.decoder.length_penalty,
+                          per_node_beam_size=self.model.decoder.per_node_beam_size, num_keep_best=1,
+                          reorder_cache=self.model.cache_reorder == "correct")
+        tokens, _, _ = eng.decode(frames.shape[0], sc, save_logits=False)
+        return tokens[:, 0].long()
