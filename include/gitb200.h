@@ -135,6 +135,11 @@ int gitb200_op_attention_groups(const void* qkv_dev, void* out_dev, int n_groups
 int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, int sos, int eos,
                       const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, void* stream);
 
+/* Per-launch timing of the tcgen05 GEMM kernel with CUDA events recorded on the launching stream
+ * (enable != 0 resets the counters).  read: summed milliseconds, summed 2*M*N*K flops, launches. */
+void gitb200_profile_gemm(int enable);
+void gitb200_profile_gemm_read(double* ms, double* flops, long long* launches);
+
 /* Number of kernels this library has launched since the last call with reset != 0 (bench.py's gpu_launches). */
 long long gitb200_launch_count(int reset);
 

@@ -500,6 +500,16 @@ long long gitb200_launch_count(int reset) {
   return v;
 }
 
+void gitb200_profile_gemm(int enable) { gemm_profile_enable(enable); }
+void gitb200_profile_gemm_read(double* ms, double* flops, long long* launches) {
+  double a = 0, b = 0;
+  long long n = 0;
+  gemm_profile_read(&a, &b, &n);
+  if (ms) *ms = a;
+  if (flops) *flops = b;
+  if (launches) *launches = n;
+}
+
 const char* gitb200_last_error(const gitb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int gitb200_create(const gitb200_config* cfg, int device, gitb200_ctx** out) {

@@ -208,13 +208,15 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-__device__ __forceinline__ float dot8_group(const float (&q)[8], const float (&k)[8]) {
+// Dot product over the 8 lanes of one key group.  `gmask` names exactly those 8 lanes: the groups of a warp run
+// different trip counts at the tails of the key loops, so a full-warp shuffle mask would be undefined behaviour.
+__device__ __forceinline__ float dot8_group(const float (&q)[8], const float (&k)[8], uint32_t gmask) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s = fmaf(q[i], k[i], s);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(gmask, s, 1);
+  s += __shfl_xor_sync(gmask, s, 2);
+  s += __shfl_xor_sync(gmask, s, 4);
   return s;
 }
 
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 3;       // 0..15: which key of a 16-key stride this lane group handles
   const int d0 = (lane & 7) * 8;  // this lane's 8 dims of the 64-dim head
+  const uint32_t gmask = 0xFFu << (lane & 24);
   const int rl0 = chunk * TA_NB;
   const int n_loc = min(TA_NB, a.rows_per_clip - rl0);
   const int width = a.heads * HD;
@@ -263,8 +266,8 @@ __global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs
 #pragma unroll
     for (int r = 0; r < TA_NB; ++r) {
       if (r < n_loc) {  // block-uniform
-        acc_add(acc[r], dot8_group(q[r], k0), v0);
-        acc_add(acc[r], dot8_group(q[r], k1), v1);
+        acc_add(acc[r], dot8_group(q[r], k0, gmask), v0);
+        acc_add(acc[r], dot8_group(q[r], k1, gmask), v1);
       }
     }
   }
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs
     load8(vp + (size_t)key * a.ld_vis, v0);
 #pragma unroll
     for (int r = 0; r < TA_NB; ++r)
-      if (r < n_loc) acc_add(acc[r], dot8_group(q[r], k0), v0);
+      if (r < n_loc) acc_add(acc[r], dot8_group(q[r], k0, gmask), v0);
   }
 
   // ---- causal text prefix (handled by the last split); per-row keys via the ancestor table
@@ -292,11 +295,12 @@ __global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs
         float k0[8], v0[8];
         load8(t, k0);
         load8(t + width, v0);
-        acc_add(acc[r], dot8_group(q[r], k0), v0);
+        acc_add(acc[r], dot8_group(q[r], k0, gmask), v0);
       }
     }
   }
 
+  __syncwarp();
   // ---- merge the 4 lane groups of each warp (lanes differing in bits 3,4), then the 4 warps through smem
 #pragma unroll
   for (int r = 0; r < TA_NB; ++r) {

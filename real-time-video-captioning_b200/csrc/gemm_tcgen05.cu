@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -358,9 +359,53 @@ cudaError_t launch(const GemmArgs& a, const Epilogue& ep, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// ---- optional per-launch timing with CUDA events on the launching stream (bench.py's roofline leg)
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<double> flops;
+  size_t used = 0;              // pairs in flight
+  double ms = 0, fl = 0;
+  long long n = 0;
+} g_prof;
+
+void prof_drain() {
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    cudaEventSynchronize(g_prof.ev[2 * i + 1]);
+    float t = 0;
+    if (cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
+      g_prof.ms += t;
+      g_prof.fl += g_prof.flops[i];
+      ++g_prof.n;
+    }
+  }
+  g_prof.used = 0;
+}
+
 }  // namespace
 
 const char* gemm_last_error() { return g_err.c_str(); }
+
+void gemm_profile_enable(int on) {
+  if (on && g_prof.ev.empty()) {
+    g_prof.ev.resize(2 * 8192);
+    g_prof.flops.resize(8192);
+    for (auto& e : g_prof.ev) cudaEventCreate(&e);
+  }
+  if (on) {
+    g_prof.used = 0;
+    g_prof.ms = g_prof.fl = 0;
+    g_prof.n = 0;
+  }
+  g_prof.on = on != 0;
+}
+
+void gemm_profile_read(double* ms, double* flops, long long* launches) {
+  prof_drain();
+  *ms = g_prof.ms;
+  *flops = g_prof.fl;
+  *launches = g_prof.n;
+}
 
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
   if (a.M <= 0) return cudaSuccess;
@@ -376,6 +421,14 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     const long tiles256 = (long)((a.M + BM - 1) / BM) * (a.N / 256);
     bn = (a.N % 256 == 0 && tiles256 >= sm_count()) ? 256 : 128;
   }
-  if (bn == 256 && a.N % 256 == 0) return launch<256>(a, ep, stream);
-  return launch<128>(a, ep, stream);
+  size_t slot = 0;
+  if (g_prof.on) {
+    if (g_prof.used == g_prof.flops.size()) prof_drain();
+    slot = g_prof.used++;
+    g_prof.flops[slot] = 2.0 * a.M * a.N * a.K;
+    cudaEventRecord(g_prof.ev[2 * slot], stream);
+  }
+  const cudaError_t e = (bn == 256 && a.N % 256 == 0) ? launch<256>(a, ep, stream) : launch<128>(a, ep, stream);
+  if (g_prof.on) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+  return e;
 }
