@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the GIT captioning hot path (BASELINE.json metric: captions/sec on 6-frame clips).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU implementation (oracle port)
+
+One "step" = one batch of synthetic 6 x 224 x 224 clips through the whole path: CLIP ViT-B/16 encode with temporal
+embeddings, decoder pass over the visual tokens (K/V cache fill), 14 greedy decode steps (beam_size=1, max_steps=15,
+the reference's search defaults with beam 1) and the device-side search.  Workload = BASELINE.json configs[1]
+("GIT-base batched greedy decode, 6-frame MSR-VTT-shaped synthetic clips, bf16, 1 B200"); weights are random-init
+(seeded), inputs are seeded randn clips.  Prints ONE JSON line (rank 0).
+
+Timing: W warm-up steps, then K steps bracketed by barrier + cuda synchronize, timed with CUDA events on the launching
+stream, max over ranks.  Each step reads a different resident batch of frames and streams > 4 GB of activations, far
+beyond the 126 MB L2, so no explicit L2 flush is needed between iterations (config.l2 states this).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "captions_per_sec_6frame_clips"
+UNIT = "clips/s"
+FRAMES, RES = 6, 224
+# SURVEY.md 8(d) / BASELINE.md section 3: algorithmic tensor-core work per GIT-base 6-frame clip
+GFLOP_PER_CLIP = 338.42
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["bf16_tflops_sustained"]), float(p["bf16_tflops"]), float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 1400.0, 1590.0, 6650.0, "fallback"  # B200_PROFILING.md fallback figures
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        busy = [s for s in sm if s > 500] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference_cpu(steps: int, warmup: int, clips_per_step: int = 1):
+    """Reference CPU implementation of the path = the oracle port in reference-faithful mode (per-frame ViT calls,
+    hidden-state history with per-step K/V re-projection, Python search loop, per-step logits -> numpy), fp32, all host
+    threads (the reference itself cannot be imported: SURVEY.md 8c)."""
+    import torch
+    from oracle import git_oracle as go
+    from oracle import search_oracle as so
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = go.GitConfig(num_image_with_embedding=FRAMES)
+    sd = go.init_state_dict(cfg, seed=0, temporal_std=0.02, perturb=True)
+    g = torch.Generator().manual_seed(1)
+    clips = torch.randn(clips_per_step, FRAMES, 3, RES, RES, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            for c in clips:  # the reference captions one clip at a time (model.py:765-770)
+                so.caption_clip(sd, cfg, c, per_frame_calls=True, beam_size=1, max_steps=15)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return {"value": clips_per_step * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "cores": torch.get_num_threads(), "p50_ms": 1e3 * statistics.median(times) / clips_per_step,
+            "sample": f"{len(times)} steps x {clips_per_step} clip(s), greedy (beam 1, max_steps 15), fp32, after {warmup} warm-up"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--beam", type=int, default=1)
+    ap.add_argument("--max-steps", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=3, help="clips timed for the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=32, help="clips per host->device chunk on the e2e path")
+    ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "GIT-base (CLIP ViT-B/16 + 6-layer prefix-LM decoder) batched greedy caption, 6x224x224 synthetic clips",
+              "clips_per_gpu_per_step": args.batch, "frames": FRAMES, "beam_size": args.beam, "max_steps": args.max_steps,
+              "weights": "random-init (seeded)", "parallelism": f"clip-sharded dp{world}",
+              "l2": "no flush: every step streams >4 GB of activations and a 231 MB frame batch (L2 = 126 MB)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        warm = max(1, min(args.warmup, 1))
+        steps = max(1, min(args.steps, 5))
+        r = run_reference_cpu(steps, warm, 1)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic", "config": dict(config, clips_per_gpu_per_step=1, parallelism="cpu"),
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "latency_ms_p50": r["p50_ms"]}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    g = importlib.import_module("real-time-video-captioning_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gitb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # identical random-init weights on every rank (same seed)
+    from oracle import git_oracle as go  # weight initialiser only (not on the measured path)
+    ocfg = go.GitConfig(num_image_with_embedding=FRAMES)
+    sd = go.init_state_dict(ocfg, seed=0, temporal_std=0.02, perturb=True)
+    eng = g.Engine(g.make_config({"num_image_with_embedding": FRAMES}, ocfg.sos_index, ocfg.eos_index), local_rank)
+    eng.load_state_dict(sd)
+    del sd
+    sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
+    B = args.batch
+    eng.reserve(B, FRAMES, args.beam, args.max_steps)
+
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    n_sets = 2  # alternate between resident frame batches
+    frames = [torch.randn(B, FRAMES, 3, RES, RES, device=dev, generator=gen) for _ in range(n_sets)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        tok, lp, _ = eng.caption(frames[i % n_sets], sp)
+        if world > 1:  # C2: gather the caption tokens of all ranks (the path's only collective)
+            out = [torch.empty_like(tok) for _ in range(world)]
+            dist.all_gather(out, tok)
+        return tok
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.launch_count(reset=True)
+    eng.lib.gitb200_profile_gemm(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count()
+    import ctypes
+    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    eng.lib.gitb200_profile_gemm_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n))
+    eng.lib.gitb200_profile_gemm(0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True,
+                              "gemm_ms": g_ms.value, "gemm_tflops": g_fl.value / max(g_ms.value, 1e-9) / 1e9}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- e2e: same metric through the public host-buffer API (pinned host frames in, host tokens out)
+    host_frames = torch.randn(B, FRAMES, 3, RES, RES, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    eng.caption_host(host_frames, sp, chunk_clips=args.chunk)  # warm-up (allocates staging buffers)
+    sync_all()
+    e2e_steps = max(2, min(args.steps, 6))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tok_h, lp_h = eng.caption_host(host_frames, sp, chunk_clips=args.chunk)  # synchronous
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / t.item()
+    h2d = host_frames.numel() * 4
+    d2h = tok_h.numel() * 4 + lp_h.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- single-clip latency (p50) on rank 0
+    one = frames[0][:1].contiguous()
+    lat = []
+    for i in range(25):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        eng.caption(one, sp)
+        b.record(stream)
+        b.synchronize()
+        if i >= 5:
+            lat.append(a.elapsed_time(b))
+    p50 = statistics.median(lat)
+
+    sustained, burst, hbm, src = measured_peaks()
+    gemm_tflops = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<128|256>", "achieved": gemm_tflops, "peak": sustained,
+                "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": None,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / (ms if world == 1 else ms) if ms > 0 else None,
+                "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
+                "path_tflops_algorithmic": GFLOP_PER_CLIP * 1e9 * B * args.steps / (ms * 1e-3) / 1e12}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_reference_cpu(args.cpu_clips, 1, 1)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                        "p50_ms": r["p50_ms"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "Engine.caption_host (gitb200_caption_host): pinned host frames -> host tokens"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
