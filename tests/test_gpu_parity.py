@@ -289,3 +289,32 @@ def test_errors_are_loud(g):
         eng.encode(torch.zeros(1, 2, 3, 224, 224, device="cuda"))  # weights never loaded
     with pytest.raises(g.GitB200Error):
         eng.load_state_dict({"image_encoder.conv1.weight": torch.zeros(768, 3, 16, 16)})  # missing weights
+
+
+def test_cuda_path_matches_committed_golden_fixture(g):
+    """tests/golden/git_base_f2.npz (made by oracle/make_golden.py from seeded weights/inputs): the CUDA path must
+    reproduce the frozen numbers within the stated bf16 tolerances, without the oracle in the loop."""
+    import numpy as np
+    from oracle import make_golden
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "git_base_f2.npz"))
+    cfg, sd, frames, tokens = make_golden.inputs(True)
+    eng = g.Engine(g.make_config({"num_image_with_embedding": make_golden.SPEC["n_frames"]}, cfg.sos_index, cfg.eos_index), 0)
+    eng.load_state_dict(sd)
+    logits, vf, hidden = eng.forward_logits(frames.cuda(), tokens.cuda())
+    logits, vf, hidden = logits.cpu(), vf.cpu(), hidden.cpu()
+    cols = torch.from_numpy(gold["vocab_cols"])
+    L = make_golden.SPEC["caption_len"]
+    for b in range(make_golden.SPEC["n_clips"]):
+        sigma = float(gold[f"logits_stats_{b}"][1])
+        d = (logits[b][:, cols] - torch.from_numpy(gold[f"logits_cols_{b}"])).abs().max().item()
+        assert d < 0.15 * sigma, (d, sigma)
+        assert rel_fro(vf[b, ::37], torch.from_numpy(gold[f"vf_rows_{b}"])) < 2e-2
+        assert rel_fro(hidden[b][:, -L:, ::16], torch.from_numpy(gold[f"hidden_text_{b}"])) < 3e-2
+        norms = hidden[b].double().flatten(1).norm(dim=1)
+        assert torch.allclose(norms, torch.from_numpy(gold[f"hidden_norms_{b}"]), rtol=1e-2)
+        assert np.array_equal(logits[b].argmax(-1).numpy(), gold[f"logits_argmax_{b}"])  # tied head: 9-sigma margins
+    for nb in (1, 4):
+        sp = g.SearchConfig(beam_size=nb, max_steps=make_golden.SPEC["max_steps"])
+        tok, lp, _ = eng.caption(frames.cuda(), sp)
+        assert np.array_equal(tok[:, 0].cpu().numpy(), gold[f"tokens_beam{nb}"])
+        assert np.allclose(lp.cpu().numpy(), gold[f"logprobs_beam{nb}"], atol=0.02, rtol=0.02)
