@@ -1,0 +1,321 @@
+// 2-CTA (cta_group::2) persistent bf16 GEMM for the large-M contractions of the path (ViT and decoder
+// QKV / out-proj / MLP over tens of thousands of rows):  C = act(A * W^T + bias) + residual.
+//
+// A CTA pair (cluster of 2 on one TPC) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256):
+//   * each CTA TMA-loads its own 128 rows of A and HALF of the 256 W rows (128) per K block, so the pair moves
+//     64 KB per 256x256x64 MACs -- 2/3 of the L2->SM traffic of two independent 128x256 tiles, and each SM reads
+//     half as much operand data from shared memory per MMA (ncu on the 1-CTA kernel: tensor pipe 48-71 %, L2-feed
+//     and epilogue bound),
+//   * both CTAs' TMA transactions complete on the LEADER's mbarrier; the leader's single MMA thread issues the
+//     instruction for the pair and releases smem stages / publishes accumulators with multicast commits,
+//   * the epilogue (8 warps per CTA) converts 32 x 64 blocks, stages them in 128B-swizzled shared memory and writes
+//     them with TMA stores (full 128-byte lines, rows beyond M clipped by the tensor map); the residual block is
+//     brought in by a TMA load into the same staging buffer while the accumulator is read from TMEM.
+//     (The 1-CTA kernel's per-thread 16-byte row stores cost ~13.5k cycles per tile -- more than the K=768 mainloop.)
+#include <cuda.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+// shared with gemm_tcgen05.cu
+bool gemm_get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_cols, int box_rows, CUtensorMap* out);
+int gemm_sm_count();
+
+namespace {
+
+constexpr int BM = 128;          // rows per CTA (256 per pair)
+constexpr int BN = 256;          // columns per pair tile
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of W
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int EPI_COLS = 64;                       // columns per staged block (128-byte rows)
+constexpr int STAGING_BYTES = 32 * EPI_COLS * 2;   // 4 KB per epilogue warp
+constexpr int TMEM_COLS = 2 * BN;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + 1024 + 512;
+
+struct Epi2 {
+  const float* bias;
+  int act;
+  int has_res;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior tcgen05 ops of this thread have completed) on the same barrier offset in both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, int M, int N, int K,
+             Epi2 ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t staging_base = smem_base + STAGES * STAGE_BYTES;  // 1024-aligned (32 KB multiples)
+  const uint32_t bar_base = staging_base + NUM_EPI_WARPS * STAGING_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + NUM_EPI_WARPS);
+  auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
+
+  const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  const int m_pairs = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = N / BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    ptx::prefetch_tensormap(&tmap_out);
+    if (ep.has_res) ptx::prefetch_tensormap(&tmap_res);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(full_bar(s), 1);
+        ptx::mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);
+        ptx::mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // every epilogue warp of BOTH CTAs arrives on the leader's
+      }
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) ptx::mbar_init(res_bar(w), 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one thread in each CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / n_tiles) * 2 * BM + (int)rank * BM;
+        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t leader_full = mapa_rank(full_bar(stage), 0);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);  // both CTAs' bytes
+          tma_load_2d_pair(smem_a(stage), &tmap_a, leader_full, kb * BK, m0);
+          tma_load_2d_pair(smem_b(stage), &tmap_b, leader_full, kb * BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: one thread of the leader CTA
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(smem_a(stage));
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_pair(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int c_begin = (ew >> 2) * (BN / 2), c_end = c_begin + BN / 2;
+    const uint32_t stg = staging_base + ew * STAGING_BYTES;
+    const uint32_t rbar = res_bar(ew);
+    const uint32_t my_row_off = (uint32_t)lane * 128u;
+    uint32_t res_phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / n_tiles) * 2 * BM + (int)rank * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+      if (row0 < M) {  // warp-uniform: this warp's 32 rows are not entirely beyond M
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += EPI_COLS) {
+          const int col = n0 + c;
+          if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous block has left the staging buffer
+          __syncwarp();
+          if (ep.has_res && lane == 0) {
+            ptx::mbar_arrive_expect_tx(rbar, STAGING_BYTES);
+            ptx::tma_load_2d(stg, &tmap_res, rbar, col, row0);
+          }
+          uint32_t v0[32], v1[32];
+          ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c, v0);
+          ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c + 32), v1);
+          ptx::tmem_ld_wait();
+          if (ep.has_res) {
+            ptx::mbar_wait(rbar, res_phase);
+            res_phase ^= 1u;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 8 chunks of 8 columns = one 128-byte staged row
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
+            if (ep.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8 + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (ep.act == ACT_QUICK_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = quick_gelu(f[i]);
+            } else if (ep.act == ACT_GELU_ERF) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+            }
+            const uint32_t saddr = stg + my_row_off + (uint32_t)((j ^ (lane & 7)) << 4);
+            if (ep.has_res) {
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+              const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+              f[0] += a0.x; f[1] += a0.y; f[2] += a1.x; f[3] += a1.y;
+              f[4] += a2.x; f[5] += a2.y; f[6] += a3.x; f[7] += a3.y;
+            }
+            const uint32_t p0 = pack_bf16(f[0], f[1]), p1 = pack_bf16(f[2], f[3]), p2 = pack_bf16(f[4], f[5]), p3 = pack_bf16(f[6], f[7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          }
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_out, stg, col, row0);
+            ptx::tma_store_commit();
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();  // all output bytes written before the CTA may exit
+  }
+
+  ptx::tc_fence_before();
+  cluster_sync_all();  // the peer may still read this CTA's smem / signal its barriers until here
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+// Returns cudaErrorNotSupported when the shape does not suit the pair kernel (caller falls back to the 1-CTA kernel).
+cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
+  if (a.N % BN != 0 || a.out == nullptr || a.out_f32 != nullptr || a.gin > 0 || a.res_periodic) return cudaErrorNotSupported;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap ta, tb, to, tr;
+  if (!gemm_get_tensor_map(a.A, a.M, a.K, a.lda, BK, BM, &ta)) return cudaErrorInvalidValue;
+  if (!gemm_get_tensor_map(a.W, a.N, a.K, a.ldw, BK, BN / 2, &tb)) return cudaErrorInvalidValue;
+  if (!gemm_get_tensor_map(a.out, a.M, a.N, a.ldo, EPI_COLS, 32, &to)) return cudaErrorInvalidValue;
+  tr = to;
+  if (a.residual != nullptr && !gemm_get_tensor_map(a.residual, a.M, a.N, a.ldr, EPI_COLS, 32, &tr)) return cudaErrorInvalidValue;
+  const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
+  int clusters = gemm_sm_count() / 2;
+  if (tiles < clusters) clusters = tiles;
+  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0};
+  gemm2_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
+  note_launch();
+  return cudaGetLastError();
+}

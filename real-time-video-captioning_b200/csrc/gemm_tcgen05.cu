@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream);
+
 namespace {
 
 constexpr int BM = 128;       // rows per tile = UMMA M = TMEM lanes
@@ -278,9 +280,9 @@ EncodeTiledFn encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int rows, cols, ld, box_rows;
+  int rows, cols, ld, box_rows, box_cols;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
   }
 };
 struct MapKeyHash {
@@ -290,15 +292,18 @@ struct MapKeyHash {
     h = h * 1000003u ^ (size_t)k.cols;
     h = h * 1000003u ^ (size_t)k.ld;
     h = h * 1000003u ^ (size_t)k.box_rows;
+    h = h * 1000003u ^ (size_t)k.box_cols;
     return h;
   }
 };
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix (leading dimension ld), box = 64 x box_rows,
-// 128-byte swizzle; out-of-bounds elements read as zero (M / K tails).
-bool get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, rows, cols, ld, box_rows};
+}  // namespace
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix (leading dimension ld), box = box_cols x box_rows
+// (box_cols * 2 bytes == 128), 128-byte swizzle; out-of-bounds elements read as zero / are not written (M, K tails).
+bool gemm_get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_cols, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, rows, cols, ld, box_rows, box_cols};
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
@@ -312,7 +317,7 @@ bool get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_rows, C
   }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estride,
@@ -328,7 +333,7 @@ bool get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_rows, C
   return true;
 }
 
-int sm_count() {
+int gemm_sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -338,6 +343,8 @@ int sm_count() {
   }
   return n;
 }
+
+namespace {
 
 template <int BN>
 cudaError_t launch(const GemmArgs& a, const Epilogue& ep, cudaStream_t stream) {
@@ -350,10 +357,10 @@ cudaError_t launch(const GemmArgs& a, const Epilogue& ep, cudaStream_t stream) {
     attr_set = true;
   }
   CUtensorMap ta, tb;
-  if (!get_tensor_map(a.A, a.M, a.K, a.lda, BM, &ta)) return cudaErrorInvalidValue;
-  if (!get_tensor_map(a.W, a.N, a.K, a.ldw, BN, &tb)) return cudaErrorInvalidValue;
+  if (!gemm_get_tensor_map(a.A, a.M, a.K, a.lda, BK, BM, &ta)) return cudaErrorInvalidValue;
+  if (!gemm_get_tensor_map(a.W, a.N, a.K, a.ldw, BK, BN, &tb)) return cudaErrorInvalidValue;
   const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int grid = tiles < gemm_sm_count() ? tiles : gemm_sm_count();
   gemm_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, a.M, a.N, a.K, ep);
   note_launch();
   return cudaGetLastError();
@@ -419,7 +426,9 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
   int bn = force_bn;
   if (bn == 0) {
     const long tiles256 = (long)((a.M + BM - 1) / BM) * (a.N / 256);
-    bn = (a.N % 256 == 0 && tiles256 >= sm_count()) ? 256 : 128;
+    bn = (a.N % 256 == 0 && tiles256 >= gemm_sm_count()) ? 256 : 128;
+    // large-M contractions go to the CTA-pair kernel (256x256 tiles, TMA-store epilogue) when its epilogue applies
+    if (a.M >= 1024 && a.N % 256 == 0 && a.out != nullptr && a.out_f32 == nullptr && a.gin == 0 && !a.res_periodic) bn = 2;
   }
   size_t slot = 0;
   if (g_prof.on) {
@@ -428,7 +437,9 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     g_prof.flops[slot] = 2.0 * a.M * a.N * a.K;
     cudaEventRecord(g_prof.ev[2 * slot], stream);
   }
-  const cudaError_t e = (bn == 256 && a.N % 256 == 0) ? launch<256>(a, ep, stream) : launch<128>(a, ep, stream);
+  cudaError_t e = cudaErrorNotSupported;
+  if (bn == 2) e = gemm2_bf16(a, stream);
+  if (e == cudaErrorNotSupported) e = (bn != 128 && a.N % 256 == 0) ? launch<256>(a, ep, stream) : launch<128>(a, ep, stream);
   if (g_prof.on) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
   return e;
 }

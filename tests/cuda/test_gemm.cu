@@ -183,18 +183,28 @@ int main(int argc, char** argv) {
       {100, 768, 3072, 0, 1, 1, 0, 0, 0, 0, 0, 0},
       {1542, 1024, 640, 0, 1, 0, 0, 0, 0, 0, 0, 0},     // ViT-L/14 patch K=588 padded to 640 (K % 64 != 0 path via 8-multiple)
       {777, 1024, 584, 0, 1, 0, 0, 0, 0, 0, 1, 128},    // K tail (584 = 9*64 + 8)
+      // CTA-pair kernel (bn == 2): 256x256 pair tiles, TMA-store epilogue, TMA residual load
+      {256, 256, 64, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {256, 256, 768, 0, 1, 0, 0, 0, 0, 0, 0, 2},
+      {1182, 768, 768, 0, 1, 1, 0, 0, 0, 0, 0, 2},
+      {1182 * 4, 2304, 768, 0, 1, 0, 0, 0, 0, 0, 0, 2},
+      {1182 * 3, 3072, 768, ACT_QUICK_GELU, 1, 0, 0, 0, 0, 0, 0, 2},
+      {1182 * 3 + 77, 768, 3072, 0, 1, 1, 0, 0, 0, 0, 0, 2},
+      {100, 1536, 768, ACT_GELU_ERF, 1, 1, 0, 0, 0, 0, 0, 2},
+      {1542 * 2, 1024, 640, 0, 1, 0, 0, 0, 0, 0, 0, 2},
   };
   for (const Case& c : cases) fails += run_case(c);
   if (argc > 1 && fails == 0) {
     const int B = atoi(argv[1]);
     const int M = 1182 * B;
-    for (int bn : {128, 256}) {
+    for (int bn : {256, 2}) {
       bench_case(M, 2304, 768, bn, 0, 0);
       bench_case(M, 768, 768, bn, 0, 1);
       bench_case(M, 3072, 768, bn, ACT_QUICK_GELU, 0);
       bench_case(M, 768, 3072, bn, 0, 1);
     }
     bench_case(8192, 8192, 8192, 256, 0, 0);
+    bench_case(8192, 8192, 8192, 2, 0, 0);
     bench_case(64, 30720, 768, 128, 0, 0);
   }
   printf("test_gemm: %s (%d failing cases)\n", fails ? "FAILED" : "PASSED", fails);
