@@ -131,6 +131,9 @@ int gitb200_op_layernorm(const void* x_dev, int rows, int cols, const float* gam
 /* qkv: bf16 [n_groups*group_len, 3*heads*64] -> out bf16 [n_groups*group_len, heads*64] */
 int gitb200_op_attention_groups(const void* qkv_dev, void* out_dev, int n_groups, int group_len, int heads,
                                 float scale, void* stream);
+/* the same operator on the warp-level mma.sync path (the kernel the tcgen05 one replaced; kept as a cross-check) */
+int gitb200_op_attention_groups_mma(const void* qkv_dev, void* out_dev, int n_groups, int group_len, int heads,
+                                    float scale, void* stream);
 /* Search on a pre-computed score sequence: logits_dev fp32 [max_steps-1, n_clips*beam, ld]. */
 int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, int sos, int eos,
                       const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, void* stream);

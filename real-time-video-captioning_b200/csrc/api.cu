@@ -246,7 +246,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
     const VitLayer& L = c->vit[l];
     TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
     TRY(gemm(c, linear(c->lnb.p, W, L.w_qkv, W, rows, 3 * W, L.b_qkv, c->qkv.p, 3 * W), s));
-    CUDA_OK(c, attention_groups(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
+    CUDA_OK(c, attention_groups_tc(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
     {
       GemmArgs g = linear(c->attn.p, W, L.w_out, W, rows, W, L.b_out, c->x.p, W);
       g.residual = c->x.p; g.ldr = W;  // x += out_proj(attn): each element is read then written by one thread
@@ -312,7 +312,7 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
       TRY(gemm(c, linear(c->hv.p, H, L.w_qkv + (size_t)H * H, H, M, 2 * H, L.b_qkv + H, c->kv[l].p + H, 3 * H), s));
       break;
     }
-    CUDA_OK(c, attention_groups(c->kv[l].p, 3 * H, c->vattn.p, H, B, Nv, k.dec_heads, scale, s));
+    CUDA_OK(c, attention_groups_tc(c->kv[l].p, 3 * H, c->vattn.p, H, B, Nv, k.dec_heads, scale, s));
     {
       GemmArgs g = linear(c->vattn.p, H, L.w_out, H, M, H, L.b_out, c->hvb.p, H);
       g.residual = c->hv.p; g.ldr = H;
@@ -878,6 +878,12 @@ int gitb200_op_layernorm(const void* x, int rows, int cols, const float* gamma, 
 }
 
 int gitb200_op_attention_groups(const void* qkv, void* out, int n_groups, int group_len, int heads, float scale, void* stream) {
+  cudaError_t e = attention_groups_tc((const bf16*)qkv, 3 * heads * 64, (bf16*)out, heads * 64, n_groups, group_len, heads, scale, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "attention_groups_tc: %s [%s]", cudaGetErrorString(e), gemm_last_error());
+  return GITB200_OK;
+}
+
+int gitb200_op_attention_groups_mma(const void* qkv, void* out, int n_groups, int group_len, int heads, float scale, void* stream) {
   cudaError_t e = attention_groups((const bf16*)qkv, 3 * heads * 64, (bf16*)out, heads * 64, n_groups, group_len, heads, scale, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "attention_groups: %s", cudaGetErrorString(e));
   return GITB200_OK;

@@ -67,6 +67,9 @@ cudaError_t write_cls_rows(const float* cls, const bf16* pos, int n_frames, int 
 // visual pass: len Nv).  qkv: [rows, 3*H*64] bf16 laid out [q | k | v], out: [rows, H*64] bf16.
 cudaError_t attention_groups(const bf16* qkv, int ld_qkv, bf16* out, int ldo, int n_groups, int group_len,
                              int heads, float scale, cudaStream_t stream);
+// Same contract on the tcgen05 path (S and PV accumulators in TMEM, TMA-fed): the kernel the pipeline uses.
+cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo, int n_groups, int group_len,
+                                int heads, float scale, cudaStream_t stream);
 
 // Text rows attending to the visual keys of their clip plus their causal text prefix.
 struct TextAttnArgs {

@@ -223,13 +223,13 @@ def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
     return out
 
 
-def op_attention_groups(qkv: torch.Tensor, n_groups: int, group_len: int, heads: int, scale: float):
+def op_attention_groups(qkv: torch.Tensor, n_groups: int, group_len: int, heads: int, scale: float, legacy_mma: bool = False):
     lib = _lib.load()
     qkv = qkv.contiguous()
     out = torch.empty(qkv.shape[0], heads * 64, dtype=torch.bfloat16, device=qkv.device)
     s = ctypes.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)
-    check(lib.gitb200_op_attention_groups(_ptr(qkv), _ptr(out), n_groups, group_len, heads, scale, s), None,
-          "gitb200_op_attention_groups")
+    fn = lib.gitb200_op_attention_groups_mma if legacy_mma else lib.gitb200_op_attention_groups
+    check(fn(_ptr(qkv), _ptr(out), n_groups, group_len, heads, scale, s), None, "gitb200_op_attention_groups")
     return out
 
 

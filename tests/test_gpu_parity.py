@@ -106,19 +106,21 @@ def test_op_layernorm(g, rows, cols, eps):
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max()
 
 
-@pytest.mark.parametrize("n_groups,group_len,heads", [(3, 197, 12), (2, 257, 16), (1, 1182, 12), (2, 64, 12), (2, 65, 12), (5, 1, 12)])
-def test_op_attention_groups(g, n_groups, group_len, heads):
+@pytest.mark.parametrize("legacy", [False, True])
+@pytest.mark.parametrize("n_groups,group_len,heads", [(3, 197, 12), (2, 257, 16), (1, 1182, 12), (2, 64, 12), (2, 65, 12), (5, 1, 12),
+                                                      (2, 128, 12), (3, 129, 12), (2, 200, 12)])
+def test_op_attention_groups(g, n_groups, group_len, heads, legacy):
     from importlib import import_module
     eng = import_module("real-time-video-captioning_b200.engine")
     gen = torch.Generator(device="cuda").manual_seed(group_len)
     W = heads * 64
     qkv = torch.randn(n_groups * group_len, 3 * W, device="cuda", generator=gen).bfloat16()
-    out = eng.op_attention_groups(qkv, n_groups, group_len, heads, 0.125)
+    out = eng.op_attention_groups(qkv, n_groups, group_len, heads, 0.125, legacy_mma=legacy)
     q, k, v = qkv.float().view(n_groups, group_len, 3, heads, 64).permute(2, 0, 3, 1, 4)
     p = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
     ref = (p @ v).permute(0, 2, 1, 3).reshape(n_groups * group_len, W)
     err = (out.float() - ref).abs()
-    record("op_attention_groups", group_len=group_len, max_err=err.max().item())
+    record("op_attention_groups", group_len=group_len, legacy=legacy, max_err=err.max().item())
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max()
 
 
