@@ -399,7 +399,7 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
     a.q = c->tq.p; a.ldq = 3 * H; a.n_clips = t.n_clips; a.rows_per_clip = t.rows_per_clip; a.heads = k.dec_heads;
     a.vis_kv = c->kv[l].p; a.ld_vis = 3 * H; a.k_off = H; a.v_off = 2 * H; a.Nv = Nv;
     a.txt_kv = c->txt_kv[l].p; a.txt_slots = t.n_slots; a.text_slot_is_clip = t.slot_is_clip;
-    a.anc = t.anc; a.anc_ld = t.max_len; a.n_text = t.n_text; a.n_text_const = t.n_text_const;
+    a.anc = t.anc; a.anc_ld = t.max_len; a.n_text = t.n_text; a.n_text_const = t.n_text_const; a.max_text = t.max_len;
     a.scale = scale; a.out = c->ta.p; a.ldo = H; a.partial = c->partial.p; a.splits = splits;
     CUDA_OK(c, text_attention(a, s));
     {

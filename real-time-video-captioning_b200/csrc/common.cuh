@@ -59,10 +59,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires)
+// instead of burning issue slots of the warps that share its scheduler.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if (clock64() - t0 > GITB200_SPIN_LIMIT) {
       printf("gitb200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);

@@ -86,6 +86,7 @@ struct TextAttnArgs {
   int anc_ld = 0;
   const int* n_text = nullptr;   // [n_rows] number of visible text keys (pos+1); null = n_text_const
   int n_text_const = 0;
+  int max_text = 0;              // upper bound of the visible text keys of any row (sizes the score buffer)
   float scale = 0.125f;
   bf16* out = nullptr;  // [n_rows, ldo]
   int ldo = 0;

@@ -1,0 +1,34 @@
+"""Micro-benchmarks of single operators through the C ABI (CUDA events, warm, L2-exceeding inputs)."""
+import importlib
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+eng = importlib.import_module("real-time-video-captioning_b200.engine")
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def attention(B=64):
+    for name, n_groups, glen, heads in (("vit", B * 6, 197, 12), ("dec", B, 1182, 12)):
+        qkv = torch.randn(n_groups * glen, 3 * heads * 64, device="cuda").bfloat16()
+        flops = 4.0 * glen * glen * 64 * heads * n_groups
+        for legacy in (True, False):
+            ms = timeit(lambda: eng.op_attention_groups(qkv, n_groups, glen, heads, 0.125, legacy_mma=legacy))
+            print(f"attention {name} B={B} {'mma.sync' if legacy else 'tcgen05 '}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  ({ms * 1e3 / B:.1f} us/clip/layer)")
+
+
+if __name__ == "__main__":
+    attention(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
