@@ -119,15 +119,15 @@ def run_reference_cpu(steps: int, warmup: int, clips_per_step: int = 1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--max-steps", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=3, help="clips timed for the cpu_baseline leg")
-    ap.add_argument("--chunk", type=int, default=32, help="clips per host->device chunk on the e2e path")
+    ap.add_argument("--chunk", type=int, default=64, help="clips per host->device chunk on the e2e path")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     args = ap.parse_args()
 
@@ -137,7 +137,7 @@ def main():
     config = {"workload": "GIT-base (CLIP ViT-B/16 + 6-layer prefix-LM decoder) batched greedy caption, 6x224x224 synthetic clips",
               "clips_per_gpu_per_step": args.batch, "frames": FRAMES, "beam_size": args.beam, "max_steps": args.max_steps,
               "weights": "random-init (seeded)", "parallelism": f"clip-sharded dp{world}",
-              "l2": "no flush: every step streams >4 GB of activations and a 231 MB frame batch (L2 = 126 MB)"}
+              "l2": f"no flush: every step streams >{args.batch * 60 // 1000} GB of activations and a {args.batch * 3.6128:.0f} MB frame batch (L2 = 126 MB)"}
 
     if args.impl == "reference":
         if rank != 0:
