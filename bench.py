@@ -264,8 +264,16 @@ def main():
 
     sustained, burst, hbm, src = measured_peaks()
     gemm_tflops = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<128|256>", "achieved": gemm_tflops, "peak": sustained,
-                "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": None,
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_gemm2_traffic.json")) as fh:
+            traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05) + gemm_tcgen05_kernel<128> (decode rows)",
+                "achieved": gemm_tflops, "peak": sustained,
+                "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
+                "traffic_note": "avg DRAM bytes per launch of the 4 ViT-layer GEMMs at M=75648 (profiles/r01_gemm2_ncu_summary.md)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / (ms if world == 1 else ms) if ms > 0 else None,
                 "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
