@@ -207,7 +207,9 @@ int ln(gitb200_ctx* c, const bf16* x, int rows, int cols, const float* g, const 
 }
 
 // ------------------------------------------------------------------ encode
-int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s) {
+// clip_offset / total_clips: the visual features of this call land at clip index `clip_offset` of a buffer sized for
+// `total_clips` clips (host path: chunks are encoded as their frames arrive, then decoded together).
+int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, int clip_offset = 0, int total_clips = 0) {
   const gitb200_config& k = c->cfg;
   const int W = k.vit_width, T = c->T, G = k.resolution / k.patch;
   // zip() truncation of model.py:380: frames beyond the temporal-embedding list are dropped
@@ -220,7 +222,9 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   ENSURE(c, c->qkv, (size_t)rows * 3 * W);
   ENSURE(c, c->attn, (size_t)rows * W);
   ENSURE(c, c->mlp, (size_t)rows * 4 * W);
-  ENSURE(c, c->vf, (size_t)rows * W);
+  if (total_clips < clip_offset + n_clips) total_clips = clip_offset + n_clips;
+  if (clip_offset == 0) ENSURE(c, c->vf, (size_t)total_clips * F * T * W);  // later chunks must not reallocate it
+  else if (c->vf.cap < (size_t)total_clips * F * T * W) return fail(c, GITB200_ERR_STATE, "visual feature buffer too small for chunked encode");
 
   const size_t frame_elems = (size_t)3 * k.resolution * k.resolution;
   if (F == n_frames) {
@@ -265,9 +269,9 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
     }
   }
   // ln_post on all tokens + temporal embedding of the frame (frame index = (row / T) % F)
-  TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, c->vf.p, s,
+  TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, c->vf.p + (size_t)clip_offset * F * T * W, s,
          k.num_image_with_embedding > 0 ? c->temporal : nullptr, T, F));
-  c->cur_clips = n_clips;
+  c->cur_clips = clip_offset + n_clips;
   c->cur_nv = F * T;
   c->visual_pass_done = false;
   return 0;
@@ -765,20 +769,28 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
   for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
-  const int n_chunks = (n_clips + chunk_clips - 1) / chunk_clips;
-  for (int ch = 0; ch < n_chunks; ++ch) {
+  // Encode chunk by chunk as the frames arrive (copy of chunk i+1 overlaps the ViT of chunk i; a small first chunk
+  // keeps the un-overlapped head of the transfer short), then run the decoder once over all clips: the decode steps
+  // have a fixed cost per launch that is amortised over the whole batch.
+  int done = 0, ch = 0;
+  while (done < n_clips) {
     const int b = ch & 1;
-    const int c0 = ch * chunk_clips;
-    const int nc = (n_clips - c0) < chunk_clips ? (n_clips - c0) : chunk_clips;
+    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+    if (nc > n_clips - done) nc = n_clips - done;
     if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
-    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)c0 * clip_elems, (size_t)nc * clip_elems * sizeof(float),
+    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
                                cudaMemcpyHostToDevice, c->copy_stream));
     CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
     CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-    int r = gitb200_caption(c, c->stage[b].p, nc, n_frames, sp, c->out_tok.p + (size_t)c0 * per_clip_tok,
-                            c->out_lp.p + (size_t)c0 * sp->num_keep_best, nullptr, comp);
+    int r = run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips);
     if (r) return r;
     CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+    done += nc;
+    ++ch;
+  }
+  {
+    int r = run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp);
+    if (r) return r;
   }
   CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
