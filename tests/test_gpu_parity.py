@@ -320,3 +320,58 @@ def test_cuda_path_matches_committed_golden_fixture(g):
         tok, lp, _ = eng.caption(frames.cuda(), sp)
         assert np.array_equal(tok[:, 0].cpu().numpy(), gold[f"tokens_beam{nb}"])
         assert np.allclose(lp.cpu().numpy(), gold[f"logprobs_beam{nb}"], atol=0.02, rtol=0.02)
+
+
+def test_git_large_vit_l14_matches_oracle(g):
+    """BASELINE.json configs[3] geometry: CLIPViT_L_14 (1024 wide, 24 layers, 16 heads, patch 14 -> 257 tokens/frame,
+    conv K = 588 zero-padded to 640) feeding the same 6-layer decoder; the shipped teacher config
+    (data/teacher_configs/GIT_LARGE_MSRVTT/parameter.yaml).  Small clip count / frame count keeps the CPU oracle fast."""
+    param = {"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024, "num_image_with_embedding": 2}
+    cfg = go.GitConfig.from_param(param)
+    sd = go.init_state_dict(cfg, seed=31, temporal_std=0.02, perturb=True)
+    eng = g.Engine(g.make_config(param, cfg.sos_index, cfg.eos_index), 0)
+    eng.load_state_dict(sd)
+    assert eng.T == 257
+    frames = torch.randn(2, 3, 3, 224, 224, generator=torch.Generator().manual_seed(3))  # 3 frames: the third is dropped (zip)
+    tokens = torch.tensor([[101, 2023, 2003, 1037], [101, 7, 8, 9]])
+    logits, vf, hidden = eng.forward_logits(frames.cuda(), tokens.cuda())
+    assert vf.shape == (2, 2 * 257, 1024) and hidden.shape == (2, 7, 2 * 257 + 4, 768)
+    for b in range(2):
+        with torch.no_grad():
+            rl, rvf, rh = go.forward_one_custom(sd, cfg, frames[b], tokens[b:b + 1])
+        sigma = rl.std().item()
+        d = (logits[b].cpu() - rl[0]).abs()
+        e_vf = rel_fro(vf[b].cpu(), rvf[0])
+        record("git_large", clip=b, vf_rel_fro=e_vf, max_over_sigma=d.max().item() / sigma,
+               hidden_rel_fro=[rel_fro(hidden[b, i].cpu(), rh[i]) for i in range(7)])
+        assert e_vf < 2.5e-2, e_vf           # 24 layers instead of 12
+        assert d.max().item() < 0.15 * sigma and d.mean().item() < 0.03 * sigma
+    with torch.no_grad():
+        rvf = torch.cat([go.encode_clip(sd, cfg, f) for f in frames])
+    for nb, reorder in ((1, False), (4, True), (4, False)):
+        sp = g.SearchConfig(beam_size=nb, max_steps=6, reorder_cache=reorder)
+        tok, lp, _ = eng.caption(frames.cuda(), sp)
+        with torch.no_grad():
+            ref = so.infer(sd, cfg, rvf, beam_size=nb, max_steps=6, reorder_cache=reorder, save_logits=False)
+        record("git_large_caption", nb=nb, reorder=reorder, tokens=tok[:, 0].cpu().tolist(), ref_tokens=ref["predictions"].tolist(),
+               lp=lp[:, 0].cpu().tolist(), ref_lp=ref["logprobs"][:, 0].tolist())
+        if nb == 1:  # greedy on the tied head: the 9-sigma copy margin makes the sequence exact
+            assert torch.equal(tok[:, 0].cpu().long(), ref["predictions"])
+            assert torch.allclose(lp.cpu(), ref["logprobs"], atol=0.02, rtol=0.01)
+        else:
+            # beam 4 explores the rank-2.. candidates of the copy distribution, which are near-ties (SURVEY section 7), so
+            # the two searches may keep different beams after an early flip and finish on different hypotheses.  What must
+            # agree is the SCORING: both winners, teacher-forced through both implementations, get the same
+            # length-normalised log-probability (max_steps-1 scored steps, the last word is scored but dropped).
+            def norm_score(logits_row, hyp):  # logits_row [L, V] for tokens hyp [L]
+                lsm = torch.log_softmax(logits_row.float(), -1)
+                total = sum(lsm[t, hyp[t + 1]].item() for t in range(len(hyp) - 1)) + lsm[len(hyp) - 1].max().item()
+                return total / len(hyp) ** 0.6
+            for b in range(2):
+                for hyp in (tok[b, 0].cpu().long()[:5], ref["predictions"][b][:5]):
+                    el, _, _ = eng.forward_logits(frames[b:b + 1].cuda(), hyp[None].cuda(), want_hidden=False, want_features=False)
+                    with torch.no_grad():
+                        ol, _ = go.textual_forward(sd, cfg, rvf[b:b + 1], hyp[None])
+                    se, so_ = norm_score(el[0].cpu(), hyp), norm_score(ol[0], hyp)
+                    record("git_large_cross_score", clip=b, reorder=reorder, hyp=hyp.tolist(), engine=se, oracle=so_)
+                    assert abs(se - so_) < 0.03, (hyp, se, so_)
