@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 LIB_PATH = os.path.join(HERE, "libgitb200.so")
-SOURCES = ["gemm_tcgen05.cu", "gemm2_tcgen05.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "search.cu", "api.cu"]
+SOURCES = ["gemm_tcgen05.cu", "gemm2_tcgen05.cu", "gemv_skinny.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "search.cu", "api.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "gitb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-DGITB200_BUILD"]
@@ -73,7 +73,7 @@ def build_test_gemm() -> str:
     out = os.path.join(ROOT, "build", "test_gemm")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-o", out,
-           os.path.join(ROOT, "tests", "cuda", "test_gemm.cu"), os.path.join(CSRC, "gemm_tcgen05.cu"), os.path.join(CSRC, "gemm2_tcgen05.cu"),
+           os.path.join(ROOT, "tests", "cuda", "test_gemm.cu"), os.path.join(CSRC, "gemm_tcgen05.cu"), os.path.join(CSRC, "gemm2_tcgen05.cu"), os.path.join(CSRC, "gemv_skinny.cu"),
            os.path.join(ROOT, "tests", "cuda", "note_launch_stub.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

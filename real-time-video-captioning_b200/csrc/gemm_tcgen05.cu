@@ -21,6 +21,7 @@
 #include "kernels.h"
 
 cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream);
+cudaError_t gemv_skinny(const GemmArgs& a, cudaStream_t stream);
 
 namespace {
 
@@ -438,7 +439,8 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     cudaEventRecord(g_prof.ev[2 * slot], stream);
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (bn == 2) e = gemm2_bf16(a, stream);
+  if (force_bn == 1 || (force_bn == 0 && a.M <= 8)) e = gemv_skinny(a, stream);  // weight-streaming path for a few rows
+  else if (bn == 2) e = gemm2_bf16(a, stream);
   if (e == cudaErrorNotSupported) e = (bn != 128 && a.N % 256 == 0) ? launch<256>(a, ep, stream) : launch<128>(a, ep, stream);
   if (g_prof.on) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
   return e;

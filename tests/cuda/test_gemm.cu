@@ -192,6 +192,13 @@ int main(int argc, char** argv) {
       {1182 * 3 + 77, 768, 3072, 0, 1, 1, 0, 0, 0, 0, 0, 2},
       {100, 1536, 768, ACT_GELU_ERF, 1, 1, 0, 0, 0, 0, 0, 2},
       {1542 * 2, 1024, 640, 0, 1, 0, 0, 0, 0, 0, 0, 2},
+      // weight-streaming skinny kernel (bn == 1): M <= 8 decode rows
+      {1, 768, 768, 0, 1, 1, 0, 0, 0, 0, 1, 1},
+      {1, 30720, 768, 0, 1, 0, 0, 0, 0, 0, 1, 1},
+      {4, 3072, 768, ACT_GELU_ERF, 1, 0, 0, 0, 0, 0, 0, 1},
+      {4, 768, 3072, 0, 1, 1, 0, 0, 0, 0, 0, 1},
+      {3, 2304, 768, 0, 1, 0, 0, 0, 0, 0, 1, 1},
+      {8, 768, 3072, ACT_QUICK_GELU, 0, 1, 0, 0, 0, 0, 1, 1},
   };
   for (const Case& c : cases) fails += run_case(c);
   if (argc > 1 && fails == 0) {
@@ -206,6 +213,14 @@ int main(int argc, char** argv) {
     bench_case(8192, 8192, 8192, 256, 0, 0);
     bench_case(8192, 8192, 8192, 2, 0, 0);
     bench_case(64, 30720, 768, 128, 0, 0);
+    for (int m : {1, 4}) {
+      bench_case(m, 2304, 768, 1, 0, 0);
+      bench_case(m, 768, 768, 1, 0, 1);
+      bench_case(m, 3072, 768, 1, ACT_GELU_ERF, 0);
+      bench_case(m, 768, 3072, 1, 0, 1);
+      bench_case(m, 30720, 768, 1, 0, 0);
+      bench_case(m, 30720, 768, 128, 0, 0);
+    }
   }
   printf("test_gemm: %s (%d failing cases)\n", fails ? "FAILED" : "PASSED", fails);
   return fails ? 1 : 0;

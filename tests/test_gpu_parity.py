@@ -69,7 +69,7 @@ def setup(g):
 
 # ------------------------------------------------------------------------------------------ operators
 @pytest.mark.parametrize("M,N,K,act,tile", [(128, 128, 64, 0, 128), (300, 768, 768, 0, 0), (1182, 2304, 768, 0, 256),
-                                            (1182, 3072, 768, 1, 0), (777, 768, 3072, 2, 0), (5, 30720, 768, 0, 0)])
+                                            (1182, 3072, 768, 1, 0), (777, 768, 3072, 2, 0), (5, 30720, 768, 0, 0), (1, 768, 3072, 2, 1), (4, 30720, 768, 0, 0), (8, 3072, 768, 1, 0)])
 def test_op_gemm(g, M, N, K, act, tile):
     from importlib import import_module
     eng = import_module("real-time-video-captioning_b200.engine")
@@ -268,7 +268,8 @@ def test_step_api_and_generic_search_match_fused(g, setup):
     lo, vfs, hs = teacher.forward_output_logits(frames, y)
     assert lo[0].shape == (1, 5, 30522) and vfs[0].shape == (1, N_FRAMES * 197, 768) and hs[0].shape == (7, N_FRAMES * 197 + 5, 768)
     lo1, vf1, hs1 = m.forward_one_custom({"image": [frames[0, f][None].cuda() for f in range(N_FRAMES)], "caption_tokens": y[:1]})
-    assert torch.allclose(lo1.cpu(), lo[0].cpu(), atol=1e-3) and hs1.shape == hs[0].shape
+    # 5 rows take the weight-streaming skinny GEMM, 10 rows the tcgen05 tiles: same math, different summation order
+    assert torch.allclose(lo1.cpu(), lo[0].cpu(), atol=0.03) and hs1.shape == hs[0].shape
     # generate facade (inference.py:51 / real_time_inference.py:58 contract)
     gd = teacher.greedy_decode(frames, max_len=6)
     assert gd.shape == (2, 7) and (gd[:, 0] == cfg.sos_index).all()
