@@ -92,7 +92,8 @@ int gitb200_set_visual_features(gitb200_ctx* ctx, const float* visual_features_d
  * model.py:521 (kept on the device here). */
 int gitb200_decode(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev,
                    float* logits_dev, void* stream);
-/* encode + decode. */
+/* encode + decode.  For small batches (<= 8 clips) on a non-default stream, the second call with identical buffers,
+ * shapes and search parameters is captured into a CUDA graph and later identical calls replay it (latency mode). */
 int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
                     const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
                     void* stream);
@@ -142,6 +143,9 @@ int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, i
  * (enable != 0 resets the counters).  read: summed milliseconds, summed 2*M*N*K flops, launches. */
 void gitb200_profile_gemm(int enable);
 void gitb200_profile_gemm_read(double* ms, double* flops, long long* launches);
+
+/* Number of caption calls served by replaying the captured CUDA graph. */
+long long gitb200_graph_launches(const gitb200_ctx* ctx);
 
 /* Number of kernels this library has launched since the last call with reset != 0 (bench.py's gpu_launches). */
 long long gitb200_launch_count(int reset);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gitb200_op_search": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p,
                                   c_void_p]),
     "gitb200_launch_count": (c_longlong, [c_int]),
+    "gitb200_graph_launches": (c_longlong, [c_void_p]),
     "gitb200_profile_gemm": (None, [c_int]),
     "gitb200_profile_gemm_read": (None, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_longlong)]),
 }

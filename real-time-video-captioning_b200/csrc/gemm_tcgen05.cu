@@ -408,6 +408,8 @@ void gemm_profile_enable(int on) {
   g_prof.on = on != 0;
 }
 
+bool gemm_profile_enabled() { return g_prof.on; }
+
 void gemm_profile_read(double* ms, double* flops, long long* launches) {
   prof_drain();
   *ms = g_prof.ms;

@@ -37,6 +37,7 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn = 0);
 const char* gemm_last_error();
 // per-launch CUDA-event timing of the GEMM kernel (bench.py roofline): enable resets the counters
 void gemm_profile_enable(int on);
+bool gemm_profile_enabled();
 void gemm_profile_read(double* ms, double* flops, long long* launches);
 
 // out[r,:] = LN(x[r,:]) * gamma + beta (+ addend[((r / add_group) % add_period), :]); fp32 statistics.

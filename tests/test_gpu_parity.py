@@ -376,3 +376,39 @@ def test_git_large_vit_l14_matches_oracle(g):
                     se, so_ = norm_score(el[0].cpu(), hyp), norm_score(ol[0], hyp)
                     record("git_large_cross_score", clip=b, reorder=reorder, hyp=hyp.tolist(), engine=se, oracle=so_)
                     assert abs(se - so_) < 0.03, (hyp, se, so_)
+
+
+def test_cuda_graph_replay_equals_eager(g, setup):
+    """Latency mode: identical small-batch caption calls on a side stream are captured into a CUDA graph from the
+    second call on; the replays must return exactly what the eager launches returned, also after the frames change."""
+    import ctypes
+    cfg, sd, eng = setup[True]
+    frames = setup["frames"][:2].cuda().contiguous()
+    sp = g.SearchConfig(beam_size=4, max_steps=6)
+    ref_tok, ref_lp, _ = eng.caption(frames, sp)  # default stream: eager
+    tok = torch.empty_like(ref_tok)
+    lp = torch.empty_like(ref_lp)
+    side = torch.cuda.Stream()
+    c = sp.to_c()
+    before = eng.lib.gitb200_graph_launches(eng.h)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for i in range(5):
+            rc = eng.lib.gitb200_caption(eng.h, ctypes.c_void_p(frames.data_ptr()), 2, frames.shape[1], ctypes.byref(c),
+                                         ctypes.c_void_p(tok.data_ptr()), ctypes.c_void_p(lp.data_ptr()), None,
+                                         ctypes.c_void_p(side.cuda_stream))
+            assert rc == 0
+            side.synchronize()
+            assert torch.equal(tok, ref_tok) and torch.allclose(lp, ref_lp, atol=1e-6), i
+            tok.zero_()
+        assert eng.lib.gitb200_graph_launches(eng.h) - before >= 3
+        # new pixels in the same buffer: the graph must read them (it holds pointers, not data)
+        frames.copy_(setup["frames"][1:3].cuda())
+        side.wait_stream(torch.cuda.current_stream())
+        rc = eng.lib.gitb200_caption(eng.h, ctypes.c_void_p(frames.data_ptr()), 2, frames.shape[1], ctypes.byref(c),
+                                     ctypes.c_void_p(tok.data_ptr()), ctypes.c_void_p(lp.data_ptr()), None,
+                                     ctypes.c_void_p(side.cuda_stream))
+        assert rc == 0
+        side.synchronize()
+    ref2, ref2_lp, _ = eng.caption(setup["frames"][1:3].cuda().contiguous(), sp)
+    assert torch.equal(tok, ref2) and torch.allclose(lp, ref2_lp, atol=1e-6)
