@@ -121,6 +121,13 @@ int gitb200_decode_begin(gitb200_ctx* ctx, int rows_per_clip, void* stream);
 int gitb200_decode_step(gitb200_ctx* ctx, const int32_t* tokens_dev, int pos, float* logits_dev, void* stream);
 int gitb200_decode_reorder(gitb200_ctx* ctx, const int32_t* beam_idx_dev, int pos, void* stream);
 
+/* ---- frame preprocessing: image_transform(), src/utils/dataloader.py:18-32 (= real_time_inference.py:16-28) ----
+ * frames_dev: uint8 [n_frames, height, width, 3] in OpenCV's BGR HWC layout; out_dev: fp32 [n_frames, 3, size, size]
+ * (RGB, CLIP-normalised): bicubic resize of the smaller edge to `size` (no antialias, like the pinned torchvision
+ * 0.16 on tensors), centre crop, channel flip, normalise -- ready for gitb200_encode / gitb200_caption. */
+int gitb200_preprocess(const uint8_t* frames_dev, int n_frames, int height, int width, int size, float* out_dev,
+                       void* stream);
+
 /* ---- single operators (used by the parity tests; same kernels the pipeline launches) ---------- */
 /* out = act(A[M,K] * W[N,K]^T + bias) + residual; bf16 in/out (uint16 storage), fp32 bias. act: 0 none,
  * 1 QuickGELU, 2 erf-GELU.  tile_n: 0 auto, 128 or 256. */

@@ -7,7 +7,7 @@ farazali7/real-time-video-captioning, behind the reference's own Python model in
 
 All compute runs in libgitb200.so (include/gitb200.h); importing works without a GPU, running does not."""
 from ._lib import GitB200Error, LIB_PATH  # noqa: F401
-from .engine import Engine, SearchConfig, make_config, VIT_CONFIGS  # noqa: F401
+from .engine import Engine, SearchConfig, make_config, preprocess_frames, VIT_CONFIGS  # noqa: F401
 from .model import (BeamHypotheses, CLIPVisionTower, GenerativeImageTextModel, GenerativeImageTextTeacher,  # noqa: F401
                     GeneratorWithBeamSearchV2, LazyLogits, SyntheticTokenizer, TransformerDecoderTextualHead,
                     get_git_model)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "gitb200_decode_begin": (c_int, [c_void_p, c_int, c_void_p]),
     "gitb200_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gitb200_decode_reorder": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "gitb200_preprocess": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gitb200_op_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p]),
     "gitb200_op_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

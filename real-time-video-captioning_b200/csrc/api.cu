@@ -961,6 +961,13 @@ int gitb200_op_attention_groups_mma(const void* qkv, void* out, int n_groups, in
   return GITB200_OK;
 }
 
+int gitb200_preprocess(const uint8_t* frames, int n_frames, int height, int width, int size, float* out, void* stream) {
+  if (!frames || !out) return fail(nullptr, GITB200_ERR_INVALID, "bad preprocess argument");
+  cudaError_t e = preprocess_frames_u8(frames, n_frames, height, width, size, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "preprocess: %s", cudaGetErrorString(e));
+  return GITB200_OK;
+}
+
 int gitb200_op_search(const float* logits, int ld, int vocab, int n_clips, int sos, int eos, const gitb200_search_params* sp,
                       int32_t* tokens, float* logprobs, void* stream) {
   if (!logits || !sp || !tokens || !logprobs || n_clips < 1) return fail(nullptr, GITB200_ERR_INVALID, "bad op_search argument");

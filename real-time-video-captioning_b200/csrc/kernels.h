@@ -143,3 +143,7 @@ cudaError_t search_finalize(const SearchState& s, int* decoded, float* logprobs,
 cudaError_t fill_positions(int* pos, int* n_text, int rows, int L, cudaStream_t stream);
 // Step-wise decoding cache re-index: out[r][s] = in ? in[beam_idx[r]][s] : beam_idx[r] for s < pos; out[r][pos] = beam_idx[r].
 cudaError_t anc_reorder(const int* anc_in, int* anc_out, const int* beam_idx, int rows, int ld, int pos, cudaStream_t stream);
+
+// uint8 BGR HWC frames [n, H, W, 3] -> fp32 RGB NCHW [n, 3, size, size]: bicubic resize of the smaller edge to `size`,
+// centre crop, CLIP normalisation (the reference's image_transform(), src/utils/dataloader.py:18-32).
+cudaError_t preprocess_frames_u8(const uint8_t* frames, int n, int H, int W, int size, float* out, cudaStream_t stream);

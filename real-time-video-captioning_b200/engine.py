@@ -244,3 +244,16 @@ def op_search(logits: torch.Tensor, vocab: int, n_clips: int, sos: int, eos: int
     check(lib.gitb200_op_search(_ptr(logits), logits.shape[-1], vocab, n_clips, sos, eos, ctypes.byref(c), _ptr(tokens),
                                 _ptr(logprobs), s), None, "gitb200_op_search")
     return tokens, logprobs
+
+
+def preprocess_frames(frames_u8: torch.Tensor, size: int = 224) -> torch.Tensor:
+    """OpenCV frames uint8 [N, H, W, 3] (BGR, on the GPU) -> fp32 [N, 3, size, size] (RGB, CLIP-normalised): the
+    reference's image_transform() (src/utils/dataloader.py:18-32) as one CUDA kernel."""
+    lib = _lib.load()
+    assert frames_u8.is_cuda and frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[-1] == 3
+    frames_u8 = frames_u8.contiguous()
+    n, h, w, _ = frames_u8.shape
+    out = torch.empty(n, 3, size, size, dtype=torch.float32, device=frames_u8.device)
+    s = ctypes.c_void_p(torch.cuda.current_stream(frames_u8.device).cuda_stream)
+    check(lib.gitb200_preprocess(_ptr(frames_u8), n, h, w, size, _ptr(out), s), None, "gitb200_preprocess")
+    return out

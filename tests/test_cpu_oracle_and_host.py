@@ -225,3 +225,22 @@ def test_lazy_logits_and_tokenizer_and_shards():
     assert [g.shard_range(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
     tok, lp = g.caption_sharded(lambda b, e: (torch.arange(b, e).view(-1, 1, 1).int(), torch.arange(b, e).view(-1, 1).float()), 5)
     assert tok.flatten().tolist() == [0, 1, 2, 3, 4]
+
+
+# ------------------------------------------------------------------------------------------ preprocessing oracle
+@pytest.mark.parametrize("h,w", [(240, 320), (360, 640), (224, 224), (500, 300), (100, 180)])
+def test_preprocess_oracle_matches_torchvision_transforms(h, w):
+    """Pin oracle/preprocess_oracle.py against torchvision itself: the reference's Compose (dataloader.py:18-32) applied to
+    a tensor with the pinned torchvision 0.16 semantics (bicubic, antialias off)."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision.transforms import v2
+    from oracle import preprocess_oracle as po
+    frame = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(h * 1000 + w))
+    x = frame.permute(2, 0, 1).float() / 255.0                                                     # ToTensor
+    x = v2.functional.resize(x, [224], interpolation=v2.InterpolationMode.BICUBIC, antialias=False)  # Resize(224, BICUBIC)
+    x = v2.functional.center_crop(x, [224, 224])                                                   # CenterCrop(224)
+    x = x[[2, 1, 0], ...]                                                                          # BGR2RGBTransform
+    x = v2.functional.normalize(x, po.CLIP_MEAN, po.CLIP_STD)                                      # Normalize
+    got = po.preprocess_frames(frame[None])[0]
+    assert got.shape == x.shape == (3, 224, 224)
+    assert torch.allclose(got, x, atol=1e-5, rtol=1e-5), (got - x).abs().max()

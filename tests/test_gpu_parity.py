@@ -412,3 +412,29 @@ def test_cuda_graph_replay_equals_eager(g, setup):
         side.synchronize()
     ref2, ref2_lp, _ = eng.caption(setup["frames"][1:3].cuda().contiguous(), sp)
     assert torch.equal(tok, ref2) and torch.allclose(lp, ref2_lp, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 240, 320), (1, 360, 640), (3, 224, 224), (1, 500, 300), (2, 100, 180), (1, 1080, 1920)])
+def test_preprocess_kernel_matches_oracle(g, n, h, w):
+    """gitb200_preprocess == the reference's image_transform() (dataloader.py:18-32) restated in oracle/preprocess_oracle.py
+    (itself pinned against torchvision on CPU).  fp32 both sides: only FMA contraction / summation order differ."""
+    from oracle import preprocess_oracle as po
+    frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(h + w))
+    out = g.preprocess_frames(frames.cuda()).cpu()
+    ref = po.preprocess_frames(frames)
+    err = (out - ref).abs().max().item()
+    record("preprocess", h=h, w=w, max_err=err)
+    assert out.shape == (n, 3, 224, 224) and err < 2e-5, err
+
+
+def test_preprocess_feeds_the_encoder(g, setup):
+    """uint8 webcam-style frames -> preprocess kernel -> caption == caption of the oracle-preprocessed fp32 frames."""
+    from oracle import preprocess_oracle as po
+    cfg, sd, eng = setup[True]
+    raw = torch.randint(0, 256, (2 * N_FRAMES, 240, 320, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(9))
+    a = g.preprocess_frames(raw.cuda()).view(2, N_FRAMES, 3, 224, 224)
+    b = po.preprocess_frames(raw).view(2, N_FRAMES, 3, 224, 224).cuda()
+    sp = g.SearchConfig(beam_size=1, max_steps=6)
+    ta, la, _ = eng.caption(a.contiguous(), sp)
+    tb, lb, _ = eng.caption(b.contiguous(), sp)
+    assert torch.equal(ta, tb) and torch.allclose(la, lb, atol=1e-3)
