@@ -128,6 +128,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=3, help="clips timed for the cpu_baseline leg")
     ap.add_argument("--chunk", type=int, default=64, help="clips per host->device chunk on the e2e path")
+    ap.add_argument("--pipeline", type=int, default=0, help="clips per chunk of the two-stream encode/decode pipeline (0 off, -1 auto)")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     args = ap.parse_args()
 
@@ -137,6 +138,7 @@ def main():
     config = {"workload": "GIT-base (CLIP ViT-B/16 + 6-layer prefix-LM decoder) batched greedy caption, 6x224x224 synthetic clips",
               "clips_per_gpu_per_step": args.batch, "frames": FRAMES, "beam_size": args.beam, "max_steps": args.max_steps,
               "weights": "random-init (seeded)", "parallelism": f"clip-sharded dp{world}",
+              "pipeline": "two-stream chunk pipeline, auto chunk (batch/4 in [32,128])" if args.pipeline < 0 else (f"chunks of {args.pipeline}" if args.pipeline else "off"),
               "l2": f"no flush: every step streams >{args.batch * 60 // 1000} GB of activations and a {args.batch * 3.6128:.0f} MB frame batch (L2 = 126 MB)"}
 
     if args.impl == "reference":
@@ -174,7 +176,9 @@ def main():
     del sd
     sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
     B = args.batch
-    eng.reserve(B, FRAMES, args.beam, args.max_steps)
+    eng.set_pipeline(args.pipeline)
+    if args.pipeline == 0:
+        eng.reserve(B, FRAMES, args.beam, args.max_steps)
 
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     n_sets = 2  # alternate between resident frame batches

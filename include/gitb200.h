@@ -97,6 +97,13 @@ int gitb200_decode(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* t
 int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
                     const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
                     void* stream);
+/* Opt-in large-batch pipelining of gitb200_caption / gitb200_caption_host: clips per chunk (0 = off, the default;
+ * -1 = automatic: a quarter of the batch clamped to [32, 128]).  Chunks alternate between two internal streams / workspace sets so that one
+ * chunk's decode steps overlap the next chunk's ViT.  When a call is pipelined, the context does not keep the visual
+ * features of the whole batch resident afterwards.  Measured SLOWER than the single-stream schedule on B200 (kernel-
+ * granularity interleaving stretches the latency-bound decode chain behind 100-250 us GEMM kernels): kept for experiments. */
+int gitb200_set_pipeline(gitb200_ctx* ctx, int chunk_clips);
+
 /* Same with HOST buffers (frames_host should be pinned for full PCIe speed): chunks of `chunk_clips`
  * clips are copied host->device on a side stream while the previous chunk computes; tokens and
  * logprobs are copied back; returns after everything has completed (synchronous). */

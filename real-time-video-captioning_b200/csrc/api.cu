@@ -112,6 +112,15 @@ struct gitb200_ctx {
   bool graphs_enabled = true;
   long long graph_launches = 0;
 
+  // Two-stream chunk pipeline for large batches: chunk i runs encode + decode on stream i & 1 with workspace set
+  // i & 1 (this context / its twin, which shares the weights), offset by one phase so that the HBM / latency bound
+  // decode of one chunk overlaps the tensor bound encode of the next.
+  gitb200_ctx* twin = nullptr;
+  bool is_twin = false;
+  int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_enc0 = nullptr, ev_join[2] = {nullptr, nullptr};
+
   // current state
   int cur_clips = 0, cur_nv = 0;     // visual features held in vf
   int step_rows_per_clip = 0;        // step-wise decoding state
@@ -505,6 +514,84 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
   return 0;
 }
 
+void free_workspaces(gitb200_ctx* c) {
+  auto fr = [](auto& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
+  fr(c->patches); fr(c->x); fr(c->lnb); fr(c->qkv); fr(c->attn); fr(c->mlp); fr(c->vf); fr(c->hv); fr(c->hvb); fr(c->hvc);
+  fr(c->vattn); fr(c->vmlp);
+  for (auto& b : c->kv) fr(b);
+  for (auto& b : c->txt_kv) fr(b);
+  fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
+  fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
+  fr(c->out_tok); fr(c->out_lp);
+}
+
+// second workspace set that shares this context's (read-only) weights
+gitb200_ctx* make_twin(gitb200_ctx* c) {
+  gitb200_ctx* t = new gitb200_ctx();
+  t->cfg = c->cfg; t->device = c->device; t->finalized = true; t->is_twin = true; t->graphs_enabled = false; t->pipeline_chunk = 0;
+  t->T = c->T; t->kpad = c->kpad; t->vocab_pad = c->vocab_pad; t->n_temporal = c->n_temporal;
+  t->w_patch = c->w_patch; t->pos_bf16 = c->pos_bf16; t->cls = c->cls; t->ln_pre_g = c->ln_pre_g; t->ln_pre_b = c->ln_pre_b;
+  t->ln_post_g = c->ln_post_g; t->ln_post_b = c->ln_post_b; t->temporal = c->temporal; t->vit = c->vit;
+  t->w_proj = c->w_proj; t->b_proj = c->b_proj; t->lnp_g = c->lnp_g; t->lnp_b = c->lnp_b;
+  t->words_f32 = c->words_f32; t->pos_f32 = c->pos_f32; t->lne_g = c->lne_g; t->lne_b = c->lne_b; t->dec = c->dec;
+  t->w_vocab = c->w_vocab; t->b_vocab = c->b_vocab;
+  return t;
+}
+
+int ensure_pipeline(gitb200_ctx* c) {
+  if (!c->twin) c->twin = make_twin(c);
+  if (!c->pipe_stream[0]) {
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_enc0, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int pipeline_chunk_for(const gitb200_ctx* c, int n_clips) {
+  if (c->pipeline_chunk == 0 || c->is_twin) return 0;
+  int chunk = c->pipeline_chunk > 0 ? c->pipeline_chunk : (n_clips + 3) / 4;
+  if (c->pipeline_chunk < 0) {
+    if (chunk < 32) chunk = 32;
+    if (chunk > 128) chunk = 128;
+  }
+  return n_clips >= 2 * chunk ? chunk : 0;
+}
+
+// Device-resident frames, chunk pipeline on the two internal streams, joined back into `caller`.
+int caption_pipelined(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, const gitb200_search_params& sp,
+                      int32_t* tokens, float* logprobs, cudaStream_t caller, int chunk) {
+  TRY(ensure_pipeline(c));
+  const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
+  const int per_clip_tok = sp.num_keep_best * sp.max_steps;
+  CUDA_OK(c, cudaEventRecord(c->ev_fork, caller));
+  for (int i = 0; i < 2; ++i) CUDA_OK(c, cudaStreamWaitEvent(c->pipe_stream[i], c->ev_fork, 0));
+  int done = 0;
+  for (int i = 0; done < n_clips; ++i) {
+    const int w = i & 1;
+    gitb200_ctx* cw = w ? c->twin : c;
+    cudaStream_t s = c->pipe_stream[w];
+    const int nc = (n_clips - done) < chunk ? (n_clips - done) : chunk;
+    if (i == 1) CUDA_OK(c, cudaStreamWaitEvent(s, c->ev_enc0, 0));  // one phase behind: its encode meets chunk 0's decode
+    int r = run_encode(cw, frames + (size_t)done * clip_elems, nc, n_frames, s);
+    if (r == 0 && i == 0) CUDA_OK(c, cudaEventRecord(c->ev_enc0, s));
+    if (r == 0) r = run_decode(cw, sp, tokens + (size_t)done * per_clip_tok, logprobs + (size_t)done * sp.num_keep_best, nullptr, s);
+    if (r) {
+      if (w) c->err = c->twin->err;
+      return r;
+    }
+    done += nc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    CUDA_OK(c, cudaEventRecord(c->ev_join[i], c->pipe_stream[i]));
+    CUDA_OK(c, cudaStreamWaitEvent(caller, c->ev_join[i], 0));
+  }
+  return 0;
+}
+
 }  // namespace
 
 // ==================================================================== C ABI
@@ -566,14 +653,17 @@ void gitb200_destroy(gitb200_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& kv : c->raw) cudaFree(kv.second.p);
   for (void* p : c->weight_allocs) cudaFree(p);
-  auto fr = [](auto& b) { if (b.p) cudaFree(b.p); };
-  fr(c->patches); fr(c->x); fr(c->lnb); fr(c->qkv); fr(c->attn); fr(c->mlp); fr(c->vf); fr(c->hv); fr(c->hvb); fr(c->hvc);
-  fr(c->vattn); fr(c->vmlp);
-  for (auto& b : c->kv) fr(b);
-  for (auto& b : c->txt_kv) fr(b);
-  fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
-  fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
-  fr(c->out_tok); fr(c->out_lp);
+  free_workspaces(c);
+  if (c->twin) {
+    free_workspaces(c->twin);
+    delete c->twin;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (c->pipe_stream[i]) cudaStreamDestroy(c->pipe_stream[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_enc0) cudaEventDestroy(c->ev_enc0);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
@@ -804,7 +894,20 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
     c->graphs_enabled = false;
   }
   c->last_key = key;
+  if (logits == nullptr && frames && tokens && logprobs && c->finalized && n_clips > 0 && n_frames > 0) {
+    const int chunk = pipeline_chunk_for(c, n_clips);
+    if (chunk > 0) {
+      CUDA_OK(c, cudaSetDevice(c->device));
+      return caption_pipelined(c, frames, n_clips, n_frames, *sp, tokens, logprobs, s, chunk);
+    }
+  }
   return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream);
+}
+
+int gitb200_set_pipeline(gitb200_ctx* c, int chunk_clips) {
+  if (!c) return GITB200_ERR_INVALID;
+  c->pipeline_chunk = chunk_clips;
+  return GITB200_OK;
 }
 
 int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
@@ -829,26 +932,56 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
   for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
-  // Encode chunk by chunk as the frames arrive (copy of chunk i+1 overlaps the ViT of chunk i; a small first chunk
-  // keeps the un-overlapped head of the transfer short), then run the decoder once over all clips: the decode steps
-  // have a fixed cost per launch that is amortised over the whole batch.
-  int done = 0, ch = 0;
-  while (done < n_clips) {
-    const int b = ch & 1;
-    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
-    if (nc > n_clips - done) nc = n_clips - done;
-    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
-    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
-    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-    int r = run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips);
-    if (r) return r;
-    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
-    done += nc;
-    ++ch;
-  }
-  {
+  if (c->pipeline_chunk != 0) {
+    // opt-in two-stream variant: chunk i is copied, then encoded + decoded on pipeline stream i & 1 (workspace set i & 1)
+    TRY(ensure_pipeline(c));
+    int done = 0;
+    for (int ch = 0; done < n_clips; ++ch) {
+      const int b = ch & 1;
+      gitb200_ctx* cw = b ? c->twin : c;
+      cudaStream_t s = c->pipe_stream[b];
+      int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+      if (nc > n_clips - done) nc = n_clips - done;
+      if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
+      CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+      CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+      CUDA_OK(c, cudaStreamWaitEvent(s, c->ev_copy[b], 0));
+      if (ch == 1) CUDA_OK(c, cudaStreamWaitEvent(s, c->ev_enc0, 0));
+      int r = run_encode(cw, c->stage[b].p, nc, n_frames, s);
+      if (r == 0) CUDA_OK(c, cudaEventRecord(c->ev_done[b], s));
+      if (r == 0 && ch == 0) CUDA_OK(c, cudaEventRecord(c->ev_enc0, s));
+      if (r == 0) r = run_decode(cw, *sp, c->out_tok.p + (size_t)done * per_clip_tok, c->out_lp.p + (size_t)done * sp->num_keep_best, nullptr, s);
+      if (r) {
+        if (b) c->err = c->twin->err;
+        return r;
+      }
+      done += nc;
+    }
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaEventRecord(c->ev_join[i], c->pipe_stream[i]));
+      CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_join[i], 0));
+    }
+  } else {
+    // Encode chunk by chunk as the frames arrive (copy of chunk i+1 overlaps the ViT of chunk i; a small first chunk
+    // keeps the un-overlapped head of the transfer short), then run the decoder once over all clips: the decode steps
+    // have a fixed cost per launch that is amortised over the whole batch.
+    int done = 0, ch = 0;
+    while (done < n_clips) {
+      const int b = ch & 1;
+      int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+      if (nc > n_clips - done) nc = n_clips - done;
+      if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
+      CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+      CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+      CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
+      int r = run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips);
+      if (r) return r;
+      CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+      done += nc;
+      ++ch;
+    }
     int r = run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp);
     if (r) return r;
   }

@@ -192,6 +192,10 @@ class Engine:
         idx = beam_idx.to(device=self.device, dtype=torch.int32).contiguous()
         check(self.lib.gitb200_decode_reorder(self.h, _ptr(idx), pos, self._stream()), self.h, "gitb200_decode_reorder")
 
+    def set_pipeline(self, chunk_clips: int) -> None:
+        """Clips per chunk of the two-stream encode/decode pipeline (0 = off, -1 = automatic)."""
+        check(self.lib.gitb200_set_pipeline(self.h, chunk_clips), self.h, "gitb200_set_pipeline")
+
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.gitb200_launch_count(1 if reset else 0))
 
