@@ -97,6 +97,14 @@ int gitb200_decode(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* t
 int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
                     const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
                     void* stream);
+/* Opt-in (default off): ViT ln_1 / ln_2 folded into the following QKV / fc1 GEMM: the GEMM reads the raw residual stream, its
+ * weights carry gamma, its bias carries W*beta, and its epilogue applies rstd*(acc - mean*colsum) from row statistics
+ * emitted by the previous residual GEMM's epilogue.  0 restores the separate LayerNorm kernels (same result within the
+ * bf16 tolerance; the folded form skips one bf16 rounding of the normalised activations).  Measured on B200: the 24
+ * LayerNorm launches disappear (4.5 % of the step) but the heavier GEMM epilogues give most of it back (+1 % net), and
+ * the atomically accumulated statistics make results run-to-run non-bit-exact, hence off by default. */
+int gitb200_set_fold_layernorm(gitb200_ctx* ctx, int enable);
+
 /* Opt-in large-batch pipelining of gitb200_caption / gitb200_caption_host: clips per chunk (0 = off, the default;
  * -1 = automatic: a quarter of the batch clamped to [32, 128]).  Chunks alternate between two internal streams / workspace sets so that one
  * chunk's decode steps overlap the next chunk's ViT.  When a call is pipelined, the context does not keep the visual

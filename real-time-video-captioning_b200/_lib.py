@@ -50,6 +50,7 @@ SIGNATURES = {
     "gitb200_decode": (c_int, [c_void_p, POINTER(SearchParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gitb200_caption": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "gitb200_set_fold_layernorm": (c_int, [c_void_p, c_int]),
     "gitb200_set_pipeline": (c_int, [c_void_p, c_int]),
     "gitb200_caption_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p]),
     "gitb200_forward_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

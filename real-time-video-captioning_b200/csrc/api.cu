@@ -45,6 +45,9 @@ struct DevF32 {
 struct VitLayer {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc1, *b_fc2;
   bf16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+  // ln_1 folded into the QKV projection and ln_2 into fc1 (W * diag(gamma), bias + W beta, column sums of W')
+  bf16 *wf_qkv, *wf_fc1;
+  float *bf_qkv, *bf_fc1, *cs_qkv, *cs_fc1;
 };
 struct DecLayer {
   float *b_qkv, *b_out, *lna_g, *lna_b, *b_fc1, *b_fc2, *lno_g, *lno_b;
@@ -87,7 +90,7 @@ struct gitb200_ctx {
   std::vector<Buf<bf16>> kv;      // per decoder layer: [n_clips*Nv, 3H]
   std::vector<Buf<bf16>> txt_kv;  // per decoder layer: [max_len][rows][2H]
   Buf<bf16> tx, tq, ta, tb, tc, tf;
-  Buf<float> logits, partial, vf_in_f32;
+  Buf<float> logits, partial, vf_in_f32, stats_a, stats_b;  // stats_*: [rows, 2] row sums for the folded LayerNorms
   Buf<int> ibuf;       // search ints
   Buf<double> dbuf;    // search doubles
   Buf<float> fbuf;     // search floats
@@ -117,6 +120,8 @@ struct gitb200_ctx {
   // decode of one chunk overlaps the tensor bound encode of the next.
   gitb200_ctx* twin = nullptr;
   bool is_twin = false;
+  bool fold_ln = false;     // opt-in: ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); +1 % measured, and the
+                            // atomically accumulated row statistics make results run-to-run non-bit-exact -> default off
   int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_enc0 = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -265,12 +270,50 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   }
   CUDA_OK(c, write_cls_rows(c->cls, c->pos_bf16, n_clips * F, T, W, c->x.p, s));
   // ln_pre (in place semantics: x <- ln_pre(x)); the residual stream starts from the normalised tokens
-  TRY(ln(c, c->x.p, rows, W, c->ln_pre_g, c->ln_pre_b, k.vit_ln_eps, c->lnb.p, s));
+  const bool fold = c->fold_ln && rows >= 1024;  // the folded-LayerNorm epilogue lives in the CTA-pair GEMM
+  if (fold) {
+    ENSURE(c, c->stats_a, (size_t)rows * 2);
+    ENSURE(c, c->stats_b, (size_t)rows * 2);
+  }
+  {
+    LayerNormArgs a;
+    a.x = c->x.p; a.ldx = W; a.rows = rows; a.cols = W; a.gamma = c->ln_pre_g; a.beta = c->ln_pre_b; a.eps = k.vit_ln_eps;
+    a.out = c->lnb.p; a.ldo = W; a.stats_out = fold ? c->stats_a.p : nullptr;
+    CUDA_OK(c, layernorm_bf16(a, s));
+  }
   std::swap(c->x.p, c->lnb.p);
   std::swap(c->x.cap, c->lnb.cap);
   const float scale = 1.0f / sqrtf((float)(W / k.vit_heads));
   for (int l = 0; l < k.vit_layers; ++l) {
     const VitLayer& L = c->vit[l];
+    if (fold) {
+      // ln_1 and ln_2 never materialise: the QKV / fc1 GEMMs read the raw residual stream and normalise in their
+      // epilogue from the row statistics the previous residual GEMM (or ln_pre) produced.
+      {
+        GemmArgs g = linear(c->x.p, W, L.wf_qkv, W, rows, 3 * W, L.bf_qkv, c->qkv.p, 3 * W);
+        g.ln_stats = c->stats_a.p; g.ln_colsum = L.cs_qkv; g.ln_eps = k.vit_ln_eps;
+        TRY(gemm(c, g, s));
+      }
+      CUDA_OK(c, attention_groups_tc(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
+      CUDA_OK(c, cudaMemsetAsync(c->stats_b.p, 0, (size_t)rows * 2 * sizeof(float), s));
+      {
+        GemmArgs g = linear(c->attn.p, W, L.w_out, W, rows, W, L.b_out, c->x.p, W);
+        g.residual = c->x.p; g.ldr = W; g.stats_out = c->stats_b.p;
+        TRY(gemm(c, g, s));
+      }
+      {
+        GemmArgs g = linear(c->x.p, W, L.wf_fc1, W, rows, 4 * W, L.bf_fc1, c->mlp.p, 4 * W);
+        g.act = ACT_QUICK_GELU; g.ln_stats = c->stats_b.p; g.ln_colsum = L.cs_fc1; g.ln_eps = k.vit_ln_eps;
+        TRY(gemm(c, g, s));
+      }
+      CUDA_OK(c, cudaMemsetAsync(c->stats_a.p, 0, (size_t)rows * 2 * sizeof(float), s));
+      {
+        GemmArgs g = linear(c->mlp.p, 4 * W, L.w_fc2, 4 * W, rows, W, L.b_fc2, c->x.p, W);
+        g.residual = c->x.p; g.ldr = W; g.stats_out = c->stats_a.p;
+        TRY(gemm(c, g, s));
+      }
+      continue;
+    }
     TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
     TRY(gemm(c, linear(c->lnb.p, W, L.w_qkv, W, rows, 3 * W, L.b_qkv, c->qkv.p, 3 * W), s));
     CUDA_OK(c, attention_groups_tc(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
@@ -522,13 +565,14 @@ void free_workspaces(gitb200_ctx* c) {
   for (auto& b : c->txt_kv) fr(b);
   fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
   fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
-  fr(c->out_tok); fr(c->out_lp);
+  fr(c->out_tok); fr(c->out_lp); fr(c->stats_a); fr(c->stats_b);
 }
 
 // second workspace set that shares this context's (read-only) weights
 gitb200_ctx* make_twin(gitb200_ctx* c) {
   gitb200_ctx* t = new gitb200_ctx();
   t->cfg = c->cfg; t->device = c->device; t->finalized = true; t->is_twin = true; t->graphs_enabled = false; t->pipeline_chunk = 0;
+  t->fold_ln = c->fold_ln;
   t->T = c->T; t->kpad = c->kpad; t->vocab_pad = c->vocab_pad; t->n_temporal = c->n_temporal;
   t->w_patch = c->w_patch; t->pos_bf16 = c->pos_bf16; t->cls = c->cls; t->ln_pre_g = c->ln_pre_g; t->ln_pre_b = c->ln_pre_b;
   t->ln_post_g = c->ln_post_g; t->ln_post_b = c->ln_post_b; t->temporal = c->temporal; t->vit = c->vit;
@@ -723,6 +767,14 @@ int gitb200_finalize_weights(gitb200_ctx* c) {
     TRY(to_f32(c, b + "mlp.c_fc.bias", 4 * W, 4 * W, &L.b_fc1));
     TRY(to_bf16(c, b + "mlp.c_proj.weight", W, 4 * W, W, 4 * W, &L.w_fc2));
     TRY(to_f32(c, b + "mlp.c_proj.bias", W, W, &L.b_fc2));
+    TRY(walloc(c, &L.wf_qkv, (size_t)3 * W * W));
+    TRY(walloc(c, &L.bf_qkv, (size_t)3 * W));
+    TRY(walloc(c, &L.cs_qkv, (size_t)3 * W));
+    TRY(walloc(c, &L.wf_fc1, (size_t)4 * W * W));
+    TRY(walloc(c, &L.bf_fc1, (size_t)4 * W));
+    TRY(walloc(c, &L.cs_fc1, (size_t)4 * W));
+    CUDA_OK(c, ln_fold_weight(find(c, b + "attn.in_proj_weight")->p, 3 * W, W, L.ln1_g, L.ln1_b, L.b_qkv, L.wf_qkv, L.cs_qkv, L.bf_qkv, 0));
+    CUDA_OK(c, ln_fold_weight(find(c, b + "mlp.c_fc.weight")->p, 4 * W, W, L.ln2_g, L.ln2_b, L.b_fc1, L.wf_fc1, L.cs_fc1, L.bf_fc1, 0));
   }
   if (c->n_temporal > 0) {
     TRY(walloc(c, &c->temporal, (size_t)c->n_temporal * W));
@@ -902,6 +954,13 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
     }
   }
   return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream);
+}
+
+int gitb200_set_fold_layernorm(gitb200_ctx* c, int enable) {
+  if (!c) return GITB200_ERR_INVALID;
+  c->fold_ln = enable != 0;
+  if (c->twin) c->twin->fold_ln = c->fold_ln;
+  return GITB200_OK;
 }
 
 int gitb200_set_pipeline(gitb200_ctx* c, int chunk_clips) {

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LayerNormArgs a) {
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)a.cols + a.eps);
   const float* add = a.addend ? a.addend + (size_t)((warp / a.add_group) % a.add_period) * a.cols : nullptr;
+  float st1 = 0.f, st2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VECS; ++i) {
     const int c = (i * 32 + lane) * 8;
@@ -59,12 +60,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LayerNormArgs a) {
       uint4 u;
       u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
       *reinterpret_cast<uint4*>(a.out + (size_t)warp * a.ldo + c) = u;
+      if (a.stats_out) {
+        const float2 r0 = unpack_bf16(u.x), r1 = unpack_bf16(u.y), r2 = unpack_bf16(u.z), r3 = unpack_bf16(u.w);
+        st1 += (r0.x + r0.y) + (r1.x + r1.y) + (r2.x + r2.y) + (r3.x + r3.y);
+        st2 += r0.x * r0.x + r0.y * r0.y + r1.x * r1.x + r1.y * r1.y + r2.x * r2.x + r2.y * r2.y + r3.x * r3.x + r3.y * r3.y;
+      }
     }
     if (a.out_f32) {
       float4* p = reinterpret_cast<float4*>(a.out_f32 + (size_t)warp * a.ldo32 + c);
       p[0] = make_float4(o[0], o[1], o[2], o[3]);
       p[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
+  }
+  if (a.stats_out) {
+    st1 = warp_sum(st1);
+    st2 = warp_sum(st2);
+    if (lane == 0) {
+      a.stats_out[2 * (size_t)warp] = st1;
+      a.stats_out[2 * (size_t)warp + 1] = st2;
+    }
+  }
+}
+
+// one warp per output row n: fold gamma into the weights, beta into the bias, and compute the column sums
+__global__ void ln_fold_weight_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ bias, bf16* __restrict__ wf,
+                                      float* __restrict__ colsum, float* __restrict__ bias_f) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[(size_t)n * K + k];
+    const bf16 r = __float2bfloat16(wv * gamma[k]);
+    wf[(size_t)n * K + k] = r;
+    cs += __bfloat162float(r);
+    bs += wv * beta[k];
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = bias[n] + bs;
   }
 }
 
@@ -196,6 +233,14 @@ __global__ void fill_positions_kernel(int* pos, int* n_text, int rows, int L) {
 cudaError_t fill_positions(int* pos, int* n_text, int rows, int L, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   fill_positions_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(pos, n_text, rows, L);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t ln_fold_weight(const float* w, int N, int K, const float* gamma, const float* beta, const float* bias, bf16* wf,
+                           float* colsum, float* bias_f, cudaStream_t stream) {
+  if (N <= 0) return cudaSuccess;
+  ln_fold_weight_kernel<<<(N * 32 + 255) / 256, 256, 0, stream>>>(w, N, K, gamma, beta, bias, wf, colsum, bias_f);
   note_launch();
   return cudaGetLastError();
 }

@@ -44,6 +44,10 @@ struct Epi2 {
   const float* bias;
   int act;
   int has_res;
+  const float* ln_stats;   // folded LayerNorm on the A rows: (sum, sum of squares) per row, or nullptr
+  const float* ln_colsum;  // [N]
+  float ln_inv_k, ln_eps;
+  float* stats_out;        // (sum, sum of squares) of the output rows, accumulated with atomics, or nullptr
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -222,6 +226,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+      const int my_row = row0 + lane;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (ep.ln_stats != nullptr && my_row < M) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + my_row);
+        ln_mean = st.x * ep.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(st.y * ep.ln_inv_k - ln_mean * ln_mean, 0.f) + ep.ln_eps);
+      }
+      float so1 = 0.f, so2 = 0.f;
       if (row0 < M) {  // warp-uniform: this warp's 32 rows are not entirely beyond M
 #pragma unroll 1
         for (int c = c_begin; c < c_end; c += EPI_COLS) {
@@ -245,6 +257,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
+            if (ep.ln_stats != nullptr) {  // rstd * (acc - mean * colsum[n])
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + j * 8));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + j * 8 + 4));
+              const float nm = -ln_mean;
+              f[0] = fmaf(nm, c0.x, f[0]) * ln_rstd; f[1] = fmaf(nm, c0.y, f[1]) * ln_rstd;
+              f[2] = fmaf(nm, c0.z, f[2]) * ln_rstd; f[3] = fmaf(nm, c0.w, f[3]) * ln_rstd;
+              f[4] = fmaf(nm, c1.x, f[4]) * ln_rstd; f[5] = fmaf(nm, c1.y, f[5]) * ln_rstd;
+              f[6] = fmaf(nm, c1.z, f[6]) * ln_rstd; f[7] = fmaf(nm, c1.w, f[7]) * ln_rstd;
+            }
             if (ep.bias != nullptr) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8 + 4));
@@ -268,6 +289,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
             const uint32_t p0 = pack_bf16(f[0], f[1]), p1 = pack_bf16(f[2], f[3]), p2 = pack_bf16(f[4], f[5]), p3 = pack_bf16(f[6], f[7]);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            if (ep.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
+              const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1), r2 = unpack_bf16(p2), r3 = unpack_bf16(p3);
+              so1 += (r0.x + r0.y) + (r1.x + r1.y) + (r2.x + r2.y) + (r3.x + r3.y);
+              so2 = fmaf(r0.x, r0.x, so2); so2 = fmaf(r0.y, r0.y, so2); so2 = fmaf(r1.x, r1.x, so2); so2 = fmaf(r1.y, r1.y, so2);
+              so2 = fmaf(r2.x, r2.x, so2); so2 = fmaf(r2.y, r2.y, so2); so2 = fmaf(r3.x, r3.x, so2); so2 = fmaf(r3.y, r3.y, so2);
+            }
           }
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
@@ -276,6 +303,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             ptx::tma_store_commit();
           }
         }
+      }
+      if (ep.stats_out != nullptr && my_row < M) {
+        atomicAdd(ep.stats_out + 2 * (size_t)my_row, so1);
+        atomicAdd(ep.stats_out + 2 * (size_t)my_row + 1, so2);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -314,7 +345,7 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
   int clusters = gemm_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0};
+  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out};
   gemm2_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
   note_launch();
   return cudaGetLastError();

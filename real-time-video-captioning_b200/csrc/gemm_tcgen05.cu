@@ -441,7 +441,13 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     cudaEventRecord(g_prof.ev[2 * slot], stream);
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (force_bn == 1 || (force_bn == 0 && a.M <= 8)) e = gemv_skinny(a, stream);  // weight-streaming path for a few rows
+  if (a.ln_stats != nullptr || a.stats_out != nullptr) {  // only the CTA-pair kernel implements the folded LayerNorm
+    e = gemm2_bf16(a, stream);
+    if (e == cudaErrorNotSupported) {
+      g_err = "gemm_bf16: folded LayerNorm / row statistics need the CTA-pair kernel (N % 256 == 0, bf16 output, no remap)";
+      e = cudaErrorInvalidValue;
+    }
+  } else if (force_bn == 1 || (force_bn == 0 && a.M <= 8)) e = gemv_skinny(a, stream);  // weight-streaming path for a few rows
   else if (bn == 2) e = gemm2_bf16(a, stream);
   if (e == cudaErrorNotSupported) e = (bn != 128 && a.N % 256 == 0) ? launch<256>(a, ep, stream) : launch<128>(a, ep, stream);
   if (g_prof.on) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);

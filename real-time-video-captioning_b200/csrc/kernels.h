@@ -31,6 +31,15 @@ struct GemmArgs {
   // Output row remap: out_row = (r / gin) * gout + (r % gin) + goff when gin > 0 (used to leave a
   // gap for the CLS row of every frame in the patch-embedding GEMM).
   int gin = 0, gout = 0, goff = 0;
+  // LayerNorm folded into this GEMM (pre-LN blocks): A holds the UN-normalised rows x, W already carries gamma
+  // (W' = W * diag(gamma)), bias already carries W * beta, and the epilogue applies
+  //     rstd_r * (acc - mean_r * ln_colsum[n]) + bias[n]      with (sum, sum of squares) of row r in ln_stats[2r..2r+1].
+  const float* ln_stats = nullptr;   // [M, 2] fp32
+  const float* ln_colsum = nullptr;  // [N] fp32: sum_k W'[n, k]
+  float ln_eps = 1e-5f;
+  // Optional: accumulate (sum, sum of squares) of every OUTPUT row (bf16-rounded values) into stats_out[2r..2r+1]
+  // with atomics -- the statistics the next folded LayerNorm needs.  Must be zeroed by the caller.
+  float* stats_out = nullptr;
 };
 // force_bn: 0 = heuristic, 128 or 256 = tile width override (tests / tuning).
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn = 0);
@@ -54,6 +63,7 @@ struct LayerNormArgs {
   int ldo = 0;
   float* out_f32 = nullptr;  // optional fp32 copy
   int ldo32 = 0;
+  float* stats_out = nullptr;  // optional [rows, 2]: (sum, sum of squares) of the bf16-rounded output row (plain store)
 };
 cudaError_t layernorm_bf16(const LayerNormArgs& a, cudaStream_t stream);
 
@@ -147,3 +157,8 @@ cudaError_t anc_reorder(const int* anc_in, int* anc_out, const int* beam_idx, in
 // uint8 BGR HWC frames [n, H, W, 3] -> fp32 RGB NCHW [n, 3, size, size]: bicubic resize of the smaller edge to `size`,
 // centre crop, CLIP normalisation (the reference's image_transform(), src/utils/dataloader.py:18-32).
 cudaError_t preprocess_frames_u8(const uint8_t* frames, int n, int H, int W, int size, float* out, cudaStream_t stream);
+
+// LayerNorm folding at weight-load time: wf[n,k] = bf16(w[n,k] * gamma[k]); colsum[n] = sum_k float(wf[n,k]);
+// bias_f[n] = bias[n] + sum_k w[n,k] * beta[k].
+cudaError_t ln_fold_weight(const float* w, int N, int K, const float* gamma, const float* beta, const float* bias, bf16* wf,
+                           float* colsum, float* bias_f, cudaStream_t stream);

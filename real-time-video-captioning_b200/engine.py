@@ -192,6 +192,10 @@ class Engine:
         idx = beam_idx.to(device=self.device, dtype=torch.int32).contiguous()
         check(self.lib.gitb200_decode_reorder(self.h, _ptr(idx), pos, self._stream()), self.h, "gitb200_decode_reorder")
 
+    def set_fold_layernorm(self, enable: bool) -> None:
+        """ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues (default on) or run as separate LayerNorm kernels."""
+        check(self.lib.gitb200_set_fold_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fold_layernorm")
+
     def set_pipeline(self, chunk_clips: int) -> None:
         """Clips per chunk of the two-stream encode/decode pipeline (0 = off, -1 = automatic)."""
         check(self.lib.gitb200_set_pipeline(self.h, chunk_clips), self.h, "gitb200_set_pipeline")

@@ -465,3 +465,21 @@ def test_two_stream_pipeline_equals_single_stream(g, setup):
     eng.set_pipeline(0)
     assert torch.allclose(la, lb, atol=5e-3)
     assert (a == b).all(dim=-1).float().mean() >= 0.9  # beam near-ties may flip on 1e-3 score differences
+
+
+def test_folded_layernorm_matches_separate_and_oracle(g, setup):
+    """ViT ln_1 / ln_2 folded into the QKV / fc1 GEMM epilogues (row statistics from the previous residual GEMM) against
+    the separate LayerNorm kernels and against the oracle: both inside the visual-feature tolerance, the folded form
+    at least as close (it skips one bf16 rounding of the normalised activations)."""
+    cfg, sd, eng = setup[True]
+    frames = setup["frames"]
+    with torch.no_grad():
+        ref = torch.cat([go.encode_clip(sd, cfg, f) for f in frames])
+    eng.set_fold_layernorm(False)
+    sep = eng.encode(frames.cuda()).cpu()
+    eng.set_fold_layernorm(True)
+    fol = eng.encode(frames.cuda()).cpu()
+    eng.set_fold_layernorm(False)
+    e_sep, e_fol = rel_fro(sep, ref), rel_fro(fol, ref)
+    record("fold_ln", rel_fro_separate=e_sep, rel_fro_folded=e_fol, folded_vs_separate=rel_fro(fol, sep))
+    assert e_sep < 2e-2 and e_fol < 2e-2 and e_fol < e_sep * 1.25
