@@ -136,6 +136,20 @@ int gitb200_decode_begin(gitb200_ctx* ctx, int rows_per_clip, void* stream);
 int gitb200_decode_step(gitb200_ctx* ctx, const int32_t* tokens_dev, int pos, float* logits_dev, void* stream);
 int gitb200_decode_reorder(gitb200_ctx* ctx, const int32_t* beam_idx_dev, int pos, void* stream);
 
+/* ---- streaming window: the webcam loop of src/real_time_inference.py:38-61 --------------------------------------
+ * push: encode ONE preprocessed frame (fp32 [3, R, R]) with the ViT as it arrives and keep its features (after ln_post,
+ * before the temporal embedding) in a ring of num_image_with_embedding frames; caption: add the temporal embeddings in
+ * arrival order (oldest frame = position 0), run the decoder + search on the frames currently in the window
+ * (tokens_dev int32 [1, num_keep_best, max_steps]).  The caption after 6 pushes equals gitb200_caption on those 6
+ * frames, but only one frame's ViT (35 of 211 GFLOP) stands between the last frame and its caption.  reset empties the
+ * window (the reference clears its frame list after every caption: non-overlapping windows; not clearing it gives a
+ * sliding window with per-frame feature reuse). */
+int gitb200_stream_reset(gitb200_ctx* ctx);
+int gitb200_stream_push(gitb200_ctx* ctx, const float* frame_dev, void* stream);
+int gitb200_stream_frames(const gitb200_ctx* ctx);
+int gitb200_stream_caption(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev,
+                           void* stream);
+
 /* ---- frame preprocessing: image_transform(), src/utils/dataloader.py:18-32 (= real_time_inference.py:16-28) ----
  * frames_dev: uint8 [n_frames, height, width, 3] in OpenCV's BGR HWC layout; out_dev: fp32 [n_frames, 3, size, size]
  * (RGB, CLIP-normalised): bicubic resize of the smaller edge to `size` (no antialias, like the pinned torchvision

@@ -9,7 +9,7 @@ All compute runs in libgitb200.so (include/gitb200.h); importing works without a
 from ._lib import GitB200Error, LIB_PATH  # noqa: F401
 from .engine import Engine, SearchConfig, make_config, preprocess_frames, VIT_CONFIGS  # noqa: F401
 from .model import (BeamHypotheses, CLIPVisionTower, GenerativeImageTextModel, GenerativeImageTextTeacher,  # noqa: F401
-                    GeneratorWithBeamSearchV2, LazyLogits, SyntheticTokenizer, TransformerDecoderTextualHead,
+                    GeneratorWithBeamSearchV2, LazyLogits, StreamingCaptioner, SyntheticTokenizer, TransformerDecoderTextualHead,
                     get_git_model)
 from .metrics import calculate_bleu_score_corpus  # noqa: F401
 from .dist import shard_range, caption_sharded  # noqa: F401

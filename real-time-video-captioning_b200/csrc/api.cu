@@ -126,6 +126,11 @@ struct gitb200_ctx {
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_enc0 = nullptr, ev_join[2] = {nullptr, nullptr};
 
+  // streaming window (real_time_inference.py:38-61): per-frame ViT features (after ln_post, before the temporal
+  // embedding) of the last `num_image_with_embedding` frames
+  Buf<bf16> ring;
+  int ring_count = 0, ring_head = 0;
+
   // current state
   int cur_clips = 0, cur_nv = 0;     // visual features held in vf
   int step_rows_per_clip = 0;        // step-wise decoding state
@@ -237,7 +242,10 @@ int ln(gitb200_ctx* c, const bf16* x, int rows, int cols, const float* g, const 
 // ------------------------------------------------------------------ encode
 // clip_offset / total_clips: the visual features of this call land at clip index `clip_offset` of a buffer sized for
 // `total_clips` clips (host path: chunks are encoded as their frames arrive, then decoded together).
-int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, int clip_offset = 0, int total_clips = 0) {
+// frame_out != nullptr: streaming mode -- write ln_post(x) WITHOUT temporal embeddings to frame_out and leave the
+// context's visual features untouched.
+int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, int clip_offset = 0, int total_clips = 0,
+               bf16* frame_out = nullptr) {
   const gitb200_config& k = c->cfg;
   const int W = k.vit_width, T = c->T, G = k.resolution / k.patch;
   // zip() truncation of model.py:380: frames beyond the temporal-embedding list are dropped
@@ -251,7 +259,8 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   ENSURE(c, c->attn, (size_t)rows * W);
   ENSURE(c, c->mlp, (size_t)rows * 4 * W);
   if (total_clips < clip_offset + n_clips) total_clips = clip_offset + n_clips;
-  if (clip_offset == 0) ENSURE(c, c->vf, (size_t)total_clips * F * T * W);  // later chunks must not reallocate it
+  if (frame_out != nullptr) {
+  } else if (clip_offset == 0) ENSURE(c, c->vf, (size_t)total_clips * F * T * W);  // later chunks must not reallocate it
   else if (c->vf.cap < (size_t)total_clips * F * T * W) return fail(c, GITB200_ERR_STATE, "visual feature buffer too small for chunked encode");
 
   const size_t frame_elems = (size_t)3 * k.resolution * k.resolution;
@@ -335,6 +344,10 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
     }
   }
   // ln_post on all tokens + temporal embedding of the frame (frame index = (row / T) % F)
+  if (frame_out != nullptr) {
+    TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, frame_out, s));
+    return 0;
+  }
   TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, c->vf.p + (size_t)clip_offset * F * T * W, s,
          k.num_image_with_embedding > 0 ? c->temporal : nullptr, T, F));
   c->cur_clips = clip_offset + n_clips;
@@ -565,7 +578,7 @@ void free_workspaces(gitb200_ctx* c) {
   for (auto& b : c->txt_kv) fr(b);
   fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
   fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
-  fr(c->out_tok); fr(c->out_lp); fr(c->stats_a); fr(c->stats_b);
+  fr(c->out_tok); fr(c->out_lp); fr(c->stats_a); fr(c->stats_b); fr(c->ring);
 }
 
 // second workspace set that shares this context's (read-only) weights
@@ -954,6 +967,44 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
     }
   }
   return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream);
+}
+
+int gitb200_stream_reset(gitb200_ctx* c) {
+  if (!c) return GITB200_ERR_INVALID;
+  c->ring_count = 0;
+  c->ring_head = 0;
+  return GITB200_OK;
+}
+
+int gitb200_stream_push(gitb200_ctx* c, const float* frame, void* stream) {
+  if (!c || !frame) return fail(c, GITB200_ERR_INVALID, "bad stream_push argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  const int cap = c->cfg.num_image_with_embedding;
+  if (cap < 1) return fail(c, GITB200_ERR_STATE, "streaming needs num_image_with_embedding >= 1 (the window length)");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t per_frame = (size_t)c->T * c->cfg.vit_width;
+  ENSURE(c, c->ring, (size_t)cap * per_frame);
+  TRY(run_encode(c, frame, 1, 1, (cudaStream_t)stream, 0, 0, c->ring.p + (size_t)c->ring_head * per_frame));
+  c->ring_head = (c->ring_head + 1) % cap;
+  if (c->ring_count < cap) c->ring_count++;
+  return GITB200_OK;
+}
+
+int gitb200_stream_frames(const gitb200_ctx* c) { return c ? c->ring_count : 0; }
+
+int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int32_t* tokens, float* logprobs, void* stream) {
+  if (!c || !sp || !tokens || !logprobs) return fail(c, GITB200_ERR_INVALID, "bad stream_caption argument");
+  if (c->ring_count < 1) return fail(c, GITB200_ERR_STATE, "no frames in the streaming window: call gitb200_stream_push first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cap = c->cfg.num_image_with_embedding, n = c->ring_count, T = c->T, W = c->cfg.vit_width;
+  ENSURE(c, c->vf, (size_t)n * T * W);
+  const int first = (c->ring_head - n + cap) % cap;  // oldest frame -> temporal position 0
+  CUDA_OK(c, assemble_window(c->ring.p, first, cap, n, T, W, c->temporal, c->vf.p, s));
+  c->cur_clips = 1;
+  c->cur_nv = n * T;
+  c->visual_pass_done = false;
+  return run_decode(c, *sp, tokens, logprobs, nullptr, s);
 }
 
 int gitb200_set_fold_layernorm(gitb200_ctx* c, int enable) {

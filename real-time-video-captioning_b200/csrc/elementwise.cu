@@ -220,6 +220,28 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, int rows, int
   }
 }
 
+__global__ void assemble_window_kernel(const bf16* __restrict__ ring, int first, int cap, int n, int T, int W,
+                                       const float* __restrict__ temporal, bf16* __restrict__ vf) {
+  const size_t chunks_per_row = W / 8;
+  const size_t total = (size_t)n * T * chunks_per_row;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % chunks_per_row) * 8;
+    const size_t row = idx / chunks_per_row;
+    const int i = (int)(row / T), t = (int)(row % T);
+    const int slot = (first + i) % cap;
+    const uint4 u = *reinterpret_cast<const uint4*>(ring + ((size_t)slot * T + t) * W + c);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), d = unpack_bf16(u.z), e = unpack_bf16(u.w);
+    if (temporal) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(temporal + (size_t)i * W + c));
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(temporal + (size_t)i * W + c + 4));
+      a.x += t0.x; a.y += t0.y; b.x += t0.z; b.y += t0.w; d.x += t1.x; d.y += t1.y; e.x += t1.z; e.y += t1.w;
+    }
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(b.x, b.y); o.z = pack_bf16(d.x, d.y); o.w = pack_bf16(e.x, e.y);
+    *reinterpret_cast<uint4*>(vf + row * W + c) = o;
+  }
+}
+
 __global__ void fill_positions_kernel(int* pos, int* n_text, int rows, int L) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) {
@@ -229,6 +251,15 @@ __global__ void fill_positions_kernel(int* pos, int* n_text, int rows, int L) {
 }
 
 }  // namespace
+
+cudaError_t assemble_window(const bf16* ring, int first, int cap, int n, int T, int W, const float* temporal, bf16* vf,
+                            cudaStream_t stream) {
+  const size_t total = (size_t)n * T * (W / 8);
+  if (total == 0) return cudaSuccess;
+  assemble_window_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(ring, first, cap, n, T, W, temporal, vf);
+  note_launch();
+  return cudaGetLastError();
+}
 
 cudaError_t fill_positions(int* pos, int* n_text, int rows, int L, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;

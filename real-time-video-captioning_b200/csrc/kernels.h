@@ -162,3 +162,7 @@ cudaError_t preprocess_frames_u8(const uint8_t* frames, int n, int H, int W, int
 // bias_f[n] = bias[n] + sum_k w[n,k] * beta[k].
 cudaError_t ln_fold_weight(const float* w, int N, int K, const float* gamma, const float* beta, const float* bias, bf16* wf,
                            float* colsum, float* bias_f, cudaStream_t stream);
+
+// Streaming window: vf[i*T + t, :] = ring[((first + i) % cap)*T + t, :] + temporal[i, :]  for i < n  (bf16, fp32 temporal)
+cudaError_t assemble_window(const bf16* ring, int first, int cap, int n, int T, int W, const float* temporal, bf16* vf,
+                            cudaStream_t stream);

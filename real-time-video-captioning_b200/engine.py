@@ -192,6 +192,25 @@ class Engine:
         idx = beam_idx.to(device=self.device, dtype=torch.int32).contiguous()
         check(self.lib.gitb200_decode_reorder(self.h, _ptr(idx), pos, self._stream()), self.h, "gitb200_decode_reorder")
 
+    # ---- streaming window (real_time_inference.py:38-61)
+    def stream_reset(self) -> None:
+        check(self.lib.gitb200_stream_reset(self.h), self.h, "gitb200_stream_reset")
+
+    def stream_push(self, frame: torch.Tensor) -> int:
+        """Encode one preprocessed frame fp32 [3, R, R] (or [1, 3, R, R]) into the window; returns the frames held."""
+        assert frame.is_cuda and frame.dtype == torch.float32 and frame.numel() == 3 * self.cfg.resolution ** 2
+        frame = frame.contiguous()
+        check(self.lib.gitb200_stream_push(self.h, _ptr(frame), self._stream()), self.h, "gitb200_stream_push")
+        return int(self.lib.gitb200_stream_frames(self.h))
+
+    def stream_caption(self, sp: SearchConfig):
+        tokens = torch.empty(1, sp.num_keep_best, sp.max_steps, dtype=torch.int32, device=self.device)
+        logprobs = torch.empty(1, sp.num_keep_best, dtype=torch.float32, device=self.device)
+        c = sp.to_c()
+        check(self.lib.gitb200_stream_caption(self.h, ctypes.byref(c), _ptr(tokens), _ptr(logprobs), self._stream()), self.h,
+              "gitb200_stream_caption")
+        return tokens, logprobs
+
     def set_fold_layernorm(self, enable: bool) -> None:
         """ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues (default on) or run as separate LayerNorm kernels."""
         check(self.lib.gitb200_set_fold_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fold_layernorm")

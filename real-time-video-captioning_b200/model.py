@@ -592,3 +592,42 @@ class GenerativeImageTextTeacher(nn.Module):
                           reorder_cache=self.model.cache_reorder == "correct")
         tokens, _, _ = eng.decode(frames.shape[0], sc, save_logits=False)
         return tokens[:, 0].long()
+
+
+class StreamingCaptioner:
+    """The webcam loop of src/real_time_inference.py:38-61 on the GPU: every `stride`-th frame is preprocessed
+    (image_transform, :16-28) and its ViT features are computed as it arrives; once `window` frames are held the caption
+    is decoded -- only ONE frame's ViT stands between the last frame and its caption.  ``sliding=False`` reproduces the
+    reference (``frames.clear()`` after each caption, :61); ``sliding=True`` re-captions on every new frame with
+    per-frame feature reuse."""
+
+    def __init__(self, teacher: GenerativeImageTextTeacher, stride: int = 3, max_len: int = 25, beam_size: int = 1,
+                 sliding: bool = False):
+        from .engine import preprocess_frames
+        self._pre = preprocess_frames
+        self.teacher, self.stride, self.sliding = teacher, stride, sliding
+        self.engine = teacher.model.engine()
+        self.window = teacher.model.num_image_with_embedding or 6
+        d = teacher.model.decoder
+        self.search = SearchConfig(beam_size=beam_size, max_steps=max_len + 1, length_penalty=d.length_penalty,
+                                   per_node_beam_size=d.per_node_beam_size, num_keep_best=1)
+        self._counter = 0
+        self.latest_caption = ""
+        self.engine.stream_reset()
+
+    @torch.no_grad()
+    def push(self, frame_bgr_u8: torch.Tensor) -> Optional[str]:
+        """frame: uint8 [H, W, 3] BGR (what cv2.VideoCapture.read returns).  Returns a new caption or None."""
+        self._counter += 1
+        if self._counter < self.stride:
+            return None
+        self._counter = 0
+        x = self._pre(frame_bgr_u8.to(self.engine.device)[None], self.engine.cfg.resolution)
+        held = self.engine.stream_push(x[0])
+        if held < self.window:
+            return None
+        tokens, _ = self.engine.stream_caption(self.search)
+        self.latest_caption = self.teacher.tokenizer.decode(tokens[0, 0].tolist(), skip_special_tokens=True)
+        if not self.sliding:
+            self.engine.stream_reset()
+        return self.latest_caption

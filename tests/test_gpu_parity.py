@@ -483,3 +483,38 @@ def test_folded_layernorm_matches_separate_and_oracle(g, setup):
     e_sep, e_fol = rel_fro(sep, ref), rel_fro(fol, ref)
     record("fold_ln", rel_fro_separate=e_sep, rel_fro_folded=e_fol, folded_vs_separate=rel_fro(fol, sep))
     assert e_sep < 2e-2 and e_fol < 2e-2 and e_fol < e_sep * 1.25
+
+
+def test_streaming_window_equals_clip_caption(g, setup):
+    """gitb200_stream_push / _caption (per-frame ViT as frames arrive, temporal embeddings by arrival order) against the
+    oracle caption of the same window and against the batched clip path; sliding window over 5 frames with a 2-frame
+    window (the ring wraps), then the reference's non-overlapping mode through StreamingCaptioner."""
+    cfg, sd, eng = setup[True]
+    gen = torch.Generator().manual_seed(5)
+    frames = torch.randn(5, 3, 224, 224, generator=gen)
+    sp = g.SearchConfig(beam_size=1, max_steps=6)
+    eng.stream_reset()
+    for i in range(5):
+        held = eng.stream_push(frames[i].cuda())
+        assert held == min(i + 1, N_FRAMES)
+        if held < N_FRAMES:
+            continue
+        tok, lp = eng.stream_caption(sp)
+        window = frames[i - N_FRAMES + 1:i + 1]
+        with torch.no_grad():
+            ref = so.infer(sd, cfg, go.encode_clip(sd, cfg, window), beam_size=1, max_steps=6, save_logits=False)
+        assert torch.equal(tok[0].cpu().long(), ref["predictions"]), (i, tok, ref["predictions"])
+        assert torch.allclose(lp.cpu(), ref["logprobs"], atol=0.02, rtol=0.01)
+        t2, l2, _ = eng.caption(window[None].cuda().contiguous(), sp)
+        assert torch.equal(tok, t2) and torch.allclose(lp, l2, atol=0.01)
+    # reference loop semantics: stride 3, window of N_FRAMES, cleared after each caption
+    teacher = g.GenerativeImageTextTeacher.from_random_init({"num_image_with_embedding": N_FRAMES}, state_dict=sd)
+    cap = g.StreamingCaptioner(teacher, stride=3, max_len=5)
+    raw = torch.randint(0, 256, (12, 120, 160, 3), dtype=torch.uint8, generator=gen)
+    outs = [cap.push(f) for f in raw]
+    assert [o is not None for o in outs] == [False] * 5 + [True] + [False] * 5 + [True]
+    from oracle import preprocess_oracle as po
+    clip = po.preprocess_frames(raw[[2, 5]])  # frames 3 and 6 of the stream
+    with torch.no_grad():
+        ref = so.infer(sd, cfg, go.encode_clip(sd, cfg, clip), beam_size=1, max_steps=6, save_logits=False)
+    assert outs[5] == teacher.tokenizer.decode(ref["predictions"][0].tolist(), skip_special_tokens=True)
