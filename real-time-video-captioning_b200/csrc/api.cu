@@ -101,17 +101,23 @@ struct gitb200_ctx {
   cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 
-  // CUDA graph of one whole caption call (latency mode): captured on the second call with an identical signature
-  struct CaptionKey {
-    const void *frames = nullptr, *tokens = nullptr, *logprobs = nullptr, *logits = nullptr;
-    int n_clips = 0, n_frames = 0;
+  // CUDA graphs for the launch-bound small-batch calls (latency mode): a call signature is captured on its second
+  // occurrence and replayed afterwards.  kind: 0 caption, 1 stream_push, 2 stream_caption.
+  struct GraphKey {
+    int kind = -1;
+    const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    int i0 = 0, i1 = 0, i2 = 0;
     gitb200_search_params sp{};
-    bool operator==(const CaptionKey& o) const {
-      return frames == o.frames && tokens == o.tokens && logprobs == o.logprobs && logits == o.logits && n_clips == o.n_clips &&
-             n_frames == o.n_frames && memcmp(&sp, &o.sp, sizeof(sp)) == 0;
+    bool operator==(const GraphKey& o) const {
+      return kind == o.kind && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && i0 == o.i0 && i1 == o.i1 && i2 == o.i2 &&
+             memcmp(&sp, &o.sp, sizeof(sp)) == 0;
     }
-  } graph_key, last_key;
-  cudaGraphExec_t graph_exec = nullptr;
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;  // nullptr: seen once, not captured yet
+  };
+  std::vector<GraphEntry> graphs;
   bool graphs_enabled = true;
   long long graph_launches = 0;
 
@@ -649,6 +655,50 @@ int caption_pipelined(gitb200_ctx* c, const float* frames, int n_clips, int n_fr
   return 0;
 }
 
+bool graph_stream_ok(cudaStream_t s) { return s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread; }
+
+// Runs `body` (a sequence of launches on stream s).  First occurrence of `key`: eager.  Second: captured into a graph,
+// instantiated and launched.  Later: replayed.  Any capture failure disables graphs for this context (eager for good).
+template <class Body>
+int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s, bool eligible, Body&& body) {
+  if (!eligible || !c->graphs_enabled || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
+  gitb200_ctx::GraphEntry* ent = nullptr;
+  for (auto& g : c->graphs)
+    if (g.key == key) ent = &g;
+  if (ent && ent->exec) {
+    CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
+    c->graph_launches++;
+    return 1;  // replayed: the caller restores whatever host-side state `body` would have left
+  }
+  if (!ent) {
+    if (c->graphs.size() >= 64) {
+      for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      c->graphs.clear();
+    }
+    gitb200_ctx::GraphEntry e;
+    e.key = key;
+    c->graphs.push_back(e);
+    return body();  // every workspace gets sized by this eager run
+  }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    const int r = body();
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
+      cudaGraphDestroy(graph);
+      CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
+      c->graph_launches++;
+      return 0;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  cudaGetLastError();
+  ent->exec = nullptr;
+  c->graphs_enabled = false;
+  return body();
+}
+
 }  // namespace
 
 // ==================================================================== C ABI
@@ -721,7 +771,8 @@ void gitb200_destroy(gitb200_ctx* c) {
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_enc0) cudaEventDestroy(c->ev_enc0);
-  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  for (auto& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
   for (int i = 0; i < 2; ++i) {
@@ -923,42 +974,20 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
   if (!c || !sp) return fail(c, GITB200_ERR_INVALID, "bad caption argument");
   // Latency mode: a small batch is launch-bound (~850 kernels per caption), so the second call with the same
   // buffers / shapes on a capturable stream is recorded into a CUDA graph and later calls replay it.
-  gitb200_ctx::CaptionKey key;
-  key.frames = frames; key.tokens = tokens; key.logprobs = logprobs; key.logits = logits;
-  key.n_clips = n_clips; key.n_frames = n_frames; key.sp = *sp;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool eligible = c->graphs_enabled && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread &&
-                        n_clips <= 8 && !gemm_profile_enabled();
-  if (eligible && c->graph_exec && key == c->graph_key) {
+  if (n_clips > 0 && n_clips <= 8 && frames && tokens && logprobs && c->finalized) {
+    gitb200_ctx::GraphKey key;
+    key.kind = 0; key.p0 = frames; key.p1 = tokens; key.p2 = logprobs; key.i0 = n_clips; key.i1 = n_frames;
+    key.i2 = logits != nullptr; key.sp = *sp;
     CUDA_OK(c, cudaSetDevice(c->device));
-    CUDA_OK(c, cudaGraphLaunch(c->graph_exec, s));
-    c->graph_launches++;
-    // host-side state the eager path would have left behind
-    const int F = (c->cfg.num_image_with_embedding > 0 && n_frames > c->cfg.num_image_with_embedding) ? c->cfg.num_image_with_embedding : n_frames;
-    c->cur_clips = n_clips; c->cur_nv = F * c->T; c->visual_pass_done = true; c->visual_pass_full = 0;
-    return GITB200_OK;
-  }
-  if (eligible && key == c->last_key) {  // second identical call: every workspace is already sized -> capture
-    CUDA_OK(c, cudaSetDevice(c->device));
-    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      const int r = caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream);
-      const cudaError_t e = cudaStreamEndCapture(s, &graph);
-      if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&c->graph_exec, graph, 0) == cudaSuccess) {
-        cudaGraphDestroy(graph);
-        c->graph_key = key;
-        CUDA_OK(c, cudaGraphLaunch(c->graph_exec, s));
-        c->graph_launches++;
-        return GITB200_OK;
-      }
-      if (graph) cudaGraphDestroy(graph);
+    const int r = run_graphed(c, key, s, logits == nullptr, [&]() { return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream); });
+    if (r == 1) {  // replayed: host-side state the eager path would have left behind
+      const int F = (c->cfg.num_image_with_embedding > 0 && n_frames > c->cfg.num_image_with_embedding) ? c->cfg.num_image_with_embedding : n_frames;
+      c->cur_clips = n_clips; c->cur_nv = F * c->T; c->visual_pass_done = true; c->visual_pass_full = 0;
+      return GITB200_OK;
     }
-    cudaGetLastError();           // capture is an optimisation: fall back to eager launches for good
-    c->graph_exec = nullptr;
-    c->graphs_enabled = false;
+    return r;
   }
-  c->last_key = key;
   if (logits == nullptr && frames && tokens && logprobs && c->finalized && n_clips > 0 && n_frames > 0) {
     const int chunk = pipeline_chunk_for(c, n_clips);
     if (chunk > 0) {
@@ -984,7 +1013,13 @@ int gitb200_stream_push(gitb200_ctx* c, const float* frame, void* stream) {
   CUDA_OK(c, cudaSetDevice(c->device));
   const size_t per_frame = (size_t)c->T * c->cfg.vit_width;
   ENSURE(c, c->ring, (size_t)cap * per_frame);
-  TRY(run_encode(c, frame, 1, 1, (cudaStream_t)stream, 0, 0, c->ring.p + (size_t)c->ring_head * per_frame));
+  {
+    gitb200_ctx::GraphKey key;
+    key.kind = 1; key.p0 = frame; key.i0 = c->ring_head;
+    bf16* dst = c->ring.p + (size_t)c->ring_head * per_frame;
+    const int r = run_graphed(c, key, (cudaStream_t)stream, true, [&]() { return run_encode(c, frame, 1, 1, (cudaStream_t)stream, 0, 0, dst); });
+    if (r != 0 && r != 1) return r;
+  }
   c->ring_head = (c->ring_head + 1) % cap;
   if (c->ring_count < cap) c->ring_count++;
   return GITB200_OK;
@@ -1000,11 +1035,20 @@ int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int3
   const int cap = c->cfg.num_image_with_embedding, n = c->ring_count, T = c->T, W = c->cfg.vit_width;
   ENSURE(c, c->vf, (size_t)n * T * W);
   const int first = (c->ring_head - n + cap) % cap;  // oldest frame -> temporal position 0
-  CUDA_OK(c, assemble_window(c->ring.p, first, cap, n, T, W, c->temporal, c->vf.p, s));
-  c->cur_clips = 1;
-  c->cur_nv = n * T;
-  c->visual_pass_done = false;
-  return run_decode(c, *sp, tokens, logprobs, nullptr, s);
+  gitb200_ctx::GraphKey key;
+  key.kind = 2; key.p0 = tokens; key.p1 = logprobs; key.i0 = n; key.i1 = first; key.sp = *sp;
+  const int r = run_graphed(c, key, s, true, [&]() {
+    CUDA_OK(c, assemble_window(c->ring.p, first, cap, n, T, W, c->temporal, c->vf.p, s));
+    c->cur_clips = 1;
+    c->cur_nv = n * T;
+    c->visual_pass_done = false;
+    return run_decode(c, *sp, tokens, logprobs, nullptr, s);
+  });
+  if (r == 1) {
+    c->cur_clips = 1; c->cur_nv = n * T; c->visual_pass_done = true; c->visual_pass_full = 0;
+    return GITB200_OK;
+  }
+  return r;
 }
 
 int gitb200_set_fold_layernorm(gitb200_ctx* c, int enable) {

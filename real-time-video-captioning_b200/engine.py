@@ -204,12 +204,18 @@ class Engine:
         return int(self.lib.gitb200_stream_frames(self.h))
 
     def stream_caption(self, sp: SearchConfig):
-        tokens = torch.empty(1, sp.num_keep_best, sp.max_steps, dtype=torch.int32, device=self.device)
-        logprobs = torch.empty(1, sp.num_keep_best, dtype=torch.float32, device=self.device)
+        # persistent output buffers: identical call signatures let the library replay its captured CUDA graph
+        key = (sp.num_keep_best, sp.max_steps)
+        if not hasattr(self, "_stream_out"):
+            self._stream_out = {}
+        if key not in self._stream_out:
+            self._stream_out[key] = (torch.empty(1, sp.num_keep_best, sp.max_steps, dtype=torch.int32, device=self.device),
+                                     torch.empty(1, sp.num_keep_best, dtype=torch.float32, device=self.device))
+        tokens, logprobs = self._stream_out[key]
         c = sp.to_c()
         check(self.lib.gitb200_stream_caption(self.h, ctypes.byref(c), _ptr(tokens), _ptr(logprobs), self._stream()), self.h,
               "gitb200_stream_caption")
-        return tokens, logprobs
+        return tokens.clone(), logprobs.clone()
 
     def set_fold_layernorm(self, enable: bool) -> None:
         """ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues (default on) or run as separate LayerNorm kernels."""
