@@ -128,14 +128,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=3, help="clips timed for the cpu_baseline leg")
     ap.add_argument("--chunk", type=int, default=64, help="clips per host->device chunk on the e2e path")
+    ap.add_argument("--model", default="base", choices=["base", "large"], help="base = CLIPViT_B_16 (the metric's config); large = CLIPViT_L_14 (BASELINE.json configs[3], extra measurement)")
+    ap.add_argument("--frames", type=int, default=6)
     ap.add_argument("--pipeline", type=int, default=0, help="clips per chunk of the two-stream encode/decode pipeline (0 off, -1 auto)")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     args = ap.parse_args()
 
+    global FRAMES, GFLOP_PER_CLIP
+    FRAMES = args.frames
+    param = {"num_image_with_embedding": FRAMES}
+    if args.model == "large":
+        param.update({"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024})
+    if args.model == "large" or FRAMES != 6:  # algorithmic tensor work of the other BASELINE.md rows
+        GFLOP_PER_CLIP = {("large", 6): 1149.51, ("large", 24): 5123.70}.get((args.model, FRAMES), float("nan"))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "GIT-base (CLIP ViT-B/16 + 6-layer prefix-LM decoder) batched greedy caption, 6x224x224 synthetic clips",
+    config = {"workload": ("GIT-base (CLIP ViT-B/16" if args.model == "base" else "GIT-large (CLIP ViT-L/14") + f" + 6-layer prefix-LM decoder) batched {'greedy' if args.beam == 1 else 'beam-' + str(args.beam)} caption, {FRAMES}x224x224 synthetic clips",
               "clips_per_gpu_per_step": args.batch, "frames": FRAMES, "beam_size": args.beam, "max_steps": args.max_steps,
               "weights": "random-init (seeded)", "parallelism": f"clip-sharded dp{world}",
               "pipeline": "two-stream chunk pipeline, auto chunk (batch/4 in [32,128])" if args.pipeline < 0 else (f"chunks of {args.pipeline}" if args.pipeline else "off"),
@@ -169,9 +178,9 @@ def main():
 
     # identical random-init weights on every rank (same seed)
     from oracle import git_oracle as go  # weight initialiser only (not on the measured path)
-    ocfg = go.GitConfig(num_image_with_embedding=FRAMES)
+    ocfg = go.GitConfig.from_param(param)
     sd = go.init_state_dict(ocfg, seed=0, temporal_std=0.02, perturb=True)
-    eng = g.Engine(g.make_config({"num_image_with_embedding": FRAMES}, ocfg.sos_index, ocfg.eos_index), local_rank)
+    eng = g.Engine(g.make_config(param, ocfg.sos_index, ocfg.eos_index), local_rank)
     eng.load_state_dict(sd)
     del sd
     sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
