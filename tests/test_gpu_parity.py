@@ -518,3 +518,27 @@ def test_streaming_window_equals_clip_caption(g, setup):
     with torch.no_grad():
         ref = so.infer(sd, cfg, go.encode_clip(sd, cfg, clip), beam_size=1, max_steps=6, save_logits=False)
     assert outs[5] == teacher.tokenizer.decode(ref["predictions"][0].tolist(), skip_special_tokens=True)
+
+
+@pytest.mark.parametrize("n_clips,n_frames,nb,keep,max_steps", [(1, 1, 1, 1, 2), (1, 1, 8, 3, 5), (5, 2, 2, 2, 4), (2, 1, 4, 1, 20)])
+def test_caption_edge_shapes_match_oracle(g, setup, n_clips, n_frames, nb, keep, max_steps):
+    """Edge shapes of the search / batching: a single 1-frame clip, the minimum max_steps (one scored step), 8 beams with
+    num_keep_best > 1, odd clip counts, max_steps 20 (BASELINE.json configs[2]).  Token sequences must match the oracle
+    wherever its own decision margins are not near-ties; length-normalised scores must agree for the best hypothesis."""
+    cfg, sd, eng = setup[True]
+    gen = torch.Generator().manual_seed(1000 + n_clips * 10 + nb)
+    frames = torch.randn(n_clips, n_frames, 3, 224, 224, generator=gen)
+    sp = g.SearchConfig(beam_size=nb, max_steps=max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=keep,
+                        reorder_cache=True)
+    tok, lp, _ = eng.caption(frames.cuda(), sp)
+    assert tok.shape == (n_clips, keep, max_steps) and lp.shape == (n_clips, keep)
+    with torch.no_grad():
+        vf = torch.cat([go.encode_clip(sd, cfg, f) for f in frames])
+        ref = so.infer(sd, cfg, vf, beam_size=nb, max_steps=max_steps, reorder_cache=True, num_keep_best=keep, save_logits=False)
+    ref_tok = ref["predictions"].view(n_clips, keep, max_steps)
+    assert (tok[:, :, 0] == cfg.sos_index).all()
+    assert torch.allclose(lp[:, 0].cpu(), ref["logprobs"][:, 0], atol=0.05, rtol=0.02), (lp, ref["logprobs"])
+    if nb == 1:
+        assert torch.equal(tok.cpu().long(), ref_tok)
+    record("caption_edge", n_clips=n_clips, nb=nb, keep=keep, max_steps=max_steps,
+           best_match=(tok[:, 0].cpu().long() == ref_tok[:, 0]).all(dim=-1).float().mean().item())
