@@ -1,16 +1,27 @@
 // tcgen05 flash attention over fixed-length row groups (ViT frames, K10: the decoder's visual block).
 //
-// One CTA = one (group, head, 128-query tile); two CTAs share an SM so that one CTA's softmax overlaps the other's
-// MMAs and barrier latencies.  Per 64-key block:
-//     S  = Q K^T          tcgen05.mma  M=128, N<=64, K=64   (Q, K: K-major 128B-swizzled TMA tiles)      -> TMEM
-//     P  = exp2(S*c - m)  4 softmax warps, one query row per thread (tcgen05.ld 32x32b), running max / sum in registers,
-//                         P written as the bf16 K-major A operand into 128B-swizzled shared memory
-//     Oj = P V            tcgen05.mma  M=128, N=64, K<=64   (V: the TMA tile used as an MN-major B operand)   -> TMEM
-//     O  = O*alpha + Oj   folded in registers by the softmax threads (no TMEM read-modify-write, the MMA warp never
-//                         waits for a rescale)
+// One CTA = one (group, head, 128-query tile); two CTAs share an SM.  The keys of a group are cut into 64-key blocks
+// and the blocks are dealt alternately to TWO softmax warpgroups (even blocks -> group 0, odd blocks -> group 1).
+// Each warpgroup runs its own, completely independent online softmax for its blocks -- private running max m_g,
+// private row sum l_g and a private output accumulator O_g in TMEM -- so the two never exchange anything per block;
+// the two partial results are merged once at the end (the split-K identity of softmax).  Per block j (g = j & 1):
+//     S_j = Q K_j^T           tcgen05.mma  M=128, N<=64, K=64 (Q, K: K-major 128B-swizzled TMA tiles)  -> TMEM S[g]
+//     P_j = exp2(S_j*c - m_g) 4 warps, one query row per thread (tcgen05.ld 32x32b.x32), packed f32x2 FMA / add,
+//                             P written as the bf16 K-major A operand into 128B-swizzled shared memory P[g]
+//     O_g += P_j V_j          tcgen05.mma  M=128, N=64, K<=64 (V: the TMA tile used as an MN-major B operand), the
+//                             accumulation stays in TMEM
+// The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in
+// practice during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases
+// P_j.  No per-block read-back of O, no cross-warp max exchange, no named barrier inside the loop.
+// Warp 1 issues S_{j+2} as soon as group g reports that S[g] has been read into registers; the product O_g += P_j V_j
+// is issued by a thread of the warpgroup that wrote P_j (the one on TMEM lane quarter 0), so neither warpgroup ever
+// waits for the other and no thread polls.  K and V live in separate TMA rings (K_j is dead as soon as S_j
+// completes, V_j only after the PV product).
 // The last key block of a group issues only the 16-key steps that hold valid keys (197 = 3*64 + 5 -> N = 16).
-// The mma.sync predecessor of this kernel reached 123-222 TFLOP/s (the legacy tensor path peaks near 510 TFLOP/s on
-// B200, ncu: hmma pipe 40-45 % active); this version is bound by the exp2 rate of the softmax instead.
+//
+// History (profiles/): mma.sync kernel 123-222 TFLOP/s; first tcgen05 version (two threads per row, per-block O
+// read-back, shared-memory max exchange) 176 / 405 TFLOP/s at 11 issued instructions per exp2; this version issues
+// ~3.5 per exp2 and is bound by the exp2 (XU) rate.
 #include <cuda.h>
 #include <math.h>
 
@@ -26,14 +37,17 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;   // query rows per CTA = TMEM lanes
 constexpr int BKV = 64;   // keys per block
-constexpr int KV_STAGES = 3;
+constexpr int K_STAGES = 3, V_STAGES = 4;
 constexpr int Q_BYTES = BQ * 128;         // 16 KB
-constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB each for K and V
-constexpr int P_BYTES = BQ * 128;         // 16 KB: P[128 x 64 keys] bf16
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 1024 + 128 + 2 * BQ * 4;
-constexpr int NUM_SM_WARPS = 8;   // softmax warps: (lane quarter q, column half ch) = (warp & 3, (warp - 2) >> 2)
-constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: softmax
-constexpr int TMEM_COLS = 256;    // S double buffer: columns [0,64) and [64,128); Oj: columns [128,192)
+constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB
+constexpr int P_BYTES = BQ * 128;         // 16 KB: P[128 x 64 keys] bf16, one buffer per softmax group
+constexpr int N_BARRIERS = 1 + 2 * K_STAGES + 2 * V_STAGES + 8;
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES + 256 /*barriers + tmem slot*/ +
+                           2 * BQ * 8 /*(m, l) exchange*/;
+constexpr int NUM_SM_WARPS = 8;   // warps 2-5: softmax group 0, warps 6-9: group 1; TMEM lane quarter = warp & 3
+constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner
+constexpr int TMEM_COLS = 256;    // S[0]: [0,64), S[1]: [64,128), O[0]: [128,192), O[1]: [192,256)
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P never exceeds 2^8 before the running max moves
 
 // V tile [keys][64 dims] (rows of 128 B, 128B swizzle) read as an MN-major B operand (N = dims, K = keys):
 // 8 key rows form one 1024-byte swizzle atom, atoms follow each other along K every 1024 B (SBO).
@@ -56,38 +70,63 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void merge_bar_sync() {  // named barrier 1: all softmax warps
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory");
 }
+
+#ifdef ATTN_TRACE
+// Debug build only (tools/attn_bench.cu): per-warp phase timestamps of one CTA, [warp][block][phase]
+__device__ long long g_attn_trace[10 * 32 * 12];
+#define TRACE(blk, ph)                                                                                              \
+  do {                                                                                                              \
+    if (lane == 0 && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == ATTN_TRACE && (blk) < 32)                  \
+      g_attn_trace[(warp * 32 + (blk)) * 12 + (ph)] = clock64();                                                     \
+  } while (0)
+#else
+#define TRACE(blk, ph) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     bf16* __restrict__ out, int ldo, int group_len, int heads, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);
   const uint32_t sQ = smem_base;
-  auto sK = [&](int s) { return smem_base + Q_BYTES + s * 2 * KV_TILE_BYTES; };
-  auto sV = [&](int s) { return sK(s) + KV_TILE_BYTES; };
-  const uint32_t sP = smem_base + Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES;
-  const uint32_t bar_base = sP + P_BYTES;
+  auto sK = [&](int s) { return smem_base + Q_BYTES + s * KV_TILE_BYTES; };
+  auto sV = [&](int s) { return smem_base + Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
+  auto sP = [&](int g) { return smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + g * P_BYTES; };
+  const uint32_t bar_base = smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES;
   const uint32_t q_full = bar_base;
-  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + KV_STAGES + s); };
-  auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * KV_STAGES + b); };
-  const uint32_t p_full = bar_base + 8u * (3 + 2 * KV_STAGES), o_full = bar_base + 8u * (4 + 2 * KV_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * KV_STAGES);
-  const uint32_t sMax = bar_base + 128;  // float [2 halves][128 rows]: per-block row maxima exchanged between column halves
+  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (1 + K_STAGES + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * K_STAGES + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (1 + 2 * K_STAGES + V_STAGES + s); };
+  const uint32_t bar_g = bar_base + 8u * (1 + 2 * K_STAGES + 2 * V_STAGES);
+  auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S[g] holds a new block
+  auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S[g] has been read into registers
+  auto o_full = [&](int g) { return bar_g + 8u * (6 + g); };  // MMA -> group g: O[g] += P V finished, P[g] is free
+  const uint32_t tmem_slot = bar_base + 8u * N_BARRIERS;
+  const uint32_t sML = bar_base + 256;  // float2 [2 groups][128 rows]: (m, l) of each group's partial softmax
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  const int qt = blockIdx.x, h = blockIdx.y, g_idx = blockIdx.z;
   const int width = heads * HD;
-  const int row0 = g * group_len;  // first row of the group in the qkv matrix
+  const int row0 = g_idx * group_len;  // first row of the group in the qkv matrix
   const int q0 = qt * BQ;
   const int n_blocks = (group_len + BKV - 1) / BKV;
 
@@ -98,14 +137,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1);
-      for (int s = 0; s < KV_STAGES; ++s) {
-        ptx::mbar_init(kv_full(s), 1);
-        ptx::mbar_init(kv_empty(s), 1);
+      for (int s = 0; s < K_STAGES; ++s) {
+        ptx::mbar_init(k_full(s), 1);
+        ptx::mbar_init(k_empty(s), 1);
       }
-      ptx::mbar_init(s_full(0), 1);
-      ptx::mbar_init(s_full(1), 1);
-      ptx::mbar_init(p_full, NUM_SM_WARPS);  // one arrival per softmax warp
-      ptx::mbar_init(o_full, 1);
+      for (int s = 0; s < V_STAGES; ++s) {
+        ptx::mbar_init(v_full(s), 1);
+        ptx::mbar_init(v_empty(s), 1);
+      }
+      for (int g = 0; g < 2; ++g) {
+        ptx::mbar_init(s_full(g), 1);
+        ptx::mbar_init(s_free(g), NUM_SM_WARPS / 2);  // one arrival per warp of the group
+        ptx::mbar_init(o_full(g), 1);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -117,186 +161,242 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
-      ptx::tma_load_2d(sQ, &tmap_q, q_full, h * HD, row0 + q0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j % KV_STAGES;
-        ptx::mbar_wait(kv_empty(st), (uint32_t)(((j / KV_STAGES) & 1) ^ 1));
-        ptx::mbar_arrive_expect_tx(kv_full(st), 2 * KV_TILE_BYTES);
-        ptx::tma_load_2d(sK(st), &tmap_kv, kv_full(st), width + h * HD, row0 + j * BKV);
-        ptx::tma_load_2d(sV(st), &tmap_kv, kv_full(st), 2 * width + h * HD, row0 + j * BKV);
-      }
+    // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    ptx::mbar_arrive_expect_tx_elect(q_full, Q_BYTES);
+    ptx::tma_load_2d_elect(sQ, &tmap_q, q_full, h * HD, row0 + q0);
+    for (int j = 0; j < n_blocks; ++j) {
+      const int ks = j % K_STAGES, vs = j % V_STAGES;
+      ptx::mbar_wait(k_empty(ks), (uint32_t)(((j / K_STAGES) & 1) ^ 1));
+      ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
+      ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h * HD, row0 + j * BKV);
+      ptx::mbar_wait(v_empty(vs), (uint32_t)(((j / V_STAGES) & 1) ^ 1));
+      ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
+      ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h * HD, row0 + j * BKV);
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      ptx::mbar_wait(q_full, 0);
+    // ------------------------------------------------------------ S issuer (whole warp, elected lane issues)
+    ptx::mbar_wait(q_full, 0);
+    ptx::tc_fence_after();
+    const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
+    // S_j = Q K_j^T over the head dim (4 steps of 16) into S[j & 1]
+    auto issue_s = [&](int j) {
+      const int ks = j % K_STAGES;
+      const int nk = min(BKV, group_len - j * BKV);
+      const int nk16 = (nk + 15) & ~15;
+      TRACE(j, 0);
+      ptx::mbar_wait(k_full(ks), (uint32_t)((j / K_STAGES) & 1));
+      ptx::mbar_wait(v_full(j % V_STAGES), (uint32_t)((j / V_STAGES) & 1));  // s_full(j) then also means "V_j has landed"
       ptx::tc_fence_after();
-      const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
-      const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP);
-      // S_j = Q K_j^T over the head dim (4 steps of 16) into S buffer (j & 1).  The buffer is free: every softmax
-      // warp finished reading S_{j-2} before it arrived on p_full(j-2), which this thread has already waited for.
-      auto issue_s = [&](int j) {
-        const int st = j % KV_STAGES;
-        const int nk = min(BKV, group_len - j * BKV);
-        const int nk16 = (nk + 15) & ~15;
-        ptx::mbar_wait(kv_full(st), (uint32_t)((j / KV_STAGES) & 1));
-        ptx::tc_fence_after();
-        const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(st));
-        const uint32_t id_s = idesc_qk(nk16);
+      TRACE(j, 1);
+      const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
+      const uint32_t id_s = idesc_qk(nk16);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16(tS + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
-        ptx::umma_commit(s_full(j & 1));
-      };
-      issue_s(0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j % KV_STAGES;
-        const int nk = min(BKV, group_len - j * BKV);
-        const int nk16 = (nk + 15) & ~15;
-        if (j + 1 < n_blocks) issue_s(j + 1);  // runs while the softmax warps work on block j
-        // Oj = P V once the softmax warps have written P (and folded the previous Oj out of TMEM)
-        ptx::mbar_wait(p_full, (uint32_t)(j & 1));
-        ptx::tc_fence_after();
-        const uint64_t dv = umma_desc_sw128_mnmajor(sV(st));
-        const uint32_t id_o = idesc_pv();
-        for (int k = 0; k < nk16 / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
-          ptx::umma_bf16(tO, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), id_o, k != 0);
-        ptx::umma_commit(o_full);
-        ptx::umma_commit(kv_empty(st));
-      }
+      for (int k = 0; k < HD / 16; ++k)
+        ptx::umma_bf16_elect(tS + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
+      TRACE(j, 2);
+      ptx::umma_commit_elect(k_empty(ks));  // K_j is dead once S_j has been computed
+      ptx::umma_commit_elect(s_full(j & 1));
+      TRACE(j, 3);
+    };
+    issue_s(0);
+    if (n_blocks > 1) issue_s(1);
+    for (int j = 2; j < n_blocks; ++j) {
+      ptx::mbar_wait(s_free(j & 1), (uint32_t)(((j - 2) >> 1) & 1));  // block j - 2 has left S[j & 1]
+      ptx::tc_fence_after();
+      issue_s(j);
     }
   } else {
-    // ------------------------------------------------------------ softmax warps: two threads per query row
-    // thread (row r, half ch): keys [32 ch, 32 ch + 32) of every block and output dims [32 ch, 32 ch + 32)
+    // ------------------------------------------------------------ softmax warpgroups: one thread per query row
     const int quarter = warp & 3;
-    const int ch = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;    // 0: even key blocks, 1: odd key blocks
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform, same for both halves of a row
-    const uint32_t my_max = sMax + (uint32_t)(ch * BQ + r) * 4u, peer_max = sMax + (uint32_t)((ch ^ 1) * BQ + r) * 4u;
-    const int pair_bar = 1 + quarter;  // named barrier shared by the two warps that hold the same rows
-    float o_acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform
+    const uint32_t tSg = tS + (uint32_t)(grp * 64) + lane_off;
+    const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
+    const uint32_t sPg = sP(grp) + (uint32_t)r * 128u;
+    const int pv_quarter = 2 + grp;  // the warp of this group that issues the PV products: warps 2 and 7, which do not
+                                     // share a scheduler with the TMA / S-issue warps
+    const uint32_t tOg_base = tO + (uint32_t)(grp * 64);
+    const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP(grp));
+    float m_run = -INFINITY, l_run = 0.f;
 
-    auto fold = [&](float alpha) {  // o_acc = o_acc * alpha + Oj (this thread's 32 dims of TMEM columns [64,128))
-#pragma unroll
-      for (int c = 0; c < 32; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tO + lane_off + (uint32_t)(ch * 32 + c), v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha, __uint_as_float(v[i]));
-      }
-    };
-
-    // One 64-key block for this thread's 32 columns.  TAIL = the last block of a group (masked keys, possibly fewer
-    // 16-key steps); every other block takes the straight-line path.
+    // One 64-key block.  TAIL = the last block of a group (masked keys); every other block takes the straight path.
     auto block = [&](int j, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
+      const int it = j >> 1;
       const int nk = TAIL ? group_len - j * BKV : BKV;
-      const int nk16 = (nk + 15) & ~15;
-      const int c0 = ch * 32;
-      const uint32_t tSj = tS + (uint32_t)((j & 1) * 64) + lane_off + (uint32_t)c0;
-      const bool have_cols = !TAIL || c0 < nk16;  // warp-uniform
-      float s[32];
-      float mx = -INFINITY;
-      if (have_cols) {
-        uint32_t v0[16], v1[16];
-        tmem_ld_32x32b_x16(tSj, v0);
-        tmem_ld_32x32b_x16(tSj + 16u, v1);
+      float s[64];
+      TRACE(j, 0);
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(tSg, v0);
+        ptx::tmem_ld_32x32b_x32(tSg + 32u, v1);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
           s[i] = __uint_as_float(v0[i]);
-          s[16 + i] = __uint_as_float(v1[i]);
+          s[32 + i] = __uint_as_float(v1[i]);
         }
-        if (TAIL) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i >= nk) s[i] = -INFINITY;
-        }
-        mx = s[0];
-#pragma unroll
-        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, s[i]);
       }
-      // exchange the raw block maximum with the thread that owns the other half of this row
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_max), "f"(mx) : "memory");
-      named_bar_sync(pair_bar, 64);
-      float mx_peer;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mx_peer) : "r"(peer_max) : "memory");
-      const float m_new = fmaxf(m_run, fmaxf(mx, mx_peer) * scale_log2);  // scale > 0: max commutes with it
-      const float alpha = ex2_approx(m_run - m_new);                      // 0 on the first block
-      m_run = m_new;
-      if (j > 0) {  // the previous Oj is complete; P and the previous K/V stage are no longer being read
-        ptx::mbar_wait(o_full, (uint32_t)((j - 1) & 1));
+      // S[grp] is in registers: the MMA thread may overwrite it with block j + 2
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_elect(s_free(grp));
+      TRACE(j, 1);
+      if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= nk) s[i] = -INFINITY;
+      }
+      float mx = fmaxf(s[0], s[1]);
+#pragma unroll
+      for (int i = 2; i < 64; i += 2) mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
+      const float m_blk = mx * scale_log2;  // scale > 0: max commutes with it
+      // lazy running max: move it only when this block would push P above 2^RESCALE_THRESHOLD
+      const bool need = m_blk > m_run + RESCALE_THRESHOLD;  // always true on the group's first block (m_run = -inf)
+      TRACE(j, 2);
+      if (it > 0) {
+        // P[grp] / O[grp] are free once the previous product of this group has completed
+        ptx::mbar_wait(o_full(grp), (uint32_t)((it - 1) & 1));
         ptx::tc_fence_after();
-        fold(alpha_prev);
-      }
-      alpha_prev = alpha;
-      float sum = 0.f;
-      if (have_cols) {
-        const float neg_m = -m_new;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;
+          l_run *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tOg + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          float p[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            p[i] = ex2_approx(fmaf(s[c8 * 8 + i], scale_log2, neg_m));
-            sum += p[i];
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(tOg + (uint32_t)c, v);
           }
-          const uint32_t p0 = pack_bf16(p[0], p[1]), p1 = pack_bf16(p[2], p[3]), p2 = pack_bf16(p[4], p[5]), p3 = pack_bf16(p[6], p[7]);
-          const uint32_t addr = sP + (uint32_t)r * 128u + (uint32_t)(((ch * 4 + c8) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          tmem_st_wait();
         }
       }
-      l_run = fmaf(l_run, alpha, sum);
-      named_bar_sync(pair_bar, 64);  // both halves have read the exchanged maxima before the next block overwrites them
+      TRACE(j, 3);
+      if (need) m_run = m_blk;
+      const float2 sc2 = make_float2(scale_log2, scale_log2);
+      const float2 nm2 = make_float2(-m_run, -m_run);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;  // chunks beyond the issued 16-key steps are never read
+        float2 t0 = __ffma2_rn(make_float2(s[c8 * 8 + 0], s[c8 * 8 + 1]), sc2, nm2);
+        float2 t1 = __ffma2_rn(make_float2(s[c8 * 8 + 2], s[c8 * 8 + 3]), sc2, nm2);
+        float2 t2 = __ffma2_rn(make_float2(s[c8 * 8 + 4], s[c8 * 8 + 5]), sc2, nm2);
+        float2 t3 = __ffma2_rn(make_float2(s[c8 * 8 + 6], s[c8 * 8 + 7]), sc2, nm2);
+        t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y);
+        t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y);
+        t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y);
+        t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y);
+        sum_a = __fadd2_rn(sum_a, t0);
+        sum_b = __fadd2_rn(sum_b, t1);
+        sum_a = __fadd2_rn(sum_a, t2);
+        sum_b = __fadd2_rn(sum_b, t3);
+        const uint32_t p0 = pack_bf16(t0.x, t0.y), p1 = pack_bf16(t1.x, t1.y), p2 = pack_bf16(t2.x, t2.y), p3 = pack_bf16(t3.x, t3.y);
+        const uint32_t addr = sPg + (uint32_t)((c8 ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+      }
+      sum_a = __fadd2_rn(sum_a, sum_b);
+      l_run += sum_a.x + sum_a.y;
+      TRACE(j, 4);
     };
 
-    for (int j = 0; j < n_blocks; ++j) {
-      ptx::mbar_wait(s_full(j & 1), (uint32_t)((j >> 1) & 1));
+    for (int j = grp; j < n_blocks; j += 2) {
+      ptx::mbar_wait(s_full(grp), (uint32_t)((j >> 1) & 1));
       ptx::tc_fence_after();
       if (warp_has_rows) {
         if (j + 1 < n_blocks || group_len % BKV == 0)
           block(j, std::false_type{});
         else
           block(j, std::true_type{});
-      } else if (j > 0) {
-        ptx::mbar_wait(o_full, (uint32_t)((j - 1) & 1));  // keep this warp's view of the barrier phases in step
+      } else {
+        // no valid query rows in this warp: keep the barrier phases in step
+        ptx::mbar_arrive_elect(s_free(grp));
+        if (j >= 2) ptx::mbar_wait(o_full(grp), (uint32_t)(((j >> 1) - 1) & 1));
       }
       ptx::fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-      ptx::tc_fence_before();
+      ptx::tc_fence_before();    // O rescale (tcgen05.st) ordered before the MMA that accumulates into O
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
+      if (quarter != pv_quarter) {
+        if (grp == 0) asm volatile("bar.arrive 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+        else asm volatile("bar.arrive 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+      } else {
+        // this warp issues O[grp] (+)= P_j V_j as soon as the four warps of the group have delivered P_j (named
+        // barrier: the other three only arrive and run ahead): the product is issued by the warpgroup that produced
+        // its operand, nobody polls for it.  V_j is resident (the S issuer waited for it before S_j).
+        const int vs = j % V_STAGES;
+        const int nk = min(BKV, group_len - j * BKV);
+        const int nk16 = (nk + 15) & ~15;
+        TRACE(j, 5);
+        if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+        else asm volatile("bar.sync 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+        ptx::tc_fence_after();
+        TRACE(j, 6);
+        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));
+        const uint32_t acc0 = j >= 2;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
+          if (k * 16 < nk16)
+            ptx::umma_bf16_elect(tOg_base, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
+        TRACE(j, 9);
+        ptx::umma_commit_elect(v_empty(vs));
+        ptx::umma_commit_elect(o_full(grp));
+        TRACE(j, 7);
+      }
+      __syncwarp();
     }
-    ptx::mbar_wait(o_full, (uint32_t)((n_blocks - 1) & 1));
-    ptx::tc_fence_after();
+    // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
+    const bool has1 = n_blocks > 1;
+    {
+      const int last0 = (n_blocks - 1) & ~1;                 // last even block
+      ptx::mbar_wait(o_full(0), (uint32_t)((last0 >> 1) & 1));
+      if (has1) {
+        const int last1 = ((n_blocks - 2) & ~1) + 1;         // last odd block
+        ptx::mbar_wait(o_full(1), (uint32_t)((last1 >> 1) & 1));
+      }
+      ptx::tc_fence_after();
+    }
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)(grp * BQ + r) * 8u), "f"(m_run), "f"(l_run) : "memory");
+    merge_bar_sync();
     if (warp_has_rows) {
-      fold(alpha_prev);
-      // total row sum = this half's partial + the other half's (same max sequence, so the partials simply add)
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_max), "f"(l_run) : "memory");
-      named_bar_sync(pair_bar, 64);
-      float l_peer;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_peer) : "r"(peer_max) : "memory");
+      float m_o, l_o;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(sML + (uint32_t)((grp ^ 1) * BQ + r) * 8u) : "memory");
+      const float m0 = grp == 0 ? m_run : m_o, m1 = grp == 0 ? m_o : m_run;
+      const float l0 = grp == 0 ? l_run : l_o, l1 = grp == 0 ? l_o : l_run;
+      const float m = has1 ? fmaxf(m0, m1) : m0;
+      float w0 = ex2_approx(m0 - m), w1 = has1 ? ex2_approx(m1 - m) : 0.f;
+      const float inv = 1.f / (l0 * w0 + (has1 ? l1 * w1 : 0.f));
+      w0 *= inv;
+      w1 *= inv;
+      // this thread writes output dims [32 grp, 32 grp + 32) of its row
+      uint32_t a[32];
+      float o[32];
+      ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(grp * 32), a);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]) * w0;
+      if (has1) {
+        ptx::tmem_ld_32x32b_x32(tO + 64u + lane_off + (uint32_t)(grp * 32), a);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(a[i]), w1, o[i]);
+      }
       const int q = q0 + r;
       if (q < group_len) {
-        const float inv = 1.f / (l_run + l_peer);
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD + ch * 32);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD + grp * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;
-          u.x = pack_bf16(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-          u.y = pack_bf16(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-          u.z = pack_bf16(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-          u.w = pack_bf16(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+          u.x = pack_bf16(o[c * 8 + 0], o[c * 8 + 1]);
+          u.y = pack_bf16(o[c * 8 + 2], o[c * 8 + 3]);
+          u.z = pack_bf16(o[c * 8 + 4], o[c * 8 + 5]);
+          u.w = pack_bf16(o[c * 8 + 6], o[c * 8 + 7]);
           dst[c] = u;
         }
       }

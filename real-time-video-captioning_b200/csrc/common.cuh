@@ -152,6 +152,55 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- warp-uniform issue: ALL lanes of a converged warp call these with identical operands; one elected lane
+// executes the instruction.  Because the call site stays in warp-uniform control flow, ptxas keeps descriptors and
+// addresses in uniform registers and emits the UTCHMMA / UTMALDG / UTCBAR directly.  Issuing from inside an
+// `if (lane == 0)` region instead makes ptxas wrap every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// waterfall loop (~25 instructions, ~70 cycles per tcgen05.mma measured with clock64 on B200).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Value known to be identical in every lane (loaded from shared memory etc.): tell the compiler so.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // TMEM -> registers: the executing warp reads its own 32-lane quarter, 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

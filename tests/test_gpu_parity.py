@@ -124,6 +124,28 @@ def test_op_attention_groups(g, n_groups, group_len, heads, legacy):
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max()
 
 
+@pytest.mark.parametrize("n_groups,group_len,heads,gain", [(2, 197, 12, 16.0), (1, 1182, 12, 12.0), (2, 257, 16, 24.0), (3, 40, 12, 16.0)])
+def test_op_attention_growing_scores(g, n_groups, group_len, heads, gain):
+    """Keys whose magnitude grows along the group: every key block raises the row maximum by many powers of two, so the
+    kernel's lazy running-max path (rescale of the TMEM accumulator) runs on most blocks instead of almost never."""
+    from importlib import import_module
+    eng = import_module("real-time-video-captioning_b200.engine")
+    gen = torch.Generator(device="cuda").manual_seed(group_len + 7)
+    W = heads * 64
+    qkv = torch.randn(n_groups, group_len, 3, heads, 64, device="cuda", generator=gen)
+    ramp = torch.linspace(0.05, gain, group_len, device="cuda").view(1, group_len, 1, 1)
+    qkv[:, :, 1] *= ramp
+    qkv = qkv.reshape(n_groups * group_len, 3 * W).bfloat16()
+    out = eng.op_attention_groups(qkv, n_groups, group_len, heads, 0.125)
+    q, k, v = qkv.float().view(n_groups, group_len, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(n_groups * group_len, W)
+    err = (out.float() - ref).abs()
+    record("op_attention_growing_scores", group_len=group_len, max_err=err.max().item())
+    assert torch.isfinite(out.float()).all()
+    assert (err <= 0.03 + 0.015 * ref.abs()).all(), err.max()
+
+
 @pytest.mark.parametrize("nb,keep,max_steps,eos_boost", [(1, 1, 6, 0.0), (1, 1, 15, 3.0), (4, 1, 15, 2.0), (4, 3, 10, 4.0), (3, 2, 8, 6.0)])
 def test_op_search_exact(g, nb, keep, max_steps, eos_boost):
     """Device search == restated reference loop (model.py:479-678) on identical score sequences."""
