@@ -353,17 +353,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
     const bool has1 = n_blocks > 1;
-    {
-      const int last0 = (n_blocks - 1) & ~1;                 // last even block
-      ptx::mbar_wait(o_full(0), (uint32_t)((last0 >> 1) & 1));
-      if (has1) {
-        const int last1 = ((n_blocks - 2) & ~1) + 1;         // last odd block
-        ptx::mbar_wait(o_full(1), (uint32_t)((last1 >> 1) & 1));
-      }
-      ptx::tc_fence_after();
+    if (grp == 0 || has1) {
+      // every thread has followed all phases of its OWN group's o_full barrier, so this parity wait is exact; the other
+      // group's last product is covered by that group's threads before they reach the named barrier below
+      const int last = grp == 0 ? ((n_blocks - 1) & ~1) : (((n_blocks - 2) & ~1) + 1);
+      ptx::mbar_wait(o_full(grp), (uint32_t)((last >> 1) & 1));
     }
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)(grp * BQ + r) * 8u), "f"(m_run), "f"(l_run) : "memory");
     merge_bar_sync();
+    ptx::tc_fence_after();
     if (warp_has_rows) {
       float m_o, l_o;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(sML + (uint32_t)((grp ^ 1) * BQ + r) * 8u) : "memory");

@@ -50,11 +50,6 @@ struct Epi2 {
   float* stats_out;        // (sum, sum of squares) of the output rows, accumulated with atomics, or nullptr
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -67,14 +62,6 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
@@ -84,20 +71,35 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// Warp-uniform issue (see common.cuh): all lanes call with identical operands, one elected lane executes.
+// TMA load whose completion bytes are signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive (once all prior tcgen05 ops of this thread have completed) on the same barrier offset in both CTAs
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+// arrive (once all prior tcgen05 ops of the elected thread have completed) on the same barrier offset in both CTAs
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar) {
   const uint16_t mask = 3;
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask)
+      : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
@@ -105,7 +107,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, int M, int N, int K,
              Epi2 ep) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);
   const uint32_t staging_base = smem_base + STAGES * STAGE_BYTES;  // 1024-aligned (32 KB multiples)
   const uint32_t bar_base = staging_base + NUM_EPI_WARPS * STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -119,7 +121,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // == %cluster_ctarank for __cluster_dims__(2, 1, 1); written this way so that ptxas sees a uniform value (a branch on
+  // the special register read, even broadcast with shfl, made it wrap every UTCHMMA in a waterfall loop)
+  const uint32_t rank = blockIdx.x & 1u;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   const int m_pairs = (M + 2 * BM - 1) / (2 * BM);
@@ -155,10 +159,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (one thread in each CTA)
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp of each CTA, elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -167,9 +172,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t leader_full = mapa_rank(full_bar(stage), 0);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);  // both CTAs' bytes
-          tma_load_2d_pair(smem_a(stage), &tmap_a, leader_full, kb * BK, m0);
-          tma_load_2d_pair(smem_b(stage), &tmap_b, leader_full, kb * BK, n0);
+          if (rank == 0) ptx::mbar_arrive_expect_tx_elect(full_bar(stage), 2 * STAGE_BYTES);  // both CTAs' bytes
+          tma_load_2d_pair_elect(smem_a(stage), &tmap_a, leader_full, kb * BK, m0);
+          tma_load_2d_pair_elect(smem_b(stage), &tmap_b, leader_full, kb * BK, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -178,34 +183,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: one thread of the leader CTA
-    if (rank == 0 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer: warp 1 of the leader CTA.  The whole warp
+    // runs the loop (warp-uniform control flow keeps descriptors in uniform registers: no per-instruction
+    // ELECT / R2UR / BRA.U.ANY waterfall around every UTCHMMA); one elected lane executes the tcgen05 instructions.
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      uint32_t it = 0;       // k blocks issued so far: stage = it % STAGES, phase = (it / STAGES) & 1
+      uint32_t tile_it = 0;  // tiles issued so far: accumulator = tile_it & 1, phase = (tile_it >> 1) & 1
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_it) {
+        const uint32_t acc = tile_it & 1u;
+        ptx::mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          ptx::mbar_wait(full_bar(stage), (it / STAGES) & 1u);
           ptx::tc_fence_after();
           const uint64_t da = ptx::umma_desc_sw128_kmajor(smem_a(stage));
           const uint64_t db = ptx::umma_desc_sw128_kmajor(smem_b(stage));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit_pair(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+            umma_bf16_pair_elect(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_pair_elect(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit_pair_elect(tfull_bar(acc));
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
@@ -240,9 +241,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           const int col = n0 + c;
           if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous block has left the staging buffer
           __syncwarp();
-          if (ep.has_res && lane == 0) {
-            ptx::mbar_arrive_expect_tx(rbar, STAGING_BYTES);
-            ptx::tma_load_2d(stg, &tmap_res, rbar, col, row0);
+          if (ep.has_res) {
+            ptx::mbar_arrive_expect_tx_elect(rbar, STAGING_BYTES);
+            ptx::tma_load_2d_elect(stg, &tmap_res, rbar, col, row0);
           }
           uint32_t v0[32], v1[32];
           ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c, v0);

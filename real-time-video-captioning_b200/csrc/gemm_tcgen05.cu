@@ -61,7 +61,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     int N, int K, Epilogue ep) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
+  const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);  // SWIZZLE_128B wants 1024-B alignment
   const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -105,10 +105,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = ptx::warp_uniform(tmem_base);
 
+  // Producer and MMA issuer run as WHOLE warps in warp-uniform control flow; one elected lane executes each TMA /
+  // tcgen05 instruction (common.cuh: issuing from an `if (lane == 0)` region makes ptxas wrap every UTCHMMA in a
+  // ~25-instruction waterfall loop).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -116,9 +120,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          ptx::tma_load_2d(smem_a(stage), &tmap_a, full_bar(stage), kb * BK, m0);
-          ptx::tma_load_2d(smem_b(stage), &tmap_b, full_bar(stage), kb * BK, n0);
+          ptx::mbar_arrive_expect_tx_elect(full_bar(stage), C::STAGE_BYTES);
+          ptx::tma_load_2d_elect(smem_a(stage), &tmap_a, full_bar(stage), kb * BK, m0);
+          ptx::tma_load_2d_elect(smem_b(stage), &tmap_b, full_bar(stage), kb * BK, n0);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -127,8 +131,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -146,10 +150,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            ptx::umma_bf16_elect(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(empty_bar(stage));  // smem slot is free once these MMAs have read it
-          if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));  // accumulator complete
+          ptx::umma_commit_elect(empty_bar(stage));  // smem slot is free once these MMAs have read it
+          if (kb == num_kb - 1) ptx::umma_commit_elect(tfull_bar(acc));  // accumulator complete
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;

@@ -124,6 +124,24 @@ def test_op_attention_groups(g, n_groups, group_len, heads, legacy):
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max()
 
 
+@pytest.mark.parametrize("group_len,heads", [(197, 12), (1182, 12), (257, 16), (70, 12)])
+def test_op_attention_deterministic_and_batch_invariant(g, group_len, heads):
+    """The kernel must be bit-reproducible run to run and a group's result must not depend on its position in the batch
+    (the two softmax warpgroups, the lazy rescale and the hand-off barriers leave no room for a timing dependence)."""
+    from importlib import import_module
+    eng = import_module("real-time-video-captioning_b200.engine")
+    gen = torch.Generator(device="cuda").manual_seed(group_len * 3 + 1)
+    W = heads * 64
+    n_groups = 37
+    qkv = (torch.randn(n_groups * group_len, 3 * W, device="cuda", generator=gen) * 1.5).bfloat16()
+    outs = [eng.op_attention_groups(qkv, n_groups, group_len, heads, 0.125).clone() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    for gi in (0, 17, 36):
+        one = eng.op_attention_groups(qkv[gi * group_len:(gi + 1) * group_len].contiguous(), 1, group_len, heads, 0.125)
+        assert torch.equal(one, outs[0][gi * group_len:(gi + 1) * group_len])
+
+
 @pytest.mark.parametrize("n_groups,group_len,heads,gain", [(2, 197, 12, 16.0), (1, 1182, 12, 12.0), (2, 257, 16, 24.0), (3, 40, 12, 16.0)])
 def test_op_attention_growing_scores(g, n_groups, group_len, heads, gain):
     """Keys whose magnitude grows along the group: every key block raises the row maximum by many powers of two, so the
@@ -459,7 +477,10 @@ def test_preprocess_feeds_the_encoder(g, setup):
     sp = g.SearchConfig(beam_size=1, max_steps=6)
     ta, la, _ = eng.caption(a.contiguous(), sp)
     tb, lb, _ = eng.caption(b.contiguous(), sp)
-    assert torch.equal(ta, tb) and torch.allclose(la, lb, atol=1e-3)
+    # the inputs differ by ~2e-6; the attention kernel's lazy running max can then take a different rescale decision,
+    # which changes bf16 roundings of P (not the mathematics): allow the same 2 % the caption tests allow on log-probs
+    assert torch.equal(ta, tb), (ta, tb)
+    assert torch.allclose(la, lb, rtol=2e-2, atol=1e-3), (la, lb)
 
 
 def test_two_stream_pipeline_equals_single_stream(g, setup):
@@ -475,9 +496,13 @@ def test_two_stream_pipeline_equals_single_stream(g, setup):
     eng.set_pipeline(16)  # three chunks of 16 clips
     t1, l1, _ = eng.caption(frames.cuda(), sp)
     torch.cuda.synchronize()
-    assert torch.equal(t0, t1) and torch.allclose(l0, l1, atol=5e-3)
+    assert torch.equal(t0, t1), (t0, t1)
+    assert torch.allclose(l0, l1, rtol=2e-2, atol=5e-3), (l0 - l1).abs().max()
     th, lh = eng.caption_host(frames.pin_memory(), sp, chunk_clips=16)
-    assert torch.equal(t0.cpu(), th) and torch.allclose(l0.cpu(), lh, atol=5e-3)
+    assert torch.equal(t0.cpu(), th), (t0, th)
+    # chunked encodes take a different summation order upstream of the attention kernel, whose lazy running max may then
+    # take a different (equally valid) rescale decision: bf16-level differences, same 2 % as the other caption tests
+    assert torch.allclose(l0.cpu(), lh, rtol=2e-2, atol=5e-3), (l0.cpu() - lh).abs().max()
     sp4 = g.SearchConfig(beam_size=4, max_steps=6, reorder_cache=True)
     eng.set_pipeline(0)
     a, la, _ = eng.caption(frames.cuda(), sp4)
@@ -485,7 +510,7 @@ def test_two_stream_pipeline_equals_single_stream(g, setup):
     b, lb, _ = eng.caption(frames.cuda(), sp4)
     torch.cuda.synchronize()
     eng.set_pipeline(0)
-    assert torch.allclose(la, lb, atol=5e-3)
+    assert torch.allclose(la, lb, rtol=2e-2, atol=5e-3)
     assert (a == b).all(dim=-1).float().mean() >= 0.9  # beam near-ties may flip on 1e-3 score differences
 
 
