@@ -82,6 +82,14 @@ int gitb200_logits_ld(const gitb200_ctx* ctx);        /* leading dimension of ev
  * below and, if visual_features_dev != NULL, also writes them as fp32 [n_clips, F'*T, Dv]. */
 int gitb200_encode(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames, float* visual_features_dev,
                    void* stream);
+/* Single-image branch of the same forward (batch['image'] is a tensor, not a list: model.py:387-388):
+ * images_dev fp32 [n_images, 3, R, R] -> visual features [n_images, T, Dv], NO temporal embedding. */
+int gitb200_encode_images(gitb200_ctx* ctx, const float* images_dev, int n_images, float* visual_features_dev, void* stream);
+/* Forward hooks on image_encoder.transformer.resblocks[i] (registered at model.py:847, read at :912-913): while taps are
+ * set, every encode (gitb200_encode / _forward_logits / _caption) also writes the OUTPUT of each listed resblock as fp32
+ * [n_layers, n_clips, F', T, Dv] to out_dev (the reference's hook sees the same values as [T, F', Dv] per clip).
+ * layers_host: resblock indices on the host; n_layers = 0 removes the taps.  out_dev must stay valid while taps are set. */
+int gitb200_set_vit_taps(gitb200_ctx* ctx, const int32_t* layers_host, int n_layers, float* out_dev);
 /* Use caller-provided visual features (infer(batch, visual_features, ...), model.py:426). fp32 [n_clips, nv, Dv]. */
 int gitb200_set_visual_features(gitb200_ctx* ctx, const float* visual_features_dev, int n_clips, int nv, void* stream);
 

@@ -1,8 +1,8 @@
 """CPU oracle for the caption search loop -- TEST INFRASTRUCTURE ONLY (see oracle/git_oracle.py header).
 
-Restates ``GeneratorWithBeamSearchV2.search`` (/root/reference/src/models/model.py:479-678) for the
-greedy-beam branch the reference uses (do_sample=False) and the upstream ``BeamHypotheses`` helper it
-constructs at model.py:503 (legacy HuggingFace beam hypotheses container; recalled -- SURVEY 3.3).
+Restates ``GeneratorWithBeamSearchV2.search`` (/root/reference/src/models/model.py:479-678): the
+greedy-beam branch the reference uses (do_sample=False), the sampling branch (:532-554) with the upstream
+``top_k_top_p_filtering`` (:537), and the upstream ``BeamHypotheses`` helper it constructs at model.py:503 (legacy HuggingFace beam hypotheses container; recalled -- SURVEY 3.3).
 Plus ``infer`` (model.py:426-462) and the teacher's caption / logit post-processing (model.py:762-793).
 
 PARITY STATUS: unpinned by the reference (no test in /root/reference pins search output).  Anchors:
@@ -54,14 +54,42 @@ class BeamHypotheses:
             return self.worst_score >= best_sum_logprobs / self.max_length ** self.length_penalty
 
 
+def top_k_top_p_filtering(logits: torch.Tensor, top_k=0, top_p=1.0, filter_value=-float("Inf"), min_tokens_to_keep=1):
+    """Upstream generativeimage2text ``top_k_top_p_filtering`` (called at model.py:537; the legacy HuggingFace sampling
+    filter, recalled): keep the top_k highest logits and/or the smallest prefix of the sorted distribution whose
+    cumulative probability exceeds top_p (never fewer than min_tokens_to_keep); everything else becomes filter_value.
+    Like upstream, ``top_k=None`` / ``top_p=None`` (the defaults ``search`` forwards) raise TypeError on the comparisons."""
+    if top_k > 0:
+        top_k = min(max(top_k, min_tokens_to_keep), logits.size(-1))
+        kth = torch.topk(logits, top_k)[0][..., -1, None]
+        logits[logits < kth] = filter_value
+    if top_p < 1.0:
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+        cumulative = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+        remove_sorted = cumulative > top_p
+        if min_tokens_to_keep > 1:
+            remove_sorted[..., :min_tokens_to_keep] = 0
+        remove_sorted[..., 1:] = remove_sorted[..., :-1].clone()  # shift right: the token that crosses top_p is kept
+        remove_sorted[..., 0] = 0
+        remove = remove_sorted.scatter(1, sorted_indices, remove_sorted)
+        logits[remove] = filter_value
+    return logits
+
+
 def search(input_ids: torch.Tensor, step: Callable[[torch.Tensor], torch.Tensor], *, eos_index: int, max_steps: int,
            beam_size: int, length_penalty: float, per_node_beam_size: int = 2, num_keep_best: int = 1,
-           on_reorder: Optional[Callable[[torch.Tensor], None]] = None, save_logits: bool = True):
-    """model.py:479-678, greedy-beam branch.  Returns (decoded, logprobs, saved_logits).
+           on_reorder: Optional[Callable[[torch.Tensor], None]] = None, save_logits: bool = True,
+           do_sample: bool = False, top_k=None, top_p=None, num_return_sequences: int = 1,
+           repetition_penalty: float = 1.0, temperature: float = 1.0):
+    """model.py:479-678: the greedy-beam branch the reference uses and the sampling branch (:532-554).
+    Returns (decoded, logprobs, saved_logits).
 
     ``on_reorder(beam_idx)`` is called after every beam re-order; the reference never re-indexes the
     model-side cache (model.py:623-634 is commented out), so passing None reproduces it exactly.
     """
+    if num_return_sequences != 1:                                                       # :481-484
+        input_ids = input_ids[:, None, :].expand(input_ids.shape[0], num_return_sequences, input_ids.shape[1])
+        input_ids = input_ids.reshape(-1, input_ids.shape[-1])
     batch_size, cur_len = input_ids.shape
     num_beams = beam_size
     pad_token_id = eos_index
@@ -82,12 +110,33 @@ def search(input_ids: torch.Tensor, step: Callable[[torch.Tensor], torch.Tensor]
         vocab_size = scores.shape[-1]
         if save_logits:
             saved_logits.append([i.detach().cpu().numpy() for i in scores])             # :521
-        scores = F.log_softmax(scores, dim=-1)                                          # :557
-        assert scores.size() == (batch_size * num_beams, vocab_size)
-        _scores = scores + beam_scores[:, None].expand_as(scores)                       # :561
-        _scores = _scores.view(batch_size, num_beams * vocab_size)                      # :563
-        next_scores, next_words = torch.topk(_scores, per_node_beam_size * num_beams, dim=1, largest=True,
-                                             sorted=True)                               # :564
+        if repetition_penalty != 1.0:                                                   # :524-531
+            for i in range(batch_size * num_beams):
+                for previous_token in set(input_ids[i].tolist()):
+                    if scores[i, previous_token] < 0:
+                        scores[i, previous_token] *= repetition_penalty
+                    else:
+                        scores[i, previous_token] /= repetition_penalty
+        if do_sample:                                                                   # :532
+            if temperature != 1.0:
+                scores = scores / temperature                                           # :535
+            scores = top_k_top_p_filtering(scores, top_k=top_k, top_p=top_p, min_tokens_to_keep=2)   # :537
+            next_words = torch.multinomial(F.softmax(scores, dim=-1), num_samples=per_node_beam_size)  # :540
+            _scores = F.log_softmax(scores, dim=-1)                                     # :543
+            _scores = torch.gather(_scores, -1, next_words)                             # :544
+            next_scores = _scores + beam_scores[:, None].expand_as(_scores)             # :545
+            beam_indices = torch.arange(num_beams, device=next_words.device) * vocab_size   # :548
+            beam_indices = beam_indices.repeat(batch_size, per_node_beam_size)          # :549
+            next_words = next_words.view(batch_size, per_node_beam_size * num_beams)     # :550
+            next_words = next_words + beam_indices                                      # :552
+            next_scores = next_scores.view(batch_size, per_node_beam_size * num_beams)  # :553
+        else:
+            scores = F.log_softmax(scores, dim=-1)                                      # :557
+            assert scores.size() == (batch_size * num_beams, vocab_size)
+            _scores = scores + beam_scores[:, None].expand_as(scores)                   # :561
+            _scores = _scores.view(batch_size, num_beams * vocab_size)                  # :563
+            next_scores, next_words = torch.topk(_scores, per_node_beam_size * num_beams, dim=1, largest=True,
+                                                 sorted=True)                           # :564
         next_batch_beam = []
         for batch_ex in range(batch_size):                                              # :573
             done[batch_ex] = done[batch_ex] or generated_hyps[batch_ex].is_done(next_scores[batch_ex].max().item())

@@ -46,6 +46,8 @@ SIGNATURES = {
     "gitb200_tokens_per_frame": (c_int, [c_void_p]),
     "gitb200_logits_ld": (c_int, [c_void_p]),
     "gitb200_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gitb200_encode_images": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "gitb200_set_vit_taps": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "gitb200_set_visual_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "gitb200_decode": (c_int, [c_void_p, POINTER(SearchParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gitb200_caption": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p, c_void_p,

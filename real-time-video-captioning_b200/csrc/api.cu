@@ -137,6 +137,10 @@ struct gitb200_ctx {
   Buf<bf16> ring;
   int ring_count = 0, ring_head = 0;
 
+  // forward-hook taps on image_encoder.transformer.resblocks[i] (model.py:847): outputs copied out by the next encodes
+  std::vector<int> tap_layers;
+  float* tap_out = nullptr;
+
   // current state
   int cur_clips = 0, cur_nv = 0;     // visual features held in vf
   int step_rows_per_clip = 0;        // step-wise decoding state
@@ -251,11 +255,11 @@ int ln(gitb200_ctx* c, const bf16* x, int rows, int cols, const float* g, const 
 // frame_out != nullptr: streaming mode -- write ln_post(x) WITHOUT temporal embeddings to frame_out and leave the
 // context's visual features untouched.
 int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, int clip_offset = 0, int total_clips = 0,
-               bf16* frame_out = nullptr) {
+               bf16* frame_out = nullptr, bool temporal = true) {
   const gitb200_config& k = c->cfg;
   const int W = k.vit_width, T = c->T, G = k.resolution / k.patch;
   // zip() truncation of model.py:380: frames beyond the temporal-embedding list are dropped
-  const int F = (k.num_image_with_embedding > 0 && n_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : n_frames;
+  const int F = (temporal && k.num_image_with_embedding > 0 && n_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : n_frames;
   const int rows = n_clips * F * T;
   const int prow = n_clips * F * G * G;
   ENSURE(c, c->patches, (size_t)prow * c->kpad);
@@ -299,6 +303,14 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   std::swap(c->x.p, c->lnb.p);
   std::swap(c->x.cap, c->lnb.cap);
   const float scale = 1.0f / sqrtf((float)(W / k.vit_heads));
+  // resblock output taps: fp32 [n_taps, rows, W] (rows = (clip, frame, token))
+  auto emit_tap = [&](int l) -> int {
+    if (c->tap_out == nullptr || frame_out != nullptr) return 0;
+    for (size_t i = 0; i < c->tap_layers.size(); ++i)
+      if (c->tap_layers[i] == l)
+        CUDA_OK(c, cast_bf16_to_f32(c->x.p, rows, W, W, c->tap_out + ((size_t)i * total_clips + clip_offset) * F * T * W, W, s));
+    return 0;
+  };
   for (int l = 0; l < k.vit_layers; ++l) {
     const VitLayer& L = c->vit[l];
     if (fold) {
@@ -327,6 +339,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
         g.residual = c->x.p; g.ldr = W; g.stats_out = c->stats_a.p;
         TRY(gemm(c, g, s));
       }
+      TRY(emit_tap(l));
       continue;
     }
     TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
@@ -348,6 +361,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
       g.residual = c->x.p; g.ldr = W;
       TRY(gemm(c, g, s));
     }
+    TRY(emit_tap(l));
   }
   // ln_post on all tokens + temporal embedding of the frame (frame index = (row / T) % F)
   if (frame_out != nullptr) {
@@ -355,7 +369,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
     return 0;
   }
   TRY(ln(c, c->x.p, rows, W, c->ln_post_g, c->ln_post_b, k.vit_ln_eps, c->vf.p + (size_t)clip_offset * F * T * W, s,
-         k.num_image_with_embedding > 0 ? c->temporal : nullptr, T, F));
+         (temporal && k.num_image_with_embedding > 0) ? c->temporal : nullptr, T, F));
   c->cur_clips = clip_offset + n_clips;
   c->cur_nv = F * T;
   c->visual_pass_done = false;
@@ -661,7 +675,7 @@ bool graph_stream_ok(cudaStream_t s) { return s != nullptr && s != cudaStreamLeg
 // instantiated and launched.  Later: replayed.  Any capture failure disables graphs for this context (eager for good).
 template <class Body>
 int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s, bool eligible, Body&& body) {
-  if (!eligible || !c->graphs_enabled || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
+  if (!eligible || !c->graphs_enabled || !c->tap_layers.empty() || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
   gitb200_ctx::GraphEntry* ent = nullptr;
   for (auto& g : c->graphs)
     if (g.key == key) ent = &g;
@@ -939,6 +953,28 @@ int gitb200_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frame
   TRY(run_encode(c, frames, n_clips, n_frames, s));
   if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
   return GITB200_OK;
+}
+
+int gitb200_encode_images(gitb200_ctx* c, const float* images, int n_images, float* vf_out, void* stream) {
+  if (!c || !images || n_images < 1) return fail(c, GITB200_ERR_INVALID, "bad encode_images argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(run_encode(c, images, n_images, 1, s, 0, 0, nullptr, /*temporal=*/false));
+  if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_images * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
+  return GITB200_OK;
+}
+
+int gitb200_set_vit_taps(gitb200_ctx* c, const int32_t* layers_host, int n_layers, float* out_dev) {
+  if (!c) return GITB200_ERR_INVALID;
+  if (n_layers < 0 || (n_layers > 0 && (layers_host == nullptr || out_dev == nullptr)))
+    return fail(c, GITB200_ERR_INVALID, "gitb200_set_vit_taps: bad arguments");
+  for (int i = 0; i < n_layers; ++i)
+    if (layers_host[i] < 0 || layers_host[i] >= c->cfg.vit_layers)
+      return fail(c, GITB200_ERR_INVALID, "gitb200_set_vit_taps: layer %d outside [0, %d)", layers_host[i], c->cfg.vit_layers);
+  c->tap_layers.assign(layers_host, layers_host + n_layers);
+  c->tap_out = n_layers > 0 ? out_dev : nullptr;
+  return 0;
 }
 
 int gitb200_set_visual_features(gitb200_ctx* c, const float* vf, int n_clips, int nv, void* stream) {

@@ -84,6 +84,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of scores on the FMA pipe (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n
+// to the exponent field.  x <= RESCALE_THRESHOLD by construction; x is clamped at -126 (result ~ 0).
+// The softmax is bound by the MUFU (XU) rate -- 16 exp2 per clock per SM against 128 FMA lanes -- so moving a
+// fraction of the exponentials here shortens the XU critical path (the FlashAttention-4 trick).
+// Measured on B200 (tools/attn_bench.cu, 256 clips): 1 of every 4 pairs on the polynomial = +6.7 % on the 1182-key
+// decoder shape (578 -> 617 TFLOP/s), -2 % on the 197-key ViT shape (4 key blocks per CTA: start-up bound, the extra
+// FMA work only adds latency); 2 pairs = no gain, 3 pairs = -7 %.  Hence: 1 pair for long groups, 0 for short ones.
+constexpr int LONG_GROUP = 512;
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float magic = 12582912.f;  // 1.5 * 2^23: x + magic has round(x) in its low mantissa bits
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, make_float2(magic, magic));
+  const float2 n = __fadd2_rn(t, make_float2(-magic, -magic));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.0551716685f, 0.0551716685f), f, make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
 __device__ __forceinline__ void merge_bar_sync() {  // named barrier 1: all softmax warps
   asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory");
 }
@@ -100,6 +124,7 @@ __device__ long long g_attn_trace[10 * 32 * 12];
 #define TRACE(blk, ph) do { } while (0)
 #endif
 
+template <int ATTN_POLY_PAIRS>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     bf16* __restrict__ out, int ldo, int group_len, int heads, float scale_log2) {
@@ -290,10 +315,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         float2 t1 = __ffma2_rn(make_float2(s[c8 * 8 + 2], s[c8 * 8 + 3]), sc2, nm2);
         float2 t2 = __ffma2_rn(make_float2(s[c8 * 8 + 4], s[c8 * 8 + 5]), sc2, nm2);
         float2 t3 = __ffma2_rn(make_float2(s[c8 * 8 + 6], s[c8 * 8 + 7]), sc2, nm2);
-        t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y);
-        t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y);
-        t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y);
-        t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y);
+        // exp2 of 8 scores: ATTN_POLY_PAIRS of the 4 pairs go through the FMA-pipe polynomial, the rest through MUFU
+        if (ATTN_POLY_PAIRS >= 4) t0 = ex2_poly2(t0); else { t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y); }
+        if (ATTN_POLY_PAIRS >= 3) t1 = ex2_poly2(t1); else { t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y); }
+        if (ATTN_POLY_PAIRS >= 2) t2 = ex2_poly2(t2); else { t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y); }
+        if (ATTN_POLY_PAIRS >= 1) t3 = ex2_poly2(t3); else { t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y); }
         sum_a = __fadd2_rn(sum_a, t0);
         sum_b = __fadd2_rn(sum_b, t1);
         sum_a = __fadd2_rn(sum_a, t2);
@@ -417,7 +443,8 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (ld_qkv % 8 != 0 || ldo % 8 != 0) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -426,7 +453,14 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BQ, &tq)) return cudaErrorInvalidValue;
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BKV, &tkv)) return cudaErrorInvalidValue;
   dim3 grid((group_len + BQ - 1) / BQ, heads, n_groups);
-  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+#ifdef ATTN_FORCE_POLY_PAIRS
+  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+#else
+  if (group_len >= LONG_GROUP)
+    attention_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+  else
+    attention_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+#endif
   note_launch();
   return cudaGetLastError();
 }

@@ -107,6 +107,32 @@ class Engine:
         self._cur_nv = Fe * self.T
         return out
 
+    def encode_images(self, images: torch.Tensor, want_features: bool = True) -> Optional[torch.Tensor]:
+        """Single-image branch (model.py:387-388): images fp32 [B, 3, R, R] -> [B, T, Dv], no temporal embedding."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.dim() == 4
+        images = images.contiguous()
+        B = images.shape[0]
+        out = torch.empty(B, self.T, self.cfg.vit_width, dtype=torch.float32, device=self.device) if want_features else None
+        check(self.lib.gitb200_encode_images(self.h, _ptr(images), B, _ptr(out), self._stream()), self.h, "gitb200_encode_images")
+        self._cur_nv = self.T
+        return out
+
+    def set_vit_taps(self, layers, n_clips: int = 0, n_frames: int = 0) -> Optional[torch.Tensor]:
+        """Forward-hook taps on image_encoder.transformer.resblocks[i] (model.py:847).  ``layers`` = resblock indices;
+        returns the fp32 buffer [len(layers), n_clips, F', T, Dv] the next encodes fill.  ``layers`` empty: remove."""
+        layers = list(layers)
+        if not layers:
+            check(self.lib.gitb200_set_vit_taps(self.h, None, 0, None), self.h, "gitb200_set_vit_taps")
+            self._tap_buf = None
+            return None
+        n = self.cfg.num_image_with_embedding
+        Fe = min(n_frames, n) if n > 0 else n_frames
+        buf = torch.empty(len(layers), n_clips, Fe, self.T, self.cfg.vit_width, dtype=torch.float32, device=self.device)
+        arr = (ctypes.c_int32 * len(layers))(*layers)
+        check(self.lib.gitb200_set_vit_taps(self.h, arr, len(layers), _ptr(buf)), self.h, "gitb200_set_vit_taps")
+        self._tap_buf = buf  # keeps the device memory alive while the taps are set
+        return buf
+
     def set_visual_features(self, vf: torch.Tensor) -> None:
         assert vf.is_cuda and vf.dim() == 3
         vf = vf.to(torch.float32).contiguous()

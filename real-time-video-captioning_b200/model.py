@@ -207,6 +207,24 @@ class BeamHypotheses:
         return self.worst_score >= best_sum_logprobs / self.max_length ** self.length_penalty
 
 
+def top_k_top_p_filtering(logits, top_k=0, top_p=1.0, filter_value=-float("Inf"), min_tokens_to_keep=1):
+    """Upstream sampling filter called at model.py:537: in-place top-k and nucleus (top-p) truncation of a batch of
+    logits [rows, V].  ``None`` arguments fail on the comparisons exactly like upstream (TypeError)."""
+    if top_k > 0:
+        k = min(max(top_k, min_tokens_to_keep), logits.size(-1))
+        threshold = torch.topk(logits, k)[0][..., -1, None]
+        logits[logits < threshold] = filter_value
+    if top_p < 1.0:
+        ordered, order = torch.sort(logits, descending=True)
+        drop = torch.cumsum(torch.softmax(ordered, dim=-1), dim=-1) > top_p
+        if min_tokens_to_keep > 1:
+            drop[..., :min_tokens_to_keep] = False
+        drop[..., 1:] = drop[..., :-1].clone()  # the token that crosses top_p stays
+        drop[..., 0] = False
+        logits[drop.scatter(1, order, drop)] = filter_value
+    return logits
+
+
 class LazyLogits(Sequence):
     """``logits_dict`` of the reference (model.py:521: a list over steps of a list over beam rows of
     np.ndarray[V]) backed by the device buffer the decode kernels wrote; copied to the host on first read."""
@@ -250,8 +268,6 @@ class GeneratorWithBeamSearchV2:
 
     def search(self, input_ids, step: Callable, num_keep_best=1, do_sample=False, top_k=None, top_p=None,
                num_return_sequences=1):
-        if do_sample:
-            raise NotImplementedError("sampling branch (model.py:532-554) is not used by the reference path")
         if num_return_sequences != 1:
             input_ids = input_ids[:, None, :].expand(input_ids.shape[0], num_return_sequences, input_ids.shape[1])
             input_ids = input_ids.reshape(-1, input_ids.shape[-1])
@@ -272,9 +288,19 @@ class GeneratorWithBeamSearchV2:
                 for i in range(batch_size * nb):
                     for tok in set(input_ids[i].tolist()):
                         scores[i, tok] = scores[i, tok] * self.repetition_penalty if scores[i, tok] < 0 else scores[i, tok] / self.repetition_penalty
-            lp = torch.log_softmax(scores, dim=-1) + beam_scores[:, None]
-            next_scores, next_words = torch.topk(lp.view(batch_size, nb * vocab), self.per_node_beam_size * nb, dim=1,
-                                                 largest=True, sorted=True)
+            if do_sample:  # model.py:532-554: temperature, top-k / top-p filter, per_node_beam_size samples per beam
+                if self.temperature != 1.0:
+                    scores = scores / self.temperature
+                scores = top_k_top_p_filtering(scores, top_k=top_k, top_p=top_p, min_tokens_to_keep=2)
+                words = torch.multinomial(torch.softmax(scores, dim=-1), num_samples=self.per_node_beam_size)
+                picked = torch.gather(torch.log_softmax(scores, dim=-1), -1, words) + beam_scores[:, None]
+                offsets = (torch.arange(nb, device=words.device) * vocab).repeat(batch_size, self.per_node_beam_size)
+                next_words = words.view(batch_size, self.per_node_beam_size * nb) + offsets
+                next_scores = picked.view(batch_size, self.per_node_beam_size * nb)
+            else:
+                lp = torch.log_softmax(scores, dim=-1) + beam_scores[:, None]
+                next_scores, next_words = torch.topk(lp.view(batch_size, nb * vocab), self.per_node_beam_size * nb, dim=1,
+                                                     largest=True, sorted=True)
             ns_host, nw_host = next_scores.tolist(), next_words.tolist()  # one transfer per step, not one per candidate
             nxt = []
             for b in range(batch_size):
@@ -384,11 +410,41 @@ class GenerativeImageTextModel(nn.Module):
             self._vf_token = None
         return self._engine
 
+    # ---- forward hooks (the reference's DistillationTrainer registers them at model.py:847 and :857)
+    def _hooked_resblocks(self):
+        return [i for i, blk in enumerate(self.image_encoder.transformer.resblocks) if len(blk._forward_hooks) > 0]
+
+    def _arm_vit_taps(self, eng: Engine, n_clips: int, n_frames: int):
+        layers = self._hooked_resblocks()
+        return (layers, eng.set_vit_taps(layers, n_clips, n_frames)) if layers else (layers, None)
+
+    def _fire_vit_hooks(self, eng: Engine, layers, taps) -> None:
+        """Call the registered forward hooks the way the reference's per-clip loop would have: once per clip, with the
+        resblock output in the upstream [T, F, Dv] (sequence-first) layout (read as ``[:, 0]`` at model.py:912)."""
+        if not layers:
+            return
+        eng.set_vit_taps([])
+        for c in range(taps.shape[1]):
+            for j, li in enumerate(layers):
+                blk = self.image_encoder.transformer.resblocks[li]
+                out = taps[j, c].permute(1, 0, 2)
+                for hook in list(blk._forward_hooks.values()):
+                    hook(blk, (None,), out)
+
+    def _fire_decoder_hooks(self, hidden: torch.Tensor) -> None:
+        """``textual.transformer.encoder.layer[i].output`` hooks (model.py:857): the module's output is the layer's
+        output hidden state = hidden_states[i + 1]; fired per clip with the reference's [1, Nv+L, H] shape."""
+        layers = self.textual.transformer.encoder.layer
+        if not any(len(l.output._forward_hooks) for l in layers):
+            return
+        for c in range(hidden.shape[0]):
+            for i, l in enumerate(layers):
+                for hook in list(l.output._forward_hooks.values()):
+                    hook(l.output, (None, None), hidden[c:c + 1, i + 1])
+
     @staticmethod
     def _stack_frames(images) -> torch.Tensor:
         """batch['image']: list of F tensors [B,3,H,W] (the reference passes B == 1) -> [B,F,3,H,W]."""
-        if not isinstance(images, (list, tuple)):
-            raise NotImplementedError("single-image input (no temporal embedding) is not part of the clip path")
         return torch.stack([im if im.dim() == 4 else im.unsqueeze(0) for im in images], dim=1).float()
 
     # ---- forward paths
@@ -402,9 +458,17 @@ class GenerativeImageTextModel(nn.Module):
         if self.pooling_images is not None:
             raise NotImplementedError
         eng = self.engine()
-        frames = self._stack_frames(batch["image"]).to(eng.device)
         tokens = batch["caption_tokens"]
+        if not isinstance(batch["image"], (list, tuple)):  # single image per sample: no temporal embedding (:387-388)
+            vf = eng.encode_images(batch["image"].float().to(eng.device))
+            logits, _, hidden = eng.forward_logits(None, tokens, want_hidden=True, want_features=False)
+            self._vf_token = None
+            return logits, vf, (hidden[0] if hidden.shape[0] == 1 else hidden)
+        frames = self._stack_frames(batch["image"]).to(eng.device)
+        layers, taps = self._arm_vit_taps(eng, frames.shape[0], frames.shape[1])
         logits, vf, hidden = eng.forward_logits(frames, tokens, want_hidden=True, want_features=True)
+        self._fire_vit_hooks(eng, layers, taps)
+        self._fire_decoder_hooks(hidden)
         self._vf_token = None
         hidden_states = hidden[0] if hidden.shape[0] == 1 else hidden  # reference squeezes the batch dim (B == 1)
         return logits, vf, hidden_states
@@ -415,8 +479,14 @@ class GenerativeImageTextModel(nn.Module):
             raise NotImplementedError("the GIT teacher is frozen (model.py:741-745); training forward is out of scope")
         with torch.no_grad():
             eng = self.engine()
+            if not isinstance(batch["image"], (list, tuple)):  # single image per sample (model.py:387-388)
+                vf = eng.encode_images(batch["image"].float().to(eng.device))
+                self._vf_token = vf
+                return self.infer(batch, vf, None)
             frames = self._stack_frames(batch["image"]).to(eng.device)
+            layers, taps = self._arm_vit_taps(eng, frames.shape[0], frames.shape[1])
             vf = eng.encode(frames, want_features=True)
+            self._fire_vit_hooks(eng, layers, taps)
             self._vf_token = vf
             return self.infer(batch, vf, None)
 
@@ -540,9 +610,13 @@ class GenerativeImageTextTeacher(nn.Module):
     def forward_output_logits(self, x, y):
         """model.py:747-760: lists (one entry per clip) of logits [1,L,V], visual features [1,Nv,Dv],
         hidden states [7,Nv+L,H]."""
-        eng = self.model.engine()
+        m = self.model
+        eng = m.engine()
         frames = x.to(eng.device).float()
+        layers, taps = m._arm_vit_taps(eng, frames.shape[0], frames.shape[1])
         logits, vf, hidden = eng.forward_logits(frames, y, want_hidden=True, want_features=True)
+        m._fire_vit_hooks(eng, layers, taps)
+        m._fire_decoder_hooks(hidden)
         n = frames.shape[0]
         return [logits[i:i + 1] for i in range(n)], [vf[i:i + 1] for i in range(n)], [hidden[i] for i in range(n)]
 

@@ -94,6 +94,40 @@ def test_host_search_equals_oracle_search_on_random_scores():
     assert torch.equal(dec[0], ref[0]) and torch.allclose(dec[1], ref[1], atol=1e-6)
 
 
+@pytest.mark.parametrize("top_k,top_p,temperature,rep,nrs", [(5, 1.0, 1.0, 1.0, 1), (0, 0.8, 0.7, 1.0, 1), (8, 0.9, 1.3, 1.2, 2)])
+def test_sampling_branch_equals_oracle(top_k, top_p, temperature, rep, nrs):
+    """search(do_sample=True) (model.py:532-554: temperature, top_k_top_p_filtering, multinomial, the reference's beam-offset
+    layout) and the repetition penalty (:524-531) / num_return_sequences (:481-484) paths: product == oracle under the same
+    torch RNG seed on the same scripted scores."""
+    V, eos, sos, n, nb, ms = 40, 2, 1, 2, 3, 8
+    gen = torch.Generator().manual_seed(11)
+    steps = [torch.randn(n * nrs * nb, V, generator=gen) * 2 for _ in range(ms - 1)]
+    start = torch.full((n, 1), sos)
+    torch.manual_seed(5)
+    ref = so.search(start, _scripted([s.clone() for s in steps]), eos_index=eos, max_steps=ms, beam_size=nb, length_penalty=0.6,
+                    save_logits=False, do_sample=True, top_k=top_k, top_p=top_p, num_return_sequences=nrs,
+                    repetition_penalty=rep, temperature=temperature)
+    torch.manual_seed(5)
+    dec = g.GeneratorWithBeamSearchV2(eos, ms, nb, 0.6, repetition_penalty=rep, temperature=temperature).search(
+        start, _scripted([s.clone() for s in steps]), do_sample=True, top_k=top_k, top_p=top_p, num_return_sequences=nrs)
+    assert dec[0].shape == (n * nrs, ms)
+    assert torch.equal(dec[0], ref[0]) and torch.allclose(dec[1], ref[1], atol=1e-6)
+
+
+def test_top_k_top_p_filtering_hand_case_and_upstream_error_behaviour():
+    m = importlib.import_module("real-time-video-captioning_b200.model")
+    logits = torch.log(torch.tensor([[0.5, 0.25, 0.15, 0.07, 0.03]]))
+    for f in (m.top_k_top_p_filtering, so.top_k_top_p_filtering):
+        out = f(logits.clone(), top_k=3, top_p=1.0)
+        assert torch.isinf(out[0, 3:]).all() and torch.isfinite(out[0, :3]).all()
+        out = f(logits.clone(), top_k=0, top_p=0.7)          # 0.5 + 0.25 crosses 0.7 at the second token: it is kept
+        assert torch.isfinite(out[0, :2]).all() and torch.isinf(out[0, 2:]).all()
+        out = f(logits.clone(), top_k=1, top_p=0.1, min_tokens_to_keep=2)
+        assert torch.isfinite(out[0, :2]).all() and torch.isinf(out[0, 2:]).all()
+        with pytest.raises(TypeError):                       # upstream compares None > 0 (search's default arguments)
+            f(logits.clone(), top_k=None, top_p=None)
+
+
 def test_prefix_lm_mask_and_frame_truncation():
     m = go.prefix_lm_mask(3, 2)
     assert (m[:3, :3] == 0).all() and torch.isinf(m[:3, 3:]).all() and (m[3:, :3] == 0).all()

@@ -315,6 +315,77 @@ def test_step_api_and_generic_search_match_fused(g, setup):
     assert gd.shape == (2, 7) and (gd[:, 0] == cfg.sos_index).all()
 
 
+def test_forward_hooks_see_resblock_and_decoder_layer_outputs(g, setup):
+    """The reference's DistillationTrainer hooks ``image_encoder.transformer.resblocks[i]`` (model.py:847, output used as
+    ``[:, 0]`` = CLS row of every frame, :912) and ``textual.transformer.encoder.layer[i].output`` (:857).  The hooks must
+    fire once per clip with the upstream layouts ([T, F, Dv] / [1, Nv+L, H]) and oracle-matching values."""
+    cfg, sd, _ = setup[True]
+    frames = setup["frames"][:2]
+    teacher = g.GenerativeImageTextTeacher.from_random_init({"num_image_with_embedding": N_FRAMES}, state_dict=sd)
+    m = teacher.model
+    enc_seen, dec_seen = {}, {}
+    handles = []
+    for li in (0, 6, 11):
+        handles.append(m.image_encoder.transformer.resblocks[li].register_forward_hook(
+            lambda mod, inp, out, li=li: enc_seen.setdefault(li, []).append(out.detach().cpu())))
+    for li in range(6):
+        handles.append(m.textual.transformer.encoder.layer[li].output.register_forward_hook(
+            lambda mod, inp, out, li=li: dec_seen.setdefault(li, []).append(out.detach().cpu())))
+    y = torch.randint(1000, 30000, (2, 5))
+    y[:, 0] = cfg.sos_index
+    lo, vfs, hs = teacher.forward_output_logits(frames, y)
+    assert sorted(enc_seen) == [0, 6, 11] and all(len(v) == 2 for v in enc_seen.values())
+    assert sorted(dec_seen) == list(range(6)) and all(len(v) == 2 for v in dec_seen.values())
+    with torch.no_grad():
+        for c in range(2):
+            _, blocks = go.vit_forward(sd, cfg, frames[c], return_blocks=True)          # each [F, T, W]
+            for li in (0, 6, 11):
+                got = enc_seen[li][c]
+                assert got.shape == (197, N_FRAMES, 768)                                   # upstream sequence-first layout
+                e = rel_fro(got.permute(1, 0, 2), blocks[li])
+                record("vit_hook", layer=li, clip=c, rel_fro=e)
+                assert e < 2e-2, (li, e)
+            _, _, ref_h = go.forward_one_custom(sd, cfg, frames[c], y[c:c + 1])          # [7, Nv+L, H]
+            for li in range(6):
+                got = dec_seen[li][c]
+                assert got.shape == (1, N_FRAMES * 197 + 5, 768)
+                assert rel_fro(got[0], ref_h[li + 1]) < 3e-2
+    # hooks also fire on the caption path's encode; removing them restores the un-tapped path (and CUDA graphs)
+    enc_seen.clear()
+    teacher(frames)
+    assert all(len(enc_seen[li]) == 2 for li in (0, 6, 11))
+    for h in handles:
+        h.remove()
+    enc_seen.clear()
+    teacher.forward_output_logits(frames, y)
+    assert not enc_seen
+
+
+def test_single_image_branch_matches_oracle(g, setup):
+    """batch['image'] given as ONE tensor [B, 3, H, W] instead of a list of frames (model.py:387-388): the ViT features are
+    used as they are -- no temporal embedding, T visual tokens per sample."""
+    cfg, sd, _ = setup[True]
+    images = setup["frames"][:2, 0].contiguous()
+    teacher = g.GenerativeImageTextTeacher.from_random_init({"num_image_with_embedding": N_FRAMES}, state_dict=sd)
+    m = teacher.model
+    y = torch.randint(1000, 30000, (2, 4))
+    y[:, 0] = cfg.sos_index
+    logits, vf, hidden = m.forward_one_custom({"image": images.cuda(), "caption_tokens": y})
+    with torch.no_grad():
+        ref_vf = go.vit_forward(sd, cfg, images)
+        ref_logits, ref_hidden = go.textual_forward(sd, cfg, ref_vf, y)
+    assert vf.shape == (2, 197, 768) and rel_fro(vf.cpu(), ref_vf) < 2e-2
+    sigma = ref_logits.std().item()
+    err = (logits.cpu() - ref_logits).abs()
+    record("single_image", max_err_sigma=err.max().item() / sigma)
+    assert err.max().item() < 0.15 * sigma and err.mean().item() < 0.03 * sigma
+    assert hidden.shape == (2, 7, 197 + 4, 768)
+    m.decoder.max_steps = 5
+    out = m({"image": images.cuda()})
+    ref = so.infer(sd, cfg, ref_vf, beam_size=4, max_steps=5)
+    assert torch.equal(out["predictions"].cpu(), ref["predictions"])
+
+
 def test_host_path_equals_device_path(g, setup):
     cfg, sd, eng = setup[True]
     frames = setup["frames"]
