@@ -165,9 +165,39 @@ int gitb200_stream_caption(gitb200_ctx* ctx, const gitb200_search_params* sp, in
 int gitb200_preprocess(const uint8_t* frames_dev, int n_frames, int height, int width, int size, float* out_dev,
                        void* stream);
 
+/* ---- student decoder: the decoder half of StudentCandidateV1, model.py:50-187 ---------------------
+ * nn.Embedding + PositionalEncoding + post-LN nn.TransformerDecoder (causal / padding-masked self-attention, cross-attention
+ * to the F frame tokens of `memory`, ReLU feed-forward) + the vocabulary nn.Linear.  The TinyViT image encoder that
+ * produces `memory` (timm, model.py:35-48) is NOT part of this library: memory fp32 [B, F, d_model] is an input.
+ * Weights use the reference's state-dict names (decoder.layers.N.{self_attn,multihead_attn}.{in_proj_weight,in_proj_bias,
+ * out_proj.weight,out_proj.bias}, .linear1/.linear2/.norm1-3.{weight,bias}, embed.weight, linear.{weight,bias}) plus
+ * "pos_enc.pe" = the [max_len, d_model] sinusoidal table of PositionalEncoding (model.py:324-335). */
+typedef struct gitb200_student gitb200_student;
+typedef struct {
+  int d_model, n_head, d_ffn, n_layers; /* config.py:80-84: 576, 8, 1024, 2 */
+  int vocab, max_len;                   /* tokenizer vocabulary (30522), PositionalEncoding max_len (500) */
+  int cls, sep, pad;                    /* 101, 102 (model.py:82-83), create_padding_mask's padding_token 0 (masking.py:4) */
+  float ln_eps;                         /* nn.LayerNorm default 1e-5 */
+} gitb200_student_config;
+int gitb200_student_create(const gitb200_student_config* cfg, int device, gitb200_student** out);
+void gitb200_student_destroy(gitb200_student* s);
+const char* gitb200_student_last_error(const gitb200_student* s);
+int gitb200_student_load_weight(gitb200_student* s, const char* name, const float* data, int ndim, const int64_t* shape);
+int gitb200_student_finalize(gitb200_student* s);
+int gitb200_student_logits_ld(const gitb200_student* s); /* vocabulary rounded up to 256 */
+/* forward_decoder(y, memory), model.py:135-154: tokens_dev int32 [B, L], memory_dev fp32 [B, M, d_model] ->
+ * logits_dev fp32 [B*L, logits_ld] (teacher-forced, every position). */
+int gitb200_student_forward_decoder(gitb200_student* s, const int32_t* tokens_dev, const float* memory_dev, int B, int L, int M,
+                                    float* logits_dev, void* stream);
+/* greedy_decode, model.py:156-187, on a given memory, with a K/V cache instead of the reference's full re-decode per step.
+ * tokens_dev int32 [B, max_len + 1] (CLS first); *out_len_dev = length of the reference's returned sequence: it stops only
+ * when EVERY row emitted SEP in the same step (model.py:184), columns >= *out_len_dev are not part of the result. */
+int gitb200_student_greedy_decode(gitb200_student* s, const float* memory_dev, int B, int M, int max_len, int32_t* tokens_dev,
+                                  int32_t* out_len_dev, void* stream);
+
 /* ---- single operators (used by the parity tests; same kernels the pipeline launches) ---------- */
 /* out = act(A[M,K] * W[N,K]^T + bias) + residual; bf16 in/out (uint16 storage), fp32 bias. act: 0 none,
- * 1 QuickGELU, 2 erf-GELU.  tile_n: 0 auto, 128 or 256. */
+ * 1 QuickGELU, 2 erf-GELU, 3 ReLU.  tile_n: 0 auto, 128 or 256. */
 int gitb200_op_gemm(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev,
                     const void* residual_dev, int act, void* out_bf16_dev, float* out_f32_dev, int tile_n,
                     void* stream);

@@ -27,6 +27,13 @@ class Config(Structure):
     ]
 
 
+class StudentConfig(Structure):
+    _fields_ = [
+        ("d_model", c_int), ("n_head", c_int), ("d_ffn", c_int), ("n_layers", c_int),
+        ("vocab", c_int), ("max_len", c_int), ("cls", c_int), ("sep", c_int), ("pad", c_int), ("ln_eps", c_float),
+    ]
+
+
 class SearchParams(Structure):
     _fields_ = [
         ("beam_size", c_int), ("max_steps", c_int), ("per_node_beam_size", c_int), ("num_keep_best", c_int),
@@ -46,6 +53,14 @@ SIGNATURES = {
     "gitb200_tokens_per_frame": (c_int, [c_void_p]),
     "gitb200_logits_ld": (c_int, [c_void_p]),
     "gitb200_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gitb200_student_create": (c_int, [POINTER(StudentConfig), c_int, POINTER(c_void_p)]),
+    "gitb200_student_destroy": (None, [c_void_p]),
+    "gitb200_student_last_error": (c_char_p, [c_void_p]),
+    "gitb200_student_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64)]),
+    "gitb200_student_finalize": (c_int, [c_void_p]),
+    "gitb200_student_logits_ld": (c_int, [c_void_p]),
+    "gitb200_student_forward_decoder": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gitb200_student_greedy_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gitb200_encode_images": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gitb200_set_vit_taps": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "gitb200_set_visual_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

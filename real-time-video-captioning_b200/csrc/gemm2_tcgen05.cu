@@ -279,6 +279,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             } else if (ep.act == ACT_GELU_ERF) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+            } else if (ep.act == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             const uint32_t saddr = stg + my_row_off + (uint32_t)((j ^ (lane & 7)) << 4);
             if (ep.has_res) {

@@ -211,6 +211,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           } else if (ep.act == ACT_GELU_ERF) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          } else if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
           if (ep.residual != nullptr) {
             const uint4* r4 = reinterpret_cast<const uint4*>(ep.residual + (size_t)rrow * ep.ldr + col);

@@ -83,6 +83,7 @@ gemv_skinny_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__
         if (bias) v += bias[n];
         if (act == ACT_QUICK_GELU) v = quick_gelu(v);
         else if (act == ACT_GELU_ERF) v = gelu_erf(v);
+        else if (act == ACT_RELU) v = fmaxf(v, 0.f);
         if (residual) v += __bfloat162float(residual[(size_t)m * ldr + n]);
         if (out) out[(size_t)m * ldo + n] = __float2bfloat16(v);
         if (out_f32) out_f32[(size_t)m * ldo32 + n] = v;

@@ -7,7 +7,7 @@
 
 typedef __nv_bfloat16 bf16;
 
-enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
+enum { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_RELU = 3 };
 
 // every host wrapper below reports the kernels it enqueues (gitb200_launch_count)
 void note_launch(int n = 1);

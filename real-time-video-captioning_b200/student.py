@@ -1,0 +1,199 @@
+"""Drop-in surface of the reference's student (``StudentCandidateV1``, /root/reference/src/models/model.py:50-187) for its
+DECODER half -- the part ``src/inference.py:51`` and ``src/real_time_inference.py:58`` spend their decode loop in.
+
+Same constructor arguments, attribute / state-dict names (``decoder.layers.N.*``, ``embed``, ``linear``, ``pos_enc``) and
+method contracts (``forward_decoder(y, memory)`` :135, ``greedy_decode(src, max_len)`` :156, ``forward_image_enc`` :116),
+but the decoder arithmetic runs in libgitb200.so (csrc/student.cu): tcgen05 / weight-streaming GEMMs, small attention /
+LayerNorm / argmax kernels, and a K/V cache in place of the reference's full re-decode of the growing sequence every step.
+The nn.Module tree only holds parameters; there is no torch forward and no CPU path.
+
+The TinyViT image encoder (timm ``features_only`` model, :35-48) is not rebuilt: pass ``image_encoder=`` (any module that
+returns the list of stage feature maps like timm's) or call ``greedy_decode_from_memory`` / ``forward_decoder`` with the
+``memory`` tensor [B, F, d_model] directly.  Training (``DistillationTrainer``) is out of scope.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import GitB200Error, StudentConfig
+
+
+def _check(code: int, lib, h, what: str) -> None:
+    if code != 0:
+        msg = lib.gitb200_student_last_error(h)
+        raise GitB200Error(f"{what} failed ({code}): {msg.decode() if msg else ''}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class PositionalEncoding(nn.Module):
+    """model.py:320-340: the sinusoidal table as a buffer ``pe`` [1, max_len, d_model]."""
+
+    def __init__(self, d_model: int, max_len: int = 500):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2) * -(torch.log(torch.tensor(10000.0)) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):  # pragma: no cover - guard
+        raise RuntimeError("parameter container only: the student decoder runs on the CUDA library")
+
+
+class _Params(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("parameter container only: the student decoder runs on the CUDA library")
+
+
+class _MHAParams(_Params):
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+
+
+class _DecoderLayerParams(_Params):
+    """Parameter names of nn.TransformerDecoderLayer (model.py:73-75)."""
+
+    def __init__(self, d, f):
+        super().__init__()
+        self.self_attn, self.multihead_attn = _MHAParams(d), _MHAParams(d)
+        self.linear1, self.linear2 = nn.Linear(d, f), nn.Linear(f, d)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d), nn.LayerNorm(d), nn.LayerNorm(d)
+
+
+class _DecoderParams(_Params):
+    def __init__(self, d, f, n):
+        super().__init__()
+        self.layers = nn.ModuleList([_DecoderLayerParams(d, f) for _ in range(n)])
+        self.num_layers = n
+
+
+class StudentCandidateV1(nn.Module):
+    """model.py:50-187 (decoder half on the GPU library)."""
+
+    def __init__(self, image_enc_name: Optional[str], d_model: int, n_head: int, d_ffn: int, dropout: float, num_decoder_layers: int,
+                 vocab_length: int, cls_token_id: int, sep_token_id: int, *, image_encoder: Optional[nn.Module] = None):
+        super().__init__()
+        self.image_enc_name = image_enc_name
+        self.image_encoder = image_encoder            # model.py:72 builds TinyVIT(image_enc_name) through timm
+        self.n_head, self.d_model, self.d_ffn, self.dropout = n_head, d_model, d_ffn, dropout
+        self.decoder = _DecoderParams(d_model, d_ffn, num_decoder_layers)
+        self.embed = nn.Embedding(vocab_length, d_model)
+        self.linear = nn.Linear(d_model, vocab_length)
+        self.cls_token_id, self.sep_token_id = cls_token_id, sep_token_id
+        self.pos_enc = PositionalEncoding(d_model=d_model)
+        self._h = None
+        self._lib = None
+        self._stale = True
+        self._dev = None
+
+    # ---- engine plumbing
+    def load_state_dict(self, state_dict, strict: bool = False, **kw):
+        # the reference's checkpoints also hold the TinyViT, the lazy projector heads and the template decoder_layer
+        sd = {k: v for k, v in state_dict.items() if k.startswith(("decoder.layers.", "embed.", "linear.", "pos_enc."))}
+        out = super().load_state_dict(sd, strict=False, **kw)
+        self._stale = True
+        return out
+
+    def _apply(self, fn, *a, **k):
+        self._stale = True
+        return super()._apply(fn, *a, **k)
+
+    def _engine(self):
+        p = self.embed.weight
+        if not p.is_cuda:
+            raise RuntimeError("StudentCandidateV1 runs only on a CUDA device (B200): call .to('cuda') first; there is no CPU path")
+        if self._h is not None and not self._stale and self._dev == p.device:
+            return self._h
+        self.close()
+        lib = _lib.load()
+        cfg = StudentConfig(self.d_model, self.n_head, self.d_ffn, self.decoder.num_layers, self.embed.num_embeddings,
+                            self.pos_enc.pe.shape[1], self.cls_token_id, self.sep_token_id, 0, 1e-5)
+        h = ctypes.c_void_p()
+        _check(lib.gitb200_student_create(ctypes.byref(cfg), p.device.index or 0, ctypes.byref(h)), lib, None, "gitb200_student_create")
+        weights = {k: v for k, v in self.state_dict().items() if k.startswith(("decoder.layers.", "embed.", "linear."))}
+        weights["pos_enc.pe"] = self.pos_enc.pe[0]
+        for name, t in weights.items():
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+            _check(lib.gitb200_student_load_weight(h, name.encode(), _ptr(t), t.dim(), shape), lib, h, f"load_weight({name})")
+        _check(lib.gitb200_student_finalize(h), lib, h, "gitb200_student_finalize")
+        self._h, self._lib, self._stale, self._dev = h, lib, False, p.device
+        self._ld = lib.gitb200_student_logits_ld(h)
+        return h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.gitb200_student_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+
+    # ---- reference methods
+    def forward_image_enc(self, x):
+        """model.py:116-133: [B, F, C, H, W] -> (stage feature maps, memory [B, F, De]) through the supplied image encoder."""
+        if self.image_encoder is None:
+            raise RuntimeError("no image encoder: the reference builds a timm TinyViT (model.py:35-48), which this library does "
+                               "not contain; pass image_encoder= or call greedy_decode_from_memory / forward_decoder with memory")
+        shape = x.shape
+        fmaps = self.image_encoder(x.view(shape[0] * shape[1], *shape[2:]))
+        memory = torch.mean(fmaps[-1], dim=[2, 3]).view(shape[0], shape[1], -1)
+        return fmaps, memory
+
+    @torch.no_grad()
+    def forward_decoder(self, y: torch.Tensor, memory: torch.Tensor) -> torch.Tensor:
+        """model.py:135-154: y int [B, L], memory [B, F, d_model] -> logits fp32 [B, L, vocab]."""
+        h = self._engine()
+        tok = y.to(device=self._dev, dtype=torch.int32).contiguous()
+        mem = memory.to(device=self._dev, dtype=torch.float32).contiguous()
+        B, L = tok.shape
+        if mem.shape[0] != B or mem.shape[2] != self.d_model:
+            raise ValueError("memory must be [B, F, d_model]")
+        logits = torch.empty(B * L, self._ld, dtype=torch.float32, device=self._dev)
+        _check(self._lib.gitb200_student_forward_decoder(h, _ptr(tok), _ptr(mem), B, L, mem.shape[1], _ptr(logits), self._stream()),
+               self._lib, h, "gitb200_student_forward_decoder")
+        return logits.view(B, L, self._ld)[:, :, : self.embed.num_embeddings]
+
+    @torch.no_grad()
+    def greedy_decode_from_memory(self, memory: torch.Tensor, max_len: int = 10) -> torch.Tensor:
+        """model.py:165-187 after the image encoder: LongTensor [B, <= max_len + 1] starting with CLS; decoding stops only
+        when every row emits SEP in the same step (:184)."""
+        h = self._engine()
+        mem = memory.to(device=self._dev, dtype=torch.float32).contiguous()
+        B = mem.shape[0]
+        tokens = torch.empty(B, max_len + 1, dtype=torch.int32, device=self._dev)
+        out_len = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        _check(self._lib.gitb200_student_greedy_decode(h, _ptr(mem), B, mem.shape[1], max_len, _ptr(tokens), _ptr(out_len), self._stream()),
+               self._lib, h, "gitb200_student_greedy_decode")
+        return tokens[:, : int(out_len.item())].long()
+
+    @torch.no_grad()
+    def greedy_decode(self, src: torch.Tensor, max_len: int = 10) -> torch.Tensor:
+        """model.py:156-187."""
+        _, memory = self.forward_image_enc(src)
+        return self.greedy_decode_from_memory(memory, max_len)
+
+    def forward(self, x, y):
+        """model.py:107-114: feature maps of the image encoder + the decoder logits."""
+        fmaps, memory = self.forward_image_enc(x)
+        return list(fmaps) + [self.forward_decoder(y, memory)]
