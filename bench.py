@@ -122,7 +122,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step (512: +3.5 % over 256, the decode-step weights amortise over more rows)")
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--max-steps", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
