@@ -102,6 +102,22 @@ __device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar) {
       : "memory");
 }
 
+#ifdef GEMM2_TRACE
+// Debug build only (tools/gemm2_trace.cu): phase timestamps of CTA 0, [warp][tile iteration][phase]
+__device__ long long g_gemm2_trace[10 * 16 * 8];
+#define G2TRACE(it, ph)                                                                                   \
+  do {                                                                                                    \
+    if (lane == 0 && blockIdx.x == 0 && (it) < 16) g_gemm2_trace[(warp * 16 + (it)) * 8 + (ph)] = clock64(); \
+  } while (0)
+#else
+#define G2TRACE(it, ph) do { } while (0)
+#endif
+
+// FOLD: the optional folded-LayerNorm epilogue (ln_stats / stats_out) is compiled into a separate instantiation.  As run-time
+// flags the compiler if-converted it into predicated FFMA / FMUL / PRMT that every element of every GEMM still issued
+// (ncu: 10.6 issued instructions per output element for a plain bias epilogue), and the 8 epilogue warps -- not the
+// tensor pipe -- set the tile period of the K = 768 GEMMs.
+template <bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, int M, int N, int K,
@@ -192,8 +208,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       uint32_t tile_it = 0;  // tiles issued so far: accumulator = tile_it & 1, phase = (tile_it >> 1) & 1
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_it) {
         const uint32_t acc = tile_it & 1u;
+        G2TRACE(tile_it, 0);
         ptx::mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
+        G2TRACE(tile_it, 1);
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t stage = it % STAGES;
@@ -205,8 +223,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_bf16_pair_elect(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           umma_commit_pair_elect(empty_bar(stage));
+          if (kb == 0) G2TRACE(tile_it, 2);
           if (kb == num_kb - 1) umma_commit_pair_elect(tfull_bar(acc));
         }
+        G2TRACE(tile_it, 3);
       }
     }
   } else {
@@ -220,16 +240,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint32_t res_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int e_it = -1;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      ++e_it;
       const int m0 = (tile / n_tiles) * 2 * BM + (int)rank * BM;
       const int n0 = (tile % n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
+      G2TRACE(e_it, 0);
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
+      G2TRACE(e_it, 1);
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
       const int my_row = row0 + lane;
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (ep.ln_stats != nullptr && my_row < M) {
+      if (FOLD && ep.ln_stats != nullptr && my_row < M) {
         const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + my_row);
         ln_mean = st.x * ep.ln_inv_k;
         ln_rstd = rsqrtf(fmaxf(st.y * ep.ln_inv_k - ln_mean * ln_mean, 0.f) + ep.ln_eps);
@@ -239,8 +263,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll 1
         for (int c = c_begin; c < c_end; c += EPI_COLS) {
           const int col = n0 + c;
+          // this block's 64 bias values go to registers BEFORE the waits below: inside the chunk loop every load sat
+          // behind the previous chunk's st.shared (asm memory clobber) and its latency was paid 8 times per block
+          float4 bia[16];
+          if (ep.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bia[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+          }
           if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous block has left the staging buffer
           __syncwarp();
+          G2TRACE(e_it, c == c_begin ? 2 : 5);
           if (ep.has_res) {
             ptx::mbar_arrive_expect_tx_elect(rbar, STAGING_BYTES);
             ptx::tma_load_2d_elect(stg, &tmap_res, rbar, col, row0);
@@ -249,6 +281,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c, v0);
           ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c + 32), v1);
           ptx::tmem_ld_wait();
+          G2TRACE(e_it, c == c_begin ? 3 : 6);
           if (ep.has_res) {
             ptx::mbar_wait(rbar, res_phase);
             res_phase ^= 1u;
@@ -258,7 +291,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
-            if (ep.ln_stats != nullptr) {  // rstd * (acc - mean * colsum[n])
+            if (FOLD && ep.ln_stats != nullptr) {  // rstd * (acc - mean * colsum[n])
               const float4 c0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + j * 8));
               const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col + j * 8 + 4));
               const float nm = -ln_mean;
@@ -268,8 +301,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
               f[6] = fmaf(nm, c1.z, f[6]) * ln_rstd; f[7] = fmaf(nm, c1.w, f[7]) * ln_rstd;
             }
             if (ep.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j * 8 + 4));
+              const float4 b0 = bia[2 * j], b1 = bia[2 * j + 1];
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
@@ -293,7 +325,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
             const uint32_t p0 = pack_bf16(f[0], f[1]), p1 = pack_bf16(f[2], f[3]), p2 = pack_bf16(f[4], f[5]), p3 = pack_bf16(f[6], f[7]);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
-            if (ep.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
+            if (FOLD && ep.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
               const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1), r2 = unpack_bf16(p2), r3 = unpack_bf16(p3);
               so1 += (r0.x + r0.y) + (r1.x + r1.y) + (r2.x + r2.y) + (r3.x + r3.y);
               so2 = fmaf(r0.x, r0.x, so2); so2 = fmaf(r0.y, r0.y, so2); so2 = fmaf(r1.x, r1.x, so2); so2 = fmaf(r1.y, r1.y, so2);
@@ -306,9 +338,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             ptx::tma_store_2d(&tmap_out, stg, col, row0);
             ptx::tma_store_commit();
           }
+          G2TRACE(e_it, c == c_begin ? 4 : 7);
         }
       }
-      if (ep.stats_out != nullptr && my_row < M) {
+      if (FOLD && ep.stats_out != nullptr && my_row < M) {
         atomicAdd(ep.stats_out + 2 * (size_t)my_row, so1);
         atomicAdd(ep.stats_out + 2 * (size_t)my_row + 1, so2);
       }
@@ -336,7 +369,8 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (a.N % BN != 0 || a.out == nullptr || a.out_f32 != nullptr || a.gin > 0 || a.res_periodic) return cudaErrorNotSupported;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -350,7 +384,10 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   int clusters = gemm_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
   Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out};
-  gemm2_kernel<<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
+  if (a.ln_stats != nullptr || a.stats_out != nullptr)
+    gemm2_kernel<true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
+  else
+    gemm2_kernel<false><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
   note_launch();
   return cudaGetLastError();
 }
