@@ -314,7 +314,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05) + gemm_tcgen05_kernel<128> (decode rows)",
                 "achieved": gemm_tflops, "peak": sustained,
                 "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
-                "traffic_note": "avg DRAM bytes per launch of the 4 ViT-layer GEMMs at M=75648 (profiles/r01_gemm2_ncu_summary.md)",
+                "traffic_note": "avg DRAM bytes per launch of the 4 ViT-layer GEMMs at M=605184 = 512 clips (profiles/r01_gemm2_v3_summary.md)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / (ms if world == 1 else ms) if ms > 0 else None,
                 "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
