@@ -31,6 +31,7 @@
 #include "kernels.h"
 
 bool gemm_get_tensor_map(const bf16* ptr, int rows, int cols, int ld, int box_cols, int box_rows, CUtensorMap* out);
+int gemm_sm_count();
 
 namespace {
 
@@ -41,7 +42,7 @@ constexpr int K_STAGES = 3, V_STAGES = 4;
 constexpr int Q_BYTES = BQ * 128;         // 16 KB
 constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB
 constexpr int P_BYTES = BQ * 128;         // 16 KB: P[128 x 64 keys] bf16, one buffer per softmax group
-constexpr int N_BARRIERS = 1 + 2 * K_STAGES + 2 * V_STAGES + 8;
+constexpr int N_BARRIERS = 2 + 2 * K_STAGES + 2 * V_STAGES + 8;
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES + 256 /*barriers + tmem slot*/ +
                            2 * BQ * 8 /*(m, l) exchange*/;
 constexpr int NUM_SM_WARPS = 8;   // warps 2-5: softmax group 0, warps 6-9: group 1; TMEM lane quarter = warp & 3
@@ -111,13 +112,19 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 __device__ __forceinline__ void merge_bar_sync() {  // named barrier 1: all softmax warps
   asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory");
 }
+__device__ __forceinline__ void merge_bar_sync2() {  // named barrier 4: all softmax warps, end of a work item
+  asm volatile("bar.sync 4, %0;" ::"n"(32 * 8) : "memory");
+}
 
+#ifndef ATTN_TRACE_ITEM
+#define ATTN_TRACE_ITEM 0
+#endif
 #ifdef ATTN_TRACE
 // Debug build only (tools/attn_bench.cu): per-warp phase timestamps of one CTA, [warp][block][phase]
 __device__ long long g_attn_trace[10 * 32 * 12];
 #define TRACE(blk, ph)                                                                                              \
   do {                                                                                                              \
-    if (lane == 0 && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == ATTN_TRACE && (blk) < 32)                  \
+    if (lane == 0 && blockIdx.x == ATTN_TRACE && (blk) < 32)                  \
       g_attn_trace[(warp * 32 + (blk)) * 12 + (ph)] = clock64();                                                     \
   } while (0)
 #else
@@ -127,7 +134,7 @@ __device__ long long g_attn_trace[10 * 32 * 12];
 template <int ATTN_POLY_PAIRS>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    bf16* __restrict__ out, int ldo, int group_len, int heads, float scale_log2) {
+                    bf16* __restrict__ out, int ldo, int group_len, int heads, int n_groups, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);
   const uint32_t sQ = smem_base;
@@ -135,12 +142,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   auto sV = [&](int s) { return smem_base + Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
   auto sP = [&](int g) { return smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + g * P_BYTES; };
   const uint32_t bar_base = smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES;
-  const uint32_t q_full = bar_base;
-  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar_base + 8u * (1 + K_STAGES + s); };
-  auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * K_STAGES + s); };
-  auto v_empty = [&](int s) { return bar_base + 8u * (1 + 2 * K_STAGES + V_STAGES + s); };
-  const uint32_t bar_g = bar_base + 8u * (1 + 2 * K_STAGES + 2 * V_STAGES);
+  const uint32_t q_full = bar_base, q_empty = bar_base + 8u;
+  auto k_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (2 + K_STAGES + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + V_STAGES + s); };
+  const uint32_t bar_g = bar_base + 8u * (2 + 2 * K_STAGES + 2 * V_STAGES);
   auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S[g] holds a new block
   auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S[g] has been read into registers
   auto o_full = [&](int g) { return bar_g + 8u * (6 + g); };  // MMA -> group g: O[g] += P V finished, P[g] is free
@@ -149,11 +156,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, g_idx = blockIdx.z;
   const int width = heads * HD;
-  const int row0 = g_idx * group_len;  // first row of the group in the qkv matrix
-  const int q0 = qt * BQ;
   const int n_blocks = (group_len + BKV - 1) / BKV;
+  // PERSISTENT: the CTA walks work items (query tile, head, group) with stride gridDim.x.  Barriers, TMEM and the K / V
+  // rings live across items, so the TMA producer and the S issuer run ahead into the next item while the softmax groups
+  // still finish the current one -- the ~3 us of per-CTA start-up (barrier init, TMEM allocation, first TMA round trip)
+  // and tear-down that a 4-block ViT tile used to pay once per tile is paid once per CTA.
+  const int n_qt = (group_len + BQ - 1) / BQ;
+  const int n_items = n_qt * heads * n_groups;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
@@ -162,6 +172,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1) {
     if (lane == 0) {
       ptx::mbar_init(q_full, 1);
+      ptx::mbar_init(q_empty, 1);
       for (int s = 0; s < K_STAGES; ++s) {
         ptx::mbar_init(k_full(s), 1);
         ptx::mbar_init(k_empty(s), 1);
@@ -191,48 +202,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
-    ptx::mbar_arrive_expect_tx_elect(q_full, Q_BYTES);
-    ptx::tma_load_2d_elect(sQ, &tmap_q, q_full, h * HD, row0 + q0);
-    for (int j = 0; j < n_blocks; ++j) {
-      const int ks = j % K_STAGES, vs = j % V_STAGES;
-      ptx::mbar_wait(k_empty(ks), (uint32_t)(((j / K_STAGES) & 1) ^ 1));
-      ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
-      ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h * HD, row0 + j * BKV);
-      ptx::mbar_wait(v_empty(vs), (uint32_t)(((j / V_STAGES) & 1) ^ 1));
-      ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
-      ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h * HD, row0 + j * BKV);
+    uint32_t kc = 0;  // key blocks loaded so far (all items): ring stage / phase of K and V follow from it
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int qt = w % n_qt, h = (w / n_qt) % heads, g_idx = w / (n_qt * heads);
+      const int row0 = g_idx * group_len;
+      ptx::mbar_wait(q_empty, (uint32_t)((it & 1) ^ 1));  // every S product of the previous item has read Q
+      ptx::mbar_arrive_expect_tx_elect(q_full, Q_BYTES);
+      ptx::tma_load_2d_elect(sQ, &tmap_q, q_full, h * HD, row0 + qt * BQ);
+      for (int j = 0; j < n_blocks; ++j, ++kc) {
+        const int ks = kc % K_STAGES, vs = kc % V_STAGES;
+        ptx::mbar_wait(k_empty(ks), (uint32_t)(((kc / K_STAGES) & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
+        ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h * HD, row0 + j * BKV);
+        ptx::mbar_wait(v_empty(vs), (uint32_t)(((kc / V_STAGES) & 1) ^ 1));
+        ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
+        ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h * HD, row0 + j * BKV);
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ S issuer (whole warp, elected lane issues)
-    ptx::mbar_wait(q_full, 0);
-    ptx::tc_fence_after();
     const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
-    // S_j = Q K_j^T over the head dim (4 steps of 16) into S[j & 1]
-    auto issue_s = [&](int j) {
-      const int ks = j % K_STAGES;
-      const int nk = min(BKV, group_len - j * BKV);
-      const int nk16 = (nk + 15) & ~15;
-      TRACE(j, 0);
-      ptx::mbar_wait(k_full(ks), (uint32_t)((j / K_STAGES) & 1));
-      ptx::mbar_wait(v_full(j % V_STAGES), (uint32_t)((j / V_STAGES) & 1));  // s_full(j) then also means "V_j has landed"
+    uint32_t kc = 0;             // key blocks issued so far (all items)
+    uint32_t fills0 = 0, fills1 = 0;  // fills of S[0] / S[1] so far
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      ptx::mbar_wait(q_full, (uint32_t)(it & 1));
       ptx::tc_fence_after();
-      TRACE(j, 1);
-      const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
-      const uint32_t id_s = idesc_qk(nk16);
+      for (int j = 0; j < n_blocks; ++j, ++kc) {
+        const int g = j & 1;
+        const uint32_t fills = g ? fills1 : fills0;
+        if (fills > 0) {  // the previous block of this buffer (possibly of the previous item) has left S[g]
+          ptx::mbar_wait(s_free(g), (fills - 1) & 1u);
+          ptx::tc_fence_after();
+        }
+        // S_j = Q K_j^T over the head dim (4 steps of 16) into S[j & 1]
+        const int ks = kc % K_STAGES;
+        const int nk = min(BKV, group_len - j * BKV);
+        const int nk16 = (nk + 15) & ~15;
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 0);
+        ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
+        ptx::mbar_wait(v_full(kc % V_STAGES), (kc / V_STAGES) & 1u);  // s_full(j) then also means "V_j has landed"
+        ptx::tc_fence_after();
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 1);
+        const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
+        const uint32_t id_s = idesc_qk(nk16);
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        ptx::umma_bf16_elect(tS + (uint32_t)((j & 1) * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
-      TRACE(j, 2);
-      ptx::umma_commit_elect(k_empty(ks));  // K_j is dead once S_j has been computed
-      ptx::umma_commit_elect(s_full(j & 1));
-      TRACE(j, 3);
-    };
-    issue_s(0);
-    if (n_blocks > 1) issue_s(1);
-    for (int j = 2; j < n_blocks; ++j) {
-      ptx::mbar_wait(s_free(j & 1), (uint32_t)(((j - 2) >> 1) & 1));  // block j - 2 has left S[j & 1]
-      ptx::tc_fence_after();
-      issue_s(j);
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16_elect(tS + (uint32_t)(g * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
+        ptx::umma_commit_elect(k_empty(ks));  // K_j is dead once S_j has been computed
+        ptx::umma_commit_elect(s_full(g));
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
+        if (g) ++fills1; else ++fills0;
+      }
+      ptx::umma_commit_elect(q_empty);  // Q may be replaced once every S product of this item has completed
     }
   } else {
     // ------------------------------------------------------------ softmax warpgroups: one thread per query row
@@ -240,7 +264,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int grp = (warp - 2) >> 2;    // 0: even key blocks, 1: odd key blocks
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform
     const uint32_t tSg = tS + (uint32_t)(grp * 64) + lane_off;
     const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
     const uint32_t sPg = sP(grp) + (uint32_t)r * 128u;
@@ -248,15 +271,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                      // share a scheduler with the TMA / S-issue warps
     const uint32_t tOg_base = tO + (uint32_t)(grp * 64);
     const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP(grp));
+    const bool has1 = n_blocks > 1;
+    uint32_t done = 0;  // key blocks this group has processed so far (all items): phase of s_full / o_full
+    int it = 0;
     float m_run = -INFINITY, l_run = 0.f;
 
     // One 64-key block.  TAIL = the last block of a group (masked keys); every other block takes the straight path.
-    auto block = [&](int j, auto tail_tag) {
+    // first: the group's first block of this work item (nothing to wait for: O[grp] / P[grp] were released by the merge)
+    auto block = [&](int j, bool first, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
-      const int it = j >> 1;
       const int nk = TAIL ? group_len - j * BKV : BKV;
       float s[64];
-      TRACE(j, 0);
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 0);
       {
         uint32_t v0[32], v1[32];
         ptx::tmem_ld_32x32b_x32(tSg, v0);
@@ -268,10 +294,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           s[32 + i] = __uint_as_float(v1[i]);
         }
       }
-      // S[grp] is in registers: the MMA thread may overwrite it with block j + 2
+      // S[grp] is in registers: the S issuer may overwrite it with this group's next block
       ptx::tc_fence_before();
       ptx::mbar_arrive_elect(s_free(grp));
-      TRACE(j, 1);
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 1);
       if (TAIL) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -283,10 +309,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float m_blk = mx * scale_log2;  // scale > 0: max commutes with it
       // lazy running max: move it only when this block would push P above 2^RESCALE_THRESHOLD
       const bool need = m_blk > m_run + RESCALE_THRESHOLD;  // always true on the group's first block (m_run = -inf)
-      TRACE(j, 2);
-      if (it > 0) {
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
+      if (!first) {
         // P[grp] / O[grp] are free once the previous product of this group has completed
-        ptx::mbar_wait(o_full(grp), (uint32_t)((it - 1) & 1));
+        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
         ptx::tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;
@@ -303,7 +329,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st_wait();
         }
       }
-      TRACE(j, 3);
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
       if (need) m_run = m_blk;
       const float2 sc2 = make_float2(scale_log2, scale_log2);
       const float2 nm2 = make_float2(-m_run, -m_run);
@@ -330,99 +356,112 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       sum_a = __fadd2_rn(sum_a, sum_b);
       l_run += sum_a.x + sum_a.y;
-      TRACE(j, 4);
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 4);
     };
 
-    for (int j = grp; j < n_blocks; j += 2) {
-      ptx::mbar_wait(s_full(grp), (uint32_t)((j >> 1) & 1));
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int qt = w % n_qt, h = (w / n_qt) % heads, g_idx = w / (n_qt * heads);
+      const int row0 = g_idx * group_len, q0 = qt * BQ;
+      const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform
+      const uint32_t kc0 = (uint32_t)it * (uint32_t)n_blocks;    // key blocks of earlier items: V ring position
+      m_run = -INFINITY;
+      l_run = 0.f;
+      for (int j = grp; j < n_blocks; j += 2, ++done) {
+        const bool first = j == grp;
+        ptx::mbar_wait(s_full(grp), done & 1u);
+        ptx::tc_fence_after();
+        if (warp_has_rows) {
+          if (j + 1 < n_blocks || group_len % BKV == 0)
+            block(j, first, std::false_type{});
+          else
+            block(j, first, std::true_type{});
+        } else {
+          // no valid query rows in this warp: keep the barrier phases in step
+          ptx::mbar_arrive_elect(s_free(grp));
+          if (!first) ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
+        }
+        ptx::fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
+        ptx::tc_fence_before();    // O rescale (tcgen05.st) ordered before the MMA that accumulates into O
+        __syncwarp();
+        if (quarter != pv_quarter) {
+          if (grp == 0) asm volatile("bar.arrive 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+          else asm volatile("bar.arrive 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+        } else {
+          // this warp issues O[grp] (+)= P_j V_j as soon as the four warps of the group have delivered P_j (named
+          // barrier: the other three only arrive and run ahead): the product is issued by the warpgroup that produced
+          // its operand, nobody polls for it.  V_j is resident (the S issuer waited for it before S_j).
+          const int vs = (int)((kc0 + (uint32_t)j) % V_STAGES);
+          const int nk = min(BKV, group_len - j * BKV);
+          const int nk16 = (nk + 15) & ~15;
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
+          if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+          else asm volatile("bar.sync 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
+          ptx::tc_fence_after();
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
+          const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));
+          const uint32_t acc0 = first ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
+            if (k * 16 < nk16)
+              ptx::umma_bf16_elect(tOg_base, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
+          ptx::umma_commit_elect(v_empty(vs));
+          ptx::umma_commit_elect(o_full(grp));
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
+        }
+        __syncwarp();
+      }
+      // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
+      if (grp == 0 || has1) {
+        // every thread has followed all phases of its OWN group's o_full barrier, so this parity wait is exact; the other
+        // group's last product is covered by that group's threads before they reach the named barrier below
+        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
+      }
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)(grp * BQ + r) * 8u), "f"(m_run), "f"(l_run) : "memory");
+      merge_bar_sync();
       ptx::tc_fence_after();
       if (warp_has_rows) {
-        if (j + 1 < n_blocks || group_len % BKV == 0)
-          block(j, std::false_type{});
-        else
-          block(j, std::true_type{});
-      } else {
-        // no valid query rows in this warp: keep the barrier phases in step
-        ptx::mbar_arrive_elect(s_free(grp));
-        if (j >= 2) ptx::mbar_wait(o_full(grp), (uint32_t)(((j >> 1) - 1) & 1));
-      }
-      ptx::fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-      ptx::tc_fence_before();    // O rescale (tcgen05.st) ordered before the MMA that accumulates into O
-      __syncwarp();
-      if (quarter != pv_quarter) {
-        if (grp == 0) asm volatile("bar.arrive 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-        else asm volatile("bar.arrive 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-      } else {
-        // this warp issues O[grp] (+)= P_j V_j as soon as the four warps of the group have delivered P_j (named
-        // barrier: the other three only arrive and run ahead): the product is issued by the warpgroup that produced
-        // its operand, nobody polls for it.  V_j is resident (the S issuer waited for it before S_j).
-        const int vs = j % V_STAGES;
-        const int nk = min(BKV, group_len - j * BKV);
-        const int nk16 = (nk + 15) & ~15;
-        TRACE(j, 5);
-        if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-        else asm volatile("bar.sync 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-        ptx::tc_fence_after();
-        TRACE(j, 6);
-        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));
-        const uint32_t acc0 = j >= 2;
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
-          if (k * 16 < nk16)
-            ptx::umma_bf16_elect(tOg_base, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
-        TRACE(j, 9);
-        ptx::umma_commit_elect(v_empty(vs));
-        ptx::umma_commit_elect(o_full(grp));
-        TRACE(j, 7);
-      }
-      __syncwarp();
-    }
-    // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
-    const bool has1 = n_blocks > 1;
-    if (grp == 0 || has1) {
-      // every thread has followed all phases of its OWN group's o_full barrier, so this parity wait is exact; the other
-      // group's last product is covered by that group's threads before they reach the named barrier below
-      const int last = grp == 0 ? ((n_blocks - 1) & ~1) : (((n_blocks - 2) & ~1) + 1);
-      ptx::mbar_wait(o_full(grp), (uint32_t)((last >> 1) & 1));
-    }
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)(grp * BQ + r) * 8u), "f"(m_run), "f"(l_run) : "memory");
-    merge_bar_sync();
-    ptx::tc_fence_after();
-    if (warp_has_rows) {
-      float m_o, l_o;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(sML + (uint32_t)((grp ^ 1) * BQ + r) * 8u) : "memory");
-      const float m0 = grp == 0 ? m_run : m_o, m1 = grp == 0 ? m_o : m_run;
-      const float l0 = grp == 0 ? l_run : l_o, l1 = grp == 0 ? l_o : l_run;
-      const float m = has1 ? fmaxf(m0, m1) : m0;
-      float w0 = ex2_approx(m0 - m), w1 = has1 ? ex2_approx(m1 - m) : 0.f;
-      const float inv = 1.f / (l0 * w0 + (has1 ? l1 * w1 : 0.f));
-      w0 *= inv;
-      w1 *= inv;
-      // this thread writes output dims [32 grp, 32 grp + 32) of its row
-      uint32_t a[32];
-      float o[32];
-      ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(grp * 32), a);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]) * w0;
-      if (has1) {
-        ptx::tmem_ld_32x32b_x32(tO + 64u + lane_off + (uint32_t)(grp * 32), a);
+        float m_o, l_o;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(sML + (uint32_t)((grp ^ 1) * BQ + r) * 8u) : "memory");
+        const float m0 = grp == 0 ? m_run : m_o, m1 = grp == 0 ? m_o : m_run;
+        const float l0 = grp == 0 ? l_run : l_o, l1 = grp == 0 ? l_o : l_run;
+        const float m = has1 ? fmaxf(m0, m1) : m0;
+        float w0 = ex2_approx(m0 - m), w1 = has1 ? ex2_approx(m1 - m) : 0.f;
+        const float inv = 1.f / (l0 * w0 + (has1 ? l1 * w1 : 0.f));
+        w0 *= inv;
+        w1 *= inv;
+        // this thread writes output dims [32 grp, 32 grp + 32) of its row
+        uint32_t a[32];
+        float o[32];
+        ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(grp * 32), a);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(a[i]), w1, o[i]);
-      }
-      const int q = q0 + r;
-      if (q < group_len) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD + grp * 32);
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]) * w0;
+        if (has1) {
+          ptx::tmem_ld_32x32b_x32(tO + 64u + lane_off + (uint32_t)(grp * 32), a);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16(o[c * 8 + 0], o[c * 8 + 1]);
-          u.y = pack_bf16(o[c * 8 + 2], o[c * 8 + 3]);
-          u.z = pack_bf16(o[c * 8 + 4], o[c * 8 + 5]);
-          u.w = pack_bf16(o[c * 8 + 6], o[c * 8 + 7]);
-          dst[c] = u;
+          for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(a[i]), w1, o[i]);
         }
+        // both accumulators and the (m, l) exchange are in registers: the next item may overwrite them
+        ptx::tc_fence_before();
+        merge_bar_sync2();
+        const int q = q0 + r;
+        if (q < group_len) {
+          uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD + grp * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = pack_bf16(o[c * 8 + 0], o[c * 8 + 1]);
+            u.y = pack_bf16(o[c * 8 + 2], o[c * 8 + 3]);
+            u.z = pack_bf16(o[c * 8 + 4], o[c * 8 + 5]);
+            u.w = pack_bf16(o[c * 8 + 6], o[c * 8 + 7]);
+            dst[c] = u;
+          }
+        }
+      } else {
+        ptx::tc_fence_before();
+        merge_bar_sync2();
       }
     }
   }
@@ -452,14 +491,17 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   CUtensorMap tq, tkv;
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BQ, &tq)) return cudaErrorInvalidValue;
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BKV, &tkv)) return cudaErrorInvalidValue;
-  dim3 grid((group_len + BQ - 1) / BQ, heads, n_groups);
+  const int n_items = ((group_len + BQ - 1) / BQ) * heads * n_groups;
+  int grid = 2 * gemm_sm_count();  // two CTAs per SM (TMEM: 2 x 256 columns), each walks items with stride `grid`
+  if (n_items < grid) grid = n_items;
+  const float sl2 = scale * 1.4426950408889634f;
 #ifdef ATTN_FORCE_POLY_PAIRS
-  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
 #else
   if (group_len >= LONG_GROUP)
-    attention_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+    attention_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
   else
-    attention_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, scale * 1.4426950408889634f);
+    attention_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
 #endif
   note_launch();
   return cudaGetLastError();
