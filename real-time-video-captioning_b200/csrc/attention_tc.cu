@@ -45,8 +45,10 @@ constexpr int P_BYTES = BQ * 128;         // 16 KB: P[128 x 64 keys] bf16, one b
 constexpr int N_BARRIERS = 2 + 2 * K_STAGES + 2 * V_STAGES + 8;
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES + 256 /*barriers + tmem slot*/ +
                            2 * BQ * 8 /*(m, l) exchange*/;
-constexpr int NUM_SM_WARPS = 8;   // warps 2-5: softmax group 0, warps 6-9: group 1; TMEM lane quarter = warp & 3
-constexpr int NUM_THREADS = 64 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM owner
+constexpr int NUM_SM_WARPS = 8;   // warps 4-7: softmax group 0, warps 8-11: group 1; TMEM lane quarter = warp & 3
+constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: S issuer + TMEM owner, warps 2 / 3: P V issuers
+constexpr int SERVICE_REGS = 32, SOFTMAX_REGS = 104;  // setmaxnreg split: the increase is served from the CTA's OWN pool (what its service
+                                                      // warps released; more than that deadlocks), so 128 x 32 + 256 x 104 = 30720 = the launch allocation 384 x 80
 constexpr int TMEM_COLS = 256;    // S[0]: [0,64), S[1]: [64,128), O[0]: [128,192), O[1]: [192,256)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P never exceeds 2^8 before the running max moves
 
@@ -121,7 +123,7 @@ __device__ __forceinline__ void merge_bar_sync2() {  // named barrier 4: all sof
 #endif
 #ifdef ATTN_TRACE
 // Debug build only (tools/attn_bench.cu): per-warp phase timestamps of one CTA, [warp][block][phase]
-__device__ long long g_attn_trace[10 * 32 * 12];
+__device__ long long g_attn_trace[12 * 32 * 12];
 #define TRACE(blk, ph)                                                                                              \
   do {                                                                                                              \
     if (lane == 0 && blockIdx.x == ATTN_TRACE && (blk) < 32)                  \
@@ -131,7 +133,7 @@ __device__ long long g_attn_trace[10 * 32 * 12];
 #define TRACE(blk, ph) do { } while (0)
 #endif
 
-template <int ATTN_POLY_PAIRS>
+template <int ATTN_POLY_PAIRS, bool EXP_FIRST>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     bf16* __restrict__ out, int ldo, int group_len, int heads, int n_groups, float scale_log2) {
@@ -150,6 +152,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t bar_g = bar_base + 8u * (2 + 2 * K_STAGES + 2 * V_STAGES);
   auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S[g] holds a new block
   auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S[g] has been read into registers
+  auto p_full = [&](int g) { return bar_g + 8u * (4 + g); };  // group g -> its P V issuer: P[g] written (and O[g] rescaled)
   auto o_full = [&](int g) { return bar_g + 8u * (6 + g); };  // MMA -> group g: O[g] += P V finished, P[g] is free
   const uint32_t tmem_slot = bar_base + 8u * N_BARRIERS;
   const uint32_t sML = bar_base + 256;  // float2 [2 groups][128 rows]: (m, l) of each group's partial softmax
@@ -184,6 +187,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int g = 0; g < 2; ++g) {
         ptx::mbar_init(s_full(g), 1);
         ptx::mbar_init(s_free(g), NUM_SM_WARPS / 2);  // one arrival per warp of the group
+        ptx::mbar_init(p_full(g), NUM_SM_WARPS / 2);
         ptx::mbar_init(o_full(g), 1);
       }
       ptx::fence_barrier_init();
@@ -198,10 +202,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = ptx::warp_uniform(tmem_base);
+  // register split (inside each role's branch, so that ptxas budgets the role's code accordingly): the four service warps
+  // (TMA, S issue, two P V issuers) hand registers to the eight softmax warps
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
     uint32_t kc = 0;  // key blocks loaded so far (all items): ring stage / phase of K and V follow from it
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -222,6 +229,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ S issuer (whole warp, elected lane issues)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
     const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
     uint32_t kc = 0;             // key blocks issued so far (all items)
     uint32_t fills0 = 0, fills1 = 0;  // fills of S[0] / S[1] so far
@@ -258,19 +266,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       ptx::umma_commit_elect(q_empty);  // Q may be replaced once every S product of this item has completed
     }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ P V issuer of softmax group g = warp - 2 (whole warp,
+    // elected lane issues): O[g] (+)= P_j V_j as soon as the four warps of the group have delivered P_j.  One issuer per
+    // group: each follows a single event stream with blocking waits (a shared, polling issuer spent 40 % of the kernel's
+    // issue slots spinning; issuing from a softmax warp made that warp 800 cycles per block slower than its three peers).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
+    const int g = warp - 2;
+    const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP(g));
+    uint32_t done = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const uint32_t kc0 = (uint32_t)it * (uint32_t)n_blocks;  // key blocks of earlier items: V ring position
+      for (int j = g; j < n_blocks; j += 2, ++done) {
+        const int vs = (int)((kc0 + (uint32_t)j) % V_STAGES);
+        const int nk = min(BKV, group_len - j * BKV);
+        const int nk16 = (nk + 15) & ~15;
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
+        ptx::mbar_wait(p_full(g), done & 1u);
+        ptx::tc_fence_after();
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
+        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // V_j is resident: the S issuer waited for it before S_j
+        const uint32_t acc0 = j == g ? 0u : 1u;               // the group's first block of an item starts a new O
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
+          if (k * 16 < nk16)
+            ptx::umma_bf16_elect(tO + (uint32_t)(g * 64), dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
+        ptx::umma_commit_elect(v_empty(vs));
+        ptx::umma_commit_elect(o_full(g));
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
+      }
+    }
   } else {
     // ------------------------------------------------------------ softmax warpgroups: one thread per query row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;    // 0: even key blocks, 1: odd key blocks
+    const int grp = (warp - 4) >> 2;    // 0: even key blocks, 1: odd key blocks
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t tSg = tS + (uint32_t)(grp * 64) + lane_off;
     const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
     const uint32_t sPg = sP(grp) + (uint32_t)r * 128u;
-    const int pv_quarter = 2 + grp;  // the warp of this group that issues the PV products: warps 2 and 7, which do not
-                                     // share a scheduler with the TMA / S-issue warps
-    const uint32_t tOg_base = tO + (uint32_t)(grp * 64);
-    const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP(grp));
     const bool has1 = n_blocks > 1;
     uint32_t done = 0;  // key blocks this group has processed so far (all items): phase of s_full / o_full
     int it = 0;
@@ -309,31 +346,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float m_blk = mx * scale_log2;  // scale > 0: max commutes with it
       // lazy running max: move it only when this block would push P above 2^RESCALE_THRESHOLD
       const bool need = m_blk > m_run + RESCALE_THRESHOLD;  // always true on the group's first block (m_run = -inf)
-      if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
-      if (!first) {
-        // P[grp] / O[grp] are free once the previous product of this group has completed
-        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
-        ptx::tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? ex2_approx(m_run - m_blk) : 1.0f;
-          l_run *= alpha;
-#pragma unroll 1
-          for (int c = 0; c < HD; c += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tOg + (uint32_t)c, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32b_x16(tOg + (uint32_t)c, v);
-          }
-          tmem_st_wait();
-        }
-      }
-      if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
+      const float alpha = (need && !first) ? ex2_approx(m_run - m_blk) : 1.0f;  // factor the old O / l have to take
       if (need) m_run = m_blk;
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
+      if constexpr (EXP_FIRST) {
+      // (long groups; measured +8 % on the 1182-key shape, -6 % on the 197-key shape, whose items are too short to amortise
+      // the extra register pressure)  The exponentials are computed BEFORE waiting for the previous product of this group: P stays packed in registers
+      // (32 x bf16x2) until O[grp] / P[grp] are free, so the XU-bound part of the block overlaps the P V latency of the
+      // block before it instead of queueing behind it.
       const float2 sc2 = make_float2(scale_log2, scale_log2);
       const float2 nm2 = make_float2(-m_run, -m_run);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+      uint32_t pk[32];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
         if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;  // chunks beyond the issued 16-key steps are never read
@@ -350,12 +374,83 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         sum_b = __fadd2_rn(sum_b, t1);
         sum_a = __fadd2_rn(sum_a, t2);
         sum_b = __fadd2_rn(sum_b, t3);
+        pk[c8 * 4 + 0] = pack_bf16(t0.x, t0.y);
+        pk[c8 * 4 + 1] = pack_bf16(t1.x, t1.y);
+        pk[c8 * 4 + 2] = pack_bf16(t2.x, t2.y);
+        pk[c8 * 4 + 3] = pack_bf16(t3.x, t3.y);
+      }
+      sum_a = __fadd2_rn(sum_a, sum_b);
+      l_run = fmaf(l_run, alpha, sum_a.x + sum_a.y);
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
+      if (!first) {
+        // P[grp] / O[grp] are free once the previous product of this group has completed
+        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {  // rare: the running max moved, O[grp] takes the factor in TMEM
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tOg + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(tOg + (uint32_t)c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;
+        const uint32_t addr = sPg + (uint32_t)((c8 ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[c8 * 4 + 0]), "r"(pk[c8 * 4 + 1]), "r"(pk[c8 * 4 + 2]),
+                     "r"(pk[c8 * 4 + 3])
+                     : "memory");
+      }
+      } else {
+      if (!first) {
+        // P[grp] / O[grp] are free once the previous product of this group has completed
+        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {  // rare: the running max moved, O[grp] takes the factor in TMEM
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tOg + (uint32_t)c, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(tOg + (uint32_t)c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
+      const float2 sc2 = make_float2(scale_log2, scale_log2);
+      const float2 nm2 = make_float2(-m_run, -m_run);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;  // chunks beyond the issued 16-key steps are never read
+        float2 t0 = __ffma2_rn(make_float2(s[c8 * 8 + 0], s[c8 * 8 + 1]), sc2, nm2);
+        float2 t1 = __ffma2_rn(make_float2(s[c8 * 8 + 2], s[c8 * 8 + 3]), sc2, nm2);
+        float2 t2 = __ffma2_rn(make_float2(s[c8 * 8 + 4], s[c8 * 8 + 5]), sc2, nm2);
+        float2 t3 = __ffma2_rn(make_float2(s[c8 * 8 + 6], s[c8 * 8 + 7]), sc2, nm2);
+        if (ATTN_POLY_PAIRS >= 4) t0 = ex2_poly2(t0); else { t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y); }
+        if (ATTN_POLY_PAIRS >= 3) t1 = ex2_poly2(t1); else { t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y); }
+        if (ATTN_POLY_PAIRS >= 2) t2 = ex2_poly2(t2); else { t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y); }
+        if (ATTN_POLY_PAIRS >= 1) t3 = ex2_poly2(t3); else { t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y); }
+        sum_a = __fadd2_rn(sum_a, t0);
+        sum_b = __fadd2_rn(sum_b, t1);
+        sum_a = __fadd2_rn(sum_a, t2);
+        sum_b = __fadd2_rn(sum_b, t3);
         const uint32_t p0 = pack_bf16(t0.x, t0.y), p1 = pack_bf16(t1.x, t1.y), p2 = pack_bf16(t2.x, t2.y), p3 = pack_bf16(t3.x, t3.y);
         const uint32_t addr = sPg + (uint32_t)((c8 ^ (r & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
       }
       sum_a = __fadd2_rn(sum_a, sum_b);
-      l_run += sum_a.x + sum_a.y;
+      l_run = fmaf(l_run, alpha, sum_a.x + sum_a.y);
+      }
       if (it == ATTN_TRACE_ITEM) TRACE(j, 4);
     };
 
@@ -363,7 +458,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int qt = w % n_qt, h = (w / n_qt) % heads, g_idx = w / (n_qt * heads);
       const int row0 = g_idx * group_len, q0 = qt * BQ;
       const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform
-      const uint32_t kc0 = (uint32_t)it * (uint32_t)n_blocks;    // key blocks of earlier items: V ring position
       m_run = -INFINITY;
       l_run = 0.f;
       for (int j = grp; j < n_blocks; j += 2, ++done) {
@@ -383,32 +477,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
         ptx::tc_fence_before();    // O rescale (tcgen05.st) ordered before the MMA that accumulates into O
         __syncwarp();
-        if (quarter != pv_quarter) {
-          if (grp == 0) asm volatile("bar.arrive 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-          else asm volatile("bar.arrive 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-        } else {
-          // this warp issues O[grp] (+)= P_j V_j as soon as the four warps of the group have delivered P_j (named
-          // barrier: the other three only arrive and run ahead): the product is issued by the warpgroup that produced
-          // its operand, nobody polls for it.  V_j is resident (the S issuer waited for it before S_j).
-          const int vs = (int)((kc0 + (uint32_t)j) % V_STAGES);
-          const int nk = min(BKV, group_len - j * BKV);
-          const int nk16 = (nk + 15) & ~15;
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
-          if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-          else asm volatile("bar.sync 3, %0;" ::"n"(32 * NUM_SM_WARPS / 2) : "memory");
-          ptx::tc_fence_after();
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
-          const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));
-          const uint32_t acc0 = first ? 0u : 1u;
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
-            if (k * 16 < nk16)
-              ptx::umma_bf16_elect(tOg_base, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
-          ptx::umma_commit_elect(v_empty(vs));
-          ptx::umma_commit_elect(o_full(grp));
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
-        }
+        ptx::mbar_arrive_elect(p_full(grp));  // one arrival per warp: the group's P V issuer takes it from here
         __syncwarp();
       }
       // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
@@ -482,8 +551,8 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (ld_qkv % 8 != 0 || ldo % 8 != 0) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -496,12 +565,12 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (n_items < grid) grid = n_items;
   const float sl2 = scale * 1.4426950408889634f;
 #ifdef ATTN_FORCE_POLY_PAIRS
-  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
+  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, (ATTN_FORCE_POLY_PAIRS > 0)><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
 #else
   if (group_len >= LONG_GROUP)
-    attention_tc_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
+    attention_tc_kernel<1, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
   else
-    attention_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
+    attention_tc_kernel<0, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
 #endif
   note_launch();
   return cudaGetLastError();

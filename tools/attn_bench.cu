@@ -34,19 +34,25 @@ static void run(const char* name, int n_groups, int glen, int heads, int iters) 
   const double flops = 4.0 * glen * (double)glen * 64 * heads * n_groups;
   printf("%s groups=%d len=%d: %.3f ms  %.1f TFLOP/s  (%s)\n", name, n_groups, glen, ms, flops / ms / 1e9, cudaGetErrorString(e));
 #ifdef ATTN_TRACE
-  static long long t[10 * 32 * 12];
+  static long long t[12 * 32 * 12];
   cudaMemcpyFromSymbol(t, g_attn_trace, sizeof(t));
   const int nb = (glen + 63) / 64;
   long long t0 = 0;
-  for (int w = 2; w < 10; ++w) if (t[(w * 32 + (w >= 6)) * 12] && (!t0 || t[(w * 32 + (w >= 6)) * 12] < t0)) t0 = t[(w * 32 + (w >= 6)) * 12];
-  printf("phase timestamps (clk since first block start): s_ready ld_done max_done o_ready p_done | pv: wait_start all_arrived issued v_full mmas_issued\n");
+  for (int w = 4; w < 12; ++w) {
+    const long long v = t[(w * 32 + (w >= 8)) * 12];
+    if (v && (!t0 || v < t0)) t0 = v;
+  }
+  printf("clk since the item's first block started | softmax warp: s_ready ld_done max_done exp_or_wait_done p_done\n");
   for (int j = 0; j < nb && j < 32; ++j) {
-    { const long long* r = &t[(1 * 32 + j) * 12]; printf("blk %2d S-issue: start %lld k_full %lld mma_done %lld commits %lld\n", j, r[0]-t0, r[1]-t0, r[2]-t0, r[3]-t0); }
-    for (int w = 2; w < 10; ++w) {
-      if (((w - 2) >> 2) != (j & 1)) continue;
-      const long long* r = &t[(w * 32 + j) * 12];
-      printf("blk %2d warp %d:", j, w);
-      for (int p = 0; p < 10; ++p) printf(" %7lld", r[p] ? r[p] - t0 : -1);
+    const long long* r = &t[(1 * 32 + j) * 12];
+    printf("blk %2d S-issue: start %lld operands_ready %lld mma_issued %lld committed %lld\n", j, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0);
+    r = &t[((2 + (j & 1)) * 32 + j) * 12];
+    printf("blk %2d PV-issue: wait_start %lld p_full %lld mma_issued %lld committed %lld\n", j, r[5] - t0, r[6] - t0, r[9] - t0, r[7] - t0);
+    for (int w = 4; w < 12; ++w) {
+      if (((w - 4) >> 2) != (j & 1)) continue;
+      r = &t[(w * 32 + j) * 12];
+      printf("blk %2d warp %2d:", j, w);
+      for (int p = 0; p < 5; ++p) printf(" %7lld", r[p] ? r[p] - t0 : -1);
       printf("\n");
     }
   }
