@@ -92,6 +92,48 @@ class StudentDecoderOracle(nn.Module):
         return tgt
 
 
+def beam_search_from_memory(forward_decoder, memory: torch.Tensor, cls_token_id: int, max_len: int = 10, k: int = 3) -> torch.Tensor:
+    """StudentCandidateV1.beam_search (model.py:189-316) after ``forward_image_enc``, statement by statement, with
+    ``forward_decoder`` passed in (the oracle module's, or a scripted stand-in in the host-logic tests).  Quirks kept:
+    no end-of-sequence handling (the EOS block is commented out in the reference), every beam's whole sequence is
+    re-decoded every step, k*k candidates are ranked with a full sort, the result is the highest-scoring of the k
+    final beams and always has ``max_len`` tokens."""
+    import torch.nn.functional as F
+    batch_size = memory.size(0)
+    tgt = torch.full((batch_size, 1), cls_token_id, dtype=torch.long)                                     # :200
+    sequences = tgt.unsqueeze(1).expand(-1, k, -1)                                                        # :205
+    all_candidates = torch.empty(batch_size, k * k, 3)                                                    # :207
+    decoder_output = forward_decoder(tgt, memory)                                                         # :223
+    log_probs = F.log_softmax(decoder_output[:, -1, :], dim=-1)                                           # :225
+    scores, top_indices = log_probs.topk(k, dim=-1)                                                       # :227
+    sequences = torch.cat([sequences, top_indices.unsqueeze(-1)], dim=-1)                                 # :229
+    for step in range(2, max_len):                                                                        # :232
+        for i in range(k):                                                                                # :234
+            tgt = sequences[:, i]                                                                         # :236
+            decoder_output = forward_decoder(tgt, memory)                                                 # :239
+            log_probs = F.log_softmax(decoder_output[:, -1, :], dim=-1)                                   # :241
+            top_scores, top_indices = log_probs.topk(k, dim=-1)                                           # :243
+            local_scores = scores[:, i].unsqueeze(-1) + top_scores                                        # :246
+            offset = i * k                                                                                # :248
+            all_candidates[:, offset:offset + k, 0] = local_scores                                        # :249
+            all_candidates[:, offset:offset + k, 1] = i                                                   # :250
+            all_candidates[:, offset:offset + k, 2] = top_indices                                         # :251
+        scores_to_sort = all_candidates[:, :, 0].view(batch_size, -1)                                     # :254
+        _, sorted_indices = scores_to_sort.sort(dim=1, descending=True)                                   # :256
+        topk_indices = sorted_indices[:, :k]                                                              # :258
+        new_sequences = torch.zeros(batch_size, k, step + 1, dtype=torch.long)                            # :260
+        for b in range(batch_size):                                                                       # :262
+            for idx in range(k):
+                global_idx = topk_indices[b, idx]                                                         # :266
+                beam_idx = all_candidates[b, global_idx, 1].long()                                        # :269
+                token_idx = all_candidates[b, global_idx, 2].long()                                       # :270
+                new_sequences[b, idx, :-1] = sequences[b, beam_idx, :]                                    # :273
+                new_sequences[b, idx, -1] = token_idx                                                     # :274
+                scores[b, idx] = all_candidates[b, global_idx, 0]                                         # :277
+        sequences = new_sequences                                                                         # :296
+    return sequences[torch.arange(batch_size), scores.argmax(dim=-1)]                                     # :315
+
+
 def init_student(cfg: StudentConfig, seed: int = 0, logit_gain: float = 1.0) -> StudentDecoderOracle:
     """Seeded random initialisation (PyTorch defaults for every module, then biases / LayerNorm affines perturbed so that
     no term of the arithmetic is silently zero or one)."""

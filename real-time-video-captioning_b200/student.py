@@ -188,6 +188,38 @@ class StudentCandidateV1(nn.Module):
         return tokens[:, : int(out_len.item())].long()
 
     @torch.no_grad()
+    def beam_search_from_memory(self, memory: torch.Tensor, max_len: int = 10, k: int = 3, forward_decoder=None) -> torch.Tensor:
+        """model.py:189-316 after the image encoder: the reference's k x k beam search (no end-of-sequence handling, the
+        result always has ``max_len`` tokens).  All k beams of all clips are decoded in ONE forward_decoder call per
+        step instead of k calls; candidate ranking / beam bookkeeping stay on the device as tensor ops."""
+        fd = forward_decoder or self.forward_decoder
+        B = memory.size(0)
+        dev = memory.device
+        tgt = torch.full((B, 1), self.cls_token_id, dtype=torch.long, device=dev)
+        logp = torch.log_softmax(fd(tgt, memory)[:, -1, :].float(), dim=-1)
+        scores, first = logp.topk(k, dim=-1)                                          # [B, k]
+        sequences = torch.cat([tgt.unsqueeze(1).expand(-1, k, -1), first.unsqueeze(-1)], dim=-1)   # [B, k, 2]
+        mem_k = memory.repeat_interleave(k, dim=0)                                    # row b*k + i = beam i of clip b
+        for step in range(2, max_len):
+            logp = torch.log_softmax(fd(sequences.reshape(B * k, -1), mem_k)[:, -1, :].float(), dim=-1)
+            top_scores, top_tokens = logp.topk(k, dim=-1)                             # [B*k, k]
+            cand = (scores.unsqueeze(-1) + top_scores.view(B, k, k)).view(B, k * k)   # candidate i*k + j = beam i, its j-th word
+            _, order = cand.sort(dim=1, descending=True)
+            pick = order[:, :k]                                                       # [B, k]
+            beam = pick // k
+            scores = torch.gather(cand, 1, pick)
+            words = torch.gather(top_tokens.view(B, k * k), 1, pick)
+            sequences = torch.cat([torch.gather(sequences, 1, beam.unsqueeze(-1).expand(-1, -1, sequences.shape[-1])),
+                                   words.unsqueeze(-1)], dim=-1)
+        return sequences[torch.arange(B, device=dev), scores.argmax(dim=-1)]
+
+    @torch.no_grad()
+    def beam_search(self, src: torch.Tensor, max_len: int = 10, k: int = 3) -> torch.Tensor:
+        """model.py:189-316."""
+        _, memory = self.forward_image_enc(src)
+        return self.beam_search_from_memory(memory.to(self._dev or memory.device), max_len, k)
+
+    @torch.no_grad()
     def greedy_decode(self, src: torch.Tensor, max_len: int = 10) -> torch.Tensor:
         """model.py:156-187."""
         _, memory = self.forward_image_enc(src)

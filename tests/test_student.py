@@ -82,6 +82,18 @@ def test_state_dict_names_follow_the_reference_student():
         s.greedy_decode(torch.zeros(1, 6, 3, 8, 8), 3)
 
 
+def test_beam_search_host_logic_equals_the_reference_loop():
+    """StudentCandidateV1.beam_search (model.py:189-316): the product's batched tensor form against the statement-by-statement
+    restatement, both driven by the same CPU forward_decoder (the oracle module's)."""
+    cfg = _small_cfg()
+    m = st.init_student(cfg, seed=10)
+    mem = torch.randn(4, 6, 64, generator=torch.Generator().manual_seed(11))
+    ref = st.beam_search_from_memory(m.forward_decoder, mem, cfg.cls_token_id, max_len=7, k=3)
+    s = g.StudentCandidateV1(None, 64, 4, 128, 0.3, 2, 50, cfg.cls_token_id, cfg.sep_token_id)
+    out = s.beam_search_from_memory(mem, max_len=7, k=3, forward_decoder=m.forward_decoder)
+    assert out.shape == (4, 7) and torch.equal(out, ref)
+
+
 # ------------------------------------------------------------------------------------------ GPU parity
 def _gpu_student(cfg, seed):
     m = st.init_student(cfg, seed=seed)
@@ -154,3 +166,22 @@ def test_student_greedy_stop_rule_and_reference_facade():
     tok = s.greedy_decode(src, 5)
     _, memory = s.forward_image_enc(src)
     assert memory.shape == (2, 6, 576) and torch.equal(tok.cpu(), m.greedy_decode_from_memory(memory.cpu(), 5))
+
+
+@pytest.mark.gpu
+def test_student_beam_search_on_the_gpu_decoder():
+    """beam_search on the CUDA decoder: the returned sequence, scored by the ORACLE decoder, must be within the logit tolerance
+    of the oracle's own beam-search winner (random-init margins are small, so the two may pick different near-tied beams)."""
+    cfg = st.StudentConfig()
+    m, s = _gpu_student(cfg, seed=12)
+    mem = torch.randn(3, 6, cfg.d_model, generator=torch.Generator().manual_seed(13))
+    out = s.beam_search_from_memory(mem.cuda(), max_len=6, k=3).cpu()
+    ref = st.beam_search_from_memory(m.forward_decoder, mem, cfg.cls_token_id, max_len=6, k=3)
+    assert out.shape == ref.shape == (3, 6) and (out[:, 0] == cfg.cls_token_id).all()
+
+    def seq_score(seq):
+        lp = torch.log_softmax(m.forward_decoder(seq[:, :-1], mem), dim=-1)
+        return torch.gather(lp, -1, seq[:, 1:, None]).squeeze(-1).sum(-1)
+
+    sigma = m.forward_decoder(ref[:, :-1], mem).std().item()
+    assert (seq_score(ref) - seq_score(out) < 5 * 0.15 * sigma).all()
