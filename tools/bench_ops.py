@@ -30,5 +30,20 @@ def attention(B=64):
             print(f"attention {name} B={B} {'mma.sync' if legacy else 'tcgen05 '}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s  ({ms * 1e3 / B:.1f} us/clip/layer)")
 
 
+
+
+def layernorm(rows=605184):
+    import torch.nn.functional as F  # noqa: F401
+    for cols in (768, 1024):
+        x = torch.randn(rows, cols, device="cuda").bfloat16()
+        g = torch.ones(cols, device="cuda")
+        b = torch.zeros(cols, device="cuda")
+        ms = timeit(lambda: eng.op_layernorm(x, g, b, 1e-5))
+        print(f"layernorm rows={rows} cols={cols}: {ms:.3f} ms  {2 * rows * cols * 2 / ms / 1e9:.2f} TB/s")
+
+
 if __name__ == "__main__":
-    attention(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
+    if len(sys.argv) > 2 and sys.argv[2] == "ln":
+        layernorm(int(sys.argv[1]) * 6 * 197)
+    else:
+        attention(int(sys.argv[1]) if len(sys.argv) > 1 else 64)
