@@ -1,5 +1,5 @@
 """Student decoder micro-benchmark: cached greedy decode on the GPU library vs the oracle (the reference's
-stock torch.nn decoder with full re-decode per step) on the host cores.  Usage: python tools/bench_student.py [B] [max_len]"""
+stock torch.nn decoder with full re-decode per step) on the host cores.  Usage: python tests/tools/bench_student.py [B] [max_len]"""
 import importlib
 import os
 import sys
@@ -7,7 +7,7 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import student_oracle as st  # noqa: E402
 
 g = importlib.import_module("real-time-video-captioning_b200")

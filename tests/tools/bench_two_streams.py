@@ -2,7 +2,7 @@
 overlap the encode phase of the other?"""
 import importlib, os, sys, threading, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 g = importlib.import_module("real-time-video-captioning_b200")
 from oracle import git_oracle as go
 

@@ -1,6 +1,6 @@
 import importlib, os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 g = importlib.import_module("real-time-video-captioning_b200")
 from oracle import git_oracle as go, search_oracle as so
 param = {"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024, "num_image_with_embedding": 2}
