@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs
   float* sc = sm;                              // [NB][kcap] scores -> probabilities
   float* red = sm + NB * kcap;                 // [TA_GROUPS][NB][HD] value partials (also max/sum scratch)
   const int chunks = (a.rows_per_clip + NB - 1) / NB;
-  const int clip = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-  const int h = blockIdx.y, split = blockIdx.z;
+  const int clip = blockIdx.y / chunks, chunk = blockIdx.y % chunks;
+  const int h = blockIdx.x, split = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 3, sub = lane & 7;
   const int d0 = sub * 8;
@@ -459,8 +459,10 @@ cudaError_t text_attention(const TextAttnArgs& a, cudaStream_t stream) {
   const int per = (a.Nv + a.splits - 1) / a.splits;
   const int kcap = ((per + a.max_text + 3) / 4) * 4;
   const size_t smem = ((size_t)nb * kcap + (size_t)TA_GROUPS * nb * HD) * sizeof(float);
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  dim3 grid(a.n_clips * chunks, a.heads, a.splits);
+  if (smem > 200 * 1024 || (long)a.n_clips * chunks > 65535) return cudaErrorInvalidValue;  // grid.y limit
+  // heads are the FASTEST grid dimension: the CTAs of one clip's heads are resident together and jointly read whole
+  // 1.5 KB K (then V) runs of every cache row instead of one 128-byte piece of rows 4.6 KB apart
+  dim3 grid(a.heads, a.n_clips * chunks, a.splits);
   const float sl2 = a.scale * 1.4426950408889634f;
   cudaError_t e = cudaSuccess;
   auto launch = [&](auto kernel) {
