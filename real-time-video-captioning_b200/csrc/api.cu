@@ -493,11 +493,28 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
   CUDA_OK(c, embed_text(t.tokens, t.positions, t.pos_const, rows, c->words_f32, c->pos_f32, c->lne_g, c->lne_b,
                         k.embed_ln_eps, H, c->tx.p, s));
   TRY(emit_hidden(0));
+  // Latency mode (<= 4 rows: one clip greedy or beam 4, nothing else reads the hidden states): the two LayerNorms of a layer
+  // run inside the skinny GEMMs that consume them (normalise-on-load, CTA 0 stores the normalised rows for the residuals)
+  // and the K/V scatter inside the QKV projection: 6 launches per layer instead of 9 (a decode step is launch-latency
+  // bound: ~5 us per dependent kernel against a 24 us weight-streaming floor).
+  const bool fused = rows <= 4 && t.hidden_out == nullptr && H == 768;
   for (int l = 0; l < k.dec_layers; ++l) {
     const DecLayer& L = c->dec[l];
-    TRY(gemm(c, linear(c->tx.p, H, L.w_qkv, H, rows, 3 * H, L.b_qkv, c->tq.p, 3 * H), s));
-    CUDA_OK(c, store_text_kv(c->tq.p, 3 * H, rows, 2 * H, H, t.positions, t.pos_const, t.slot_div, t.n_slots,
-                             c->txt_kv[l].p, s));
+    {
+      // fused, l > 0: tb holds the previous layer's un-normalised output; its output LayerNorm runs here and lands in tx
+      GemmArgs g = linear(fused && l > 0 ? c->tb.p : c->tx.p, H, L.w_qkv, H, rows, 3 * H, L.b_qkv, c->tq.p, 3 * H);
+      if (fused) {
+        if (l > 0) {
+          g.lnl_gamma = c->dec[l - 1].lno_g; g.lnl_beta = c->dec[l - 1].lno_b; g.lnl_eps = k.bert_ln_eps; g.lnl_out = c->tx.p; g.lnl_ldo = H;
+        }
+        g.sc_kv = c->txt_kv[l].p; g.sc_q_width = H; g.sc_kv_width = 2 * H; g.sc_pos = t.positions; g.sc_pos_const = t.pos_const;
+        g.sc_slot_div = t.slot_div; g.sc_n_slots = t.n_slots;
+      }
+      TRY(gemm(c, g, s));
+    }
+    if (!fused)
+      CUDA_OK(c, store_text_kv(c->tq.p, 3 * H, rows, 2 * H, H, t.positions, t.pos_const, t.slot_div, t.n_slots,
+                               c->txt_kv[l].p, s));
     TextAttnArgs a;
     a.q = c->tq.p; a.ldq = 3 * H; a.n_clips = t.n_clips; a.rows_per_clip = t.rows_per_clip; a.heads = k.dec_heads;
     a.vis_kv = c->kv[l].p; a.ld_vis = 3 * H; a.k_off = H; a.v_off = 2 * H; a.Nv = Nv;
@@ -510,10 +527,13 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
       g.residual = c->tx.p; g.ldr = H;
       TRY(gemm(c, g, s));
     }
-    TRY(ln(c, c->tb.p, rows, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->tc.p, s));
+    if (!fused) TRY(ln(c, c->tb.p, rows, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->tc.p, s));
     {
-      GemmArgs g = linear(c->tc.p, H, L.w_fc1, H, rows, k.ffn, L.b_fc1, c->tf.p, k.ffn);
+      GemmArgs g = linear(fused ? c->tb.p : c->tc.p, H, L.w_fc1, H, rows, k.ffn, L.b_fc1, c->tf.p, k.ffn);
       g.act = ACT_GELU_ERF;
+      if (fused) {
+        g.lnl_gamma = L.lna_g; g.lnl_beta = L.lna_b; g.lnl_eps = k.bert_ln_eps; g.lnl_out = c->tc.p; g.lnl_ldo = H;
+      }
       TRY(gemm(c, g, s));
     }
     {
@@ -521,12 +541,18 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
       g.residual = c->tc.p; g.ldr = H;
       TRY(gemm(c, g, s));
     }
-    TRY(ln(c, c->tb.p, rows, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->tx.p, s));
-    TRY(emit_hidden(l + 1));
+    if (!fused) {
+      TRY(ln(c, c->tb.p, rows, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->tx.p, s));
+      TRY(emit_hidden(l + 1));
+    }
   }
   {
-    GemmArgs g = linear(c->tx.p, H, c->w_vocab, H, rows, c->vocab_pad, c->b_vocab, nullptr, 0);
+    GemmArgs g = linear(fused ? c->tb.p : c->tx.p, H, c->w_vocab, H, rows, c->vocab_pad, c->b_vocab, nullptr, 0);
     g.out_f32 = t.logits; g.ldo32 = c->vocab_pad;
+    if (fused) {  // the last layer's output LayerNorm runs inside the vocabulary head
+      const DecLayer& L = c->dec[k.dec_layers - 1];
+      g.lnl_gamma = L.lno_g; g.lnl_beta = L.lno_b; g.lnl_eps = k.bert_ln_eps; g.lnl_out = nullptr;
+    }
     TRY(gemm(c, g, s));
   }
   return 0;

@@ -432,6 +432,10 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     g_err = "gemm_bf16: unsupported shape/stride (need N%128==0, K%8==0, 16-byte aligned rows)";
     return cudaErrorInvalidValue;
   }
+  if ((a.lnl_gamma != nullptr || a.sc_kv != nullptr) && !(force_bn == 1 || (force_bn == 0 && a.M <= 8))) {
+    g_err = "gemm_bf16: LayerNorm-on-load / K-V scatter exist only in the skinny kernel (M <= 8)";
+    return cudaErrorInvalidValue;
+  }
   Epilogue ep{a.bias, a.residual, a.ldr, a.res_periodic, a.act, a.out, a.ldo, a.out_f32, a.ldo32, a.gin, a.gout, a.goff};
   int bn = force_bn;
   if (bn == 0) {

@@ -40,6 +40,21 @@ struct GemmArgs {
   // Optional: accumulate (sum, sum of squares) of every OUTPUT row (bf16-rounded values) into stats_out[2r..2r+1]
   // with atomics -- the statistics the next folded LayerNorm needs.  Must be zeroed by the caller.
   float* stats_out = nullptr;
+  // ---- weight-streaming skinny kernel only (M <= 8 decode rows; gemm_bf16 rejects them on the tensor-core kernels) ----
+  // LayerNorm of the A rows ON LOAD (M <= 4, K == 768): A holds the UN-normalised rows; every warp normalises them exactly
+  // like layernorm_kernel (fp32 statistics, result rounded to bf16) before its dot products, and CTA 0 also stores the
+  // normalised rows to lnl_out (the residual of a later sub-layer).  Removes one launch per LayerNorm from a decode step.
+  const float* lnl_gamma = nullptr;
+  const float* lnl_beta = nullptr;
+  float lnl_eps = 0.f;
+  bf16* lnl_out = nullptr;
+  int lnl_ldo = 0;
+  // Output columns >= sc_q_width are ALSO scattered into the text K/V plane (the store_text_kv kernel fused into the QKV
+  // projection): sc_kv[(pos(m) * sc_n_slots + m / sc_slot_div) * sc_kv_width + (n - sc_q_width)].
+  bf16* sc_kv = nullptr;
+  int sc_q_width = 0, sc_kv_width = 0;
+  const int* sc_pos = nullptr;
+  int sc_pos_const = 0, sc_slot_div = 1, sc_n_slots = 0;
 };
 // force_bn: 0 = heuristic, 128 or 256 = tile width override (tests / tuning).
 cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn = 0);
