@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--frames", type=int, default=6)
     ap.add_argument("--pipeline", type=int, default=0, help="clips per chunk of the two-stream encode/decode pipeline (0 off, -1 auto)")
     ap.add_argument("--fold-ln", action="store_true", help="opt-in: ViT LayerNorms folded into the QKV / fc1 GEMM epilogues (DESIGN.md dead ends)")
+    ap.add_argument("--sweep-rows", type=int, default=-1, help="token rows per ViT / visual-pass sub-batch (-1: library default 151296 = 128 clips; 0: one sweep)")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     args = ap.parse_args()
 
@@ -187,6 +188,8 @@ def main():
     sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
     B = args.batch
     eng.set_pipeline(args.pipeline)
+    if args.sweep_rows >= 0:
+        eng.set_sweep_rows(args.sweep_rows)
     if args.fold_ln:
         eng.set_fold_layernorm(True)
     if args.pipeline == 0:

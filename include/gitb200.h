@@ -113,6 +113,16 @@ int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int 
  * the atomically accumulated statistics make results run-to-run non-bit-exact, hence off by default. */
 int gitb200_set_fold_layernorm(gitb200_ctx* ctx, int enable);
 
+/* Large batches walk the ViT and the decoder's pass over the visual tokens in sub-batches of about `rows` token rows
+ * (default 151296 = 128 six-frame ViT-B/16 clips; 0 = the whole batch in one sweep), so that the row-sized scratch
+ * (ViT activations, decoder visual hidden states, MLP buffers) is held for one sub-batch only: 4.4 instead of 17.6 GB at
+ * 512 clips.  Clips are independent on this part of the path (the reference encodes them one by one, model.py:752-759),
+ * every sub-batch writes its own slice of the visual features / visual K/V cache, and results are bit-identical whenever
+ * every sub-batch takes the same GEMM kernel as the whole batch (>= 1024 rows; a smaller ragged tail differs by bf16
+ * rounding only).  Throughput-neutral from 128 clips per sub-batch up (measured A/B on one B200); call it before
+ * gitb200_reserve. */
+int gitb200_set_sweep_rows(gitb200_ctx* ctx, int rows);
+
 /* Opt-in large-batch pipelining of gitb200_caption / gitb200_caption_host: clips per chunk (0 = off, the default;
  * -1 = automatic: a quarter of the batch clamped to [32, 128]).  Chunks alternate between two internal streams / workspace sets so that one
  * chunk's decode steps overlap the next chunk's ViT.  When a call is pipelined, the context does not keep the visual

@@ -129,6 +129,11 @@ struct gitb200_ctx {
   bool fold_ln = false;     // opt-in: ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); +1 % measured, and the
                             // atomically accumulated row statistics make results run-to-run non-bit-exact -> default off
   int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
+  // Large batches walk the ViT / the decoder's visual pass in sub-batches of about this many token rows (0: one sweep).
+  // 151296 = 128 six-frame GIT-base clips.  Throughput-neutral from 128 clips up (A/B on one box, 512 clips per step:
+  // 2431 / 2432 / 2430 / 2384 clips/s for one sweep / 128 / 256 / 64 clips per sub-batch), but the row-sized scratch
+  // shrinks with it: 17.6 -> 4.4 GB at 512 clips, so larger batches fit.
+  int sweep_rows = 151296;
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_enc0 = nullptr, ev_join[2] = {nullptr, nullptr};
 
@@ -380,42 +385,53 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
 // full_last: also run attention/FFN of the last layer on the visual rows (needed only for hidden-state output)
 int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_text, cudaStream_t s) {
   const gitb200_config& k = c->cfg;
-  const int H = k.hidden, Nv = c->cur_nv, B = c->cur_clips, M = B * Nv;
-  if (B <= 0 || Nv <= 0) return fail(c, GITB200_ERR_STATE, "no visual features: call gitb200_encode or gitb200_set_visual_features first");
-  ENSURE(c, c->hv, (size_t)M * H);
-  ENSURE(c, c->hvb, (size_t)M * H);
-  ENSURE(c, c->hvc, (size_t)M * H);
-  ENSURE(c, c->vattn, (size_t)M * H);
-  ENSURE(c, c->vmlp, (size_t)M * k.ffn);
+  const int H = k.hidden, Nv = c->cur_nv, Ball = c->cur_clips;
+  if (Ball <= 0 || Nv <= 0) return fail(c, GITB200_ERR_STATE, "no visual features: call gitb200_encode or gitb200_set_visual_features first");
+  // Clips are independent here, so a large batch walks the layers in sub-batches of ~`sweep_rows` token rows: every
+  // row-sized scratch buffer is then allocated for one sub-batch only (4x less at 512 clips; throughput-neutral from
+  // 128 clips per sub-batch up).  Row results do not depend on the sub-batch they are computed in (tests: bit-exact).
+  int Bsub = c->sweep_rows > 0 ? c->sweep_rows / Nv : Ball;
+  if (Bsub < 1) Bsub = 1;
+  if (Bsub > Ball) Bsub = Ball;
+  const int Msub = Bsub * Nv;
+  ENSURE(c, c->hv, (size_t)Msub * H);
+  ENSURE(c, c->hvb, (size_t)Msub * H);
+  ENSURE(c, c->hvc, (size_t)Msub * H);
+  ENSURE(c, c->vattn, (size_t)Msub * H);
+  ENSURE(c, c->vmlp, (size_t)Msub * k.ffn);
   if ((int)c->kv.size() != k.dec_layers) c->kv.resize(k.dec_layers);
-  for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->kv[l], (size_t)M * 3 * H);
+  for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->kv[l], (size_t)Ball * Nv * 3 * H);
+  const float scale = 1.0f / sqrtf((float)(H / k.dec_heads));
 
+ for (int b0 = 0; b0 < Ball; b0 += Bsub) {
+  const int B = (Ball - b0) < Bsub ? (Ball - b0) : Bsub, M = B * Nv;
+  const size_t kvoff = (size_t)b0 * Nv * 3 * H;
   auto emit_hidden = [&](int idx) -> int {
     if (!hidden_out) return 0;
     // hidden_out: [B, layers+1, Nv+L, H]; visual rows of clip b, state idx
     const size_t per_state = (size_t)(Nv + L_text) * H;
     for (int b = 0; b < B; ++b)
       CUDA_OK(c, cast_bf16_to_f32(c->hv.p + (size_t)b * Nv * H, Nv, H, H,
-                                  hidden_out + ((size_t)b * (k.dec_layers + 1) + idx) * per_state, H, s));
+                                  hidden_out + ((size_t)(b0 + b) * (k.dec_layers + 1) + idx) * per_state, H, s));
     return 0;
   };
 
   // visual_projection = Linear + LayerNorm
-  TRY(gemm(c, linear(c->vf.p, k.vit_width, c->w_proj, k.vit_width, M, H, c->b_proj, c->hvb.p, H), s));
+  TRY(gemm(c, linear(c->vf.p + (size_t)b0 * Nv * k.vit_width, k.vit_width, c->w_proj, k.vit_width, M, H, c->b_proj, c->hvb.p, H), s));
   TRY(ln(c, c->hvb.p, M, H, c->lnp_g, c->lnp_b, k.proj_ln_eps, c->hv.p, s));
   TRY(emit_hidden(0));
-  const float scale = 1.0f / sqrtf((float)(H / k.dec_heads));
   for (int l = 0; l < k.dec_layers; ++l) {
     const DecLayer& L = c->dec[l];
     const bool full = (l + 1 < k.dec_layers) || full_last;
+    bf16* kvl = c->kv[l].p + kvoff;
     if (full) {
-      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv, H, M, 3 * H, L.b_qkv, c->kv[l].p, 3 * H), s));
+      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv, H, M, 3 * H, L.b_qkv, kvl, 3 * H), s));
     } else {
       // last layer: only K and V of the visual tokens are ever read again
-      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv + (size_t)H * H, H, M, 2 * H, L.b_qkv + H, c->kv[l].p + H, 3 * H), s));
+      TRY(gemm(c, linear(c->hv.p, H, L.w_qkv + (size_t)H * H, H, M, 2 * H, L.b_qkv + H, kvl + H, 3 * H), s));
       break;
     }
-    CUDA_OK(c, attention_groups_tc(c->kv[l].p, 3 * H, c->vattn.p, H, B, Nv, k.dec_heads, scale, s));
+    CUDA_OK(c, attention_groups_tc(kvl, 3 * H, c->vattn.p, H, B, Nv, k.dec_heads, scale, s));
     {
       GemmArgs g = linear(c->vattn.p, H, L.w_out, H, M, H, L.b_out, c->hvb.p, H);
       g.residual = c->hv.p; g.ldr = H;
@@ -435,6 +451,7 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
     TRY(ln(c, c->hvb.p, M, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->hv.p, s));
     TRY(emit_hidden(l + 1));
   }
+ }
   c->visual_pass_done = true;
   c->visual_pass_full = full_last ? 1 : 0;
   return 0;
@@ -631,7 +648,7 @@ void free_workspaces(gitb200_ctx* c) {
 gitb200_ctx* make_twin(gitb200_ctx* c) {
   gitb200_ctx* t = new gitb200_ctx();
   t->cfg = c->cfg; t->device = c->device; t->finalized = true; t->is_twin = true; t->graphs_enabled = false; t->pipeline_chunk = 0;
-  t->fold_ln = c->fold_ln;
+  t->fold_ln = c->fold_ln; t->sweep_rows = c->sweep_rows;
   t->T = c->T; t->kpad = c->kpad; t->vocab_pad = c->vocab_pad; t->n_temporal = c->n_temporal;
   t->w_patch = c->w_patch; t->pos_bf16 = c->pos_bf16; t->cls = c->cls; t->ln_pre_g = c->ln_pre_g; t->ln_pre_b = c->ln_pre_b;
   t->ln_post_g = c->ln_post_g; t->ln_post_b = c->ln_post_b; t->temporal = c->temporal; t->vit = c->vit;
@@ -951,18 +968,24 @@ int gitb200_reserve(gitb200_ctx* c, int max_clips, int max_frames, int max_rows_
   const int F = (k.num_image_with_embedding > 0 && max_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : max_frames;
   const int W = k.vit_width, H = k.hidden, G = k.resolution / k.patch;
   const size_t rows = (size_t)max_clips * F * c->T;
-  ENSURE(c, c->patches, (size_t)max_clips * F * G * G * c->kpad);
-  ENSURE(c, c->x, rows * W);
-  ENSURE(c, c->lnb, rows * W);
-  ENSURE(c, c->qkv, rows * 3 * W);
-  ENSURE(c, c->attn, rows * W);
-  ENSURE(c, c->mlp, rows * 4 * W);
+  // row-sized scratch is needed for one sub-batch of the sweeps only (gitb200_ctx::sweep_rows); the visual features and
+  // the visual K/V cache are per clip and stay whole
+  int sub_clips = c->sweep_rows > 0 ? c->sweep_rows / (F * c->T) : max_clips;
+  if (sub_clips < 1) sub_clips = 1;
+  if (sub_clips > max_clips) sub_clips = max_clips;
+  const size_t srows = (size_t)sub_clips * F * c->T;
+  ENSURE(c, c->patches, (size_t)sub_clips * F * G * G * c->kpad);
+  ENSURE(c, c->x, srows * W);
+  ENSURE(c, c->lnb, srows * W);
+  ENSURE(c, c->qkv, srows * 3 * W);
+  ENSURE(c, c->attn, srows * W);
+  ENSURE(c, c->mlp, srows * 4 * W);
   ENSURE(c, c->vf, rows * W);
-  ENSURE(c, c->hv, rows * H);
-  ENSURE(c, c->hvb, rows * H);
-  ENSURE(c, c->hvc, rows * H);
-  ENSURE(c, c->vattn, rows * H);
-  ENSURE(c, c->vmlp, rows * k.ffn);
+  ENSURE(c, c->hv, srows * H);
+  ENSURE(c, c->hvb, srows * H);
+  ENSURE(c, c->hvc, srows * H);
+  ENSURE(c, c->vattn, srows * H);
+  ENSURE(c, c->vmlp, srows * k.ffn);
   c->kv.resize(k.dec_layers);
   for (int l = 0; l < k.dec_layers; ++l) ENSURE(c, c->kv[l], rows * 3 * H);
   const int trows = max_clips * max_rows_per_clip;
@@ -971,12 +994,35 @@ int gitb200_reserve(gitb200_ctx* c, int max_clips, int max_frames, int max_rows_
   return GITB200_OK;
 }
 
+// run_encode over `n_clips` clips in sub-batches of ~sweep_rows token rows (see gitb200_ctx::sweep_rows); every sub-batch
+// writes its slice of the visual features, so the result is the one sweep's, bit for bit.
+static int run_encode_sweeps(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, bool temporal = true) {
+  const gitb200_config& k = c->cfg;
+  const int F = (temporal && k.num_image_with_embedding > 0 && n_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : n_frames;
+  int sub = c->sweep_rows > 0 ? c->sweep_rows / (F * c->T) : n_clips;
+  if (sub < 1) sub = 1;
+  if (sub >= n_clips) return run_encode(c, frames, n_clips, n_frames, s, 0, 0, nullptr, temporal);
+  const size_t clip_elems = (size_t)n_frames * 3 * k.resolution * k.resolution;
+  for (int done = 0; done < n_clips; done += sub) {
+    const int nc = (n_clips - done) < sub ? (n_clips - done) : sub;
+    TRY(run_encode(c, frames + (size_t)done * clip_elems, nc, n_frames, s, done, n_clips, nullptr, temporal));
+  }
+  return 0;
+}
+
+int gitb200_set_sweep_rows(gitb200_ctx* c, int rows) {
+  if (!c || rows < 0) return fail(c, GITB200_ERR_INVALID, "gitb200_set_sweep_rows: rows must be >= 0");
+  c->sweep_rows = rows;
+  if (c->twin) c->twin->sweep_rows = rows;
+  return GITB200_OK;
+}
+
 int gitb200_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, float* vf_out, void* stream) {
   if (!c || !frames || n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad encode argument");
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
-  TRY(run_encode(c, frames, n_clips, n_frames, s));
+  TRY(run_encode_sweeps(c, frames, n_clips, n_frames, s));
   if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
   return GITB200_OK;
 }
@@ -986,7 +1032,7 @@ int gitb200_encode_images(gitb200_ctx* c, const float* images, int n_images, flo
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
-  TRY(run_encode(c, images, n_images, 1, s, 0, 0, nullptr, /*temporal=*/false));
+  TRY(run_encode_sweeps(c, images, n_images, 1, s, /*temporal=*/false));
   if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_images * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
   return GITB200_OK;
 }
@@ -1216,7 +1262,7 @@ int gitb200_forward_logits(gitb200_ctx* c, const float* frames, int n_clips, int
   cudaStream_t s = (cudaStream_t)stream;
   if (frames) {
     if (n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad forward_logits argument");
-    TRY(run_encode(c, frames, n_clips, n_frames, s));
+    TRY(run_encode_sweeps(c, frames, n_clips, n_frames, s));
   }
   if (c->cur_clips <= 0) return fail(c, GITB200_ERR_STATE, "no visual features");
   const int B = c->cur_clips, rows = B * L, W = c->cfg.vit_width;

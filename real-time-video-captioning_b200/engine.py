@@ -247,6 +247,10 @@ class Engine:
         """ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues (default on) or run as separate LayerNorm kernels."""
         check(self.lib.gitb200_set_fold_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fold_layernorm")
 
+    def set_sweep_rows(self, rows: int) -> None:
+        """Token rows per sub-batch of the ViT / visual-pass sweeps of a large batch (0 = one sweep; results are identical)."""
+        check(self.lib.gitb200_set_sweep_rows(self.h, rows), self.h, "gitb200_set_sweep_rows")
+
     def set_pipeline(self, chunk_clips: int) -> None:
         """Clips per chunk of the two-stream encode/decode pipeline (0 = off, -1 = automatic)."""
         check(self.lib.gitb200_set_pipeline(self.h, chunk_clips), self.h, "gitb200_set_pipeline")

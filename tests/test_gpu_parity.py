@@ -585,6 +585,43 @@ def test_two_stream_pipeline_equals_single_stream(g, setup):
     assert (a == b).all(dim=-1).float().mean() >= 0.9  # beam near-ties may flip on 1e-3 score differences
 
 
+def test_sub_batch_sweeps_equal_one_sweep(g, setup):
+    """Large batches walk the ViT and the decoder's visual pass in sub-batches (gitb200_set_sweep_rows).  Sub-batches of
+    >= 1024 rows take the same kernels as the whole batch, so features, tokens and scores are bit-identical; a smaller
+    ragged tail takes the 1-CTA GEMM and may differ by bf16 rounding only."""
+    cfg, sd, eng = setup[True]
+    gen = torch.Generator().manual_seed(78)
+    frames = torch.randn(12, N_FRAMES, 3, 224, 224, generator=gen).cuda()
+    rows_per_clip = N_FRAMES * 197
+    sp = g.SearchConfig(beam_size=1, max_steps=6)
+    sp4 = g.SearchConfig(beam_size=4, max_steps=6)
+    try:
+        eng.set_sweep_rows(0)
+        vf0 = eng.encode(frames).clone()
+        t0, l0, _ = eng.caption(frames, sp)
+        b0, lb0, _ = eng.caption(frames, sp4)
+        h0 = [x.clone() for x in eng.forward_logits(frames, torch.full((12, 3), 1012, dtype=torch.int32, device="cuda"))]
+        eng.set_sweep_rows(4 * rows_per_clip)  # 3 sub-batches of 4 clips = 1576 rows each
+        vf1 = eng.encode(frames).clone()
+        t1, l1, _ = eng.caption(frames, sp)
+        b1, lb1, _ = eng.caption(frames, sp4)
+        h1 = eng.forward_logits(frames, torch.full((12, 3), 1012, dtype=torch.int32, device="cuda"))  # hidden states too
+        torch.cuda.synchronize()
+        assert torch.equal(vf0, vf1)
+        assert torch.equal(t0, t1) and torch.equal(l0, l1)
+        assert torch.equal(b0, b1) and torch.equal(lb0, lb1)
+        assert len(h0) == 3 and all(torch.equal(a, b) for a, b in zip(h0, h1))
+        eng.set_sweep_rows(5 * rows_per_clip)  # 5 + 5 + 2 clips: the tail (788 rows) takes the 1-CTA GEMM
+        vf2 = eng.encode(frames).clone()
+        t2, l2, _ = eng.caption(frames, sp)
+        torch.cuda.synchronize()
+        assert rel_fro(vf2.float(), vf0.float()) < 1e-2
+        assert torch.equal(t0, t2)
+        assert torch.allclose(l0, l2, rtol=2e-2, atol=5e-3)
+    finally:
+        eng.set_sweep_rows(151296)
+
+
 def test_folded_layernorm_matches_separate_and_oracle(g, setup):
     """ViT ln_1 / ln_2 folded into the QKV / fc1 GEMM epilogues (row statistics from the previous residual GEMM) against
     the separate LayerNorm kernels and against the oracle: both inside the visual-feature tolerance, the folded form
