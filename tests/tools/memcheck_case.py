@@ -1,6 +1,7 @@
 """Development script: one small caption pass that touches every kernel family (CTA-pair GEMM with >= 1024 rows, 1-CTA GEMM,
 skinny GEMM, both tcgen05 attention shapes, decode-step attention with split keys, LayerNorm, search, preprocessing,
-sub-batch sweeps, host path), meant to be run under `compute-sanitizer --tool memcheck` (tests/tools/memcheck.sh)."""
+sub-batch sweeps, host path).  Written for `compute-sanitizer --tool memcheck`, which is closed on the GPU pool (runs under it
+left GPUs needing a reset), so it serves as a plain smoke pass: device and host paths must agree token for token."""
 import importlib
 import os
 import sys
