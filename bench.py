@@ -262,6 +262,24 @@ def main():
     e2e_value = world * B * e2e_steps / t.item()
     h2d = host_frames.numel() * 4
     d2h = tok_h.numel() * 4 + lp_h.numel() * 4
+    del host_frames
+
+    # ---- the same from RAW video frames (uint8 BGR 240x320, MSR-VTT's frame size): bytes over PCIe, image_transform() on the GPU
+    raw_frames = torch.randint(0, 256, (B, FRAMES, 240, 320, 3), dtype=torch.uint8,
+                               generator=torch.Generator().manual_seed(17 + rank)).pin_memory()
+    eng.caption_host_u8(raw_frames, sp, chunk_clips=args.chunk)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.caption_host_u8(raw_frames, sp, chunk_clips=args.chunk)
+    sync_all()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_raw = {"value": world * B * e2e_steps / t.item(), "unit": UNIT, "h2d_bytes_per_step": raw_frames.numel(),
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "api": "Engine.caption_host_u8 (gitb200_caption_host_u8): pinned host uint8 BGR 240x320 frames -> GPU image_transform -> host tokens"}
+    del raw_frames
 
     if rank != 0:
         if world > 1:
@@ -337,6 +355,7 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Engine.caption_host (gitb200_caption_host): pinned host frames -> host tokens"},
+            "e2e_raw_frames": e2e_raw,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
             "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream}
     print(json.dumps(line))

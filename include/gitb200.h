@@ -175,6 +175,15 @@ int gitb200_stream_caption(gitb200_ctx* ctx, const gitb200_search_params* sp, in
 int gitb200_preprocess(const uint8_t* frames_dev, int n_frames, int height, int width, int size, float* out_dev,
                        void* stream);
 
+/* Host path for RAW video frames (the caller's side is real_time_inference.py:49-57 and the dataset's
+ * cv2 frame reads, dataloader.py:61-75): frames_host uint8 [n_clips, n_frames, height, width, 3] BGR HWC (pinned
+ * recommended) -> host tokens / log-probs exactly as gitb200_caption_host.  Frames cross PCIe as bytes in chunks of
+ * `chunk_clips` clips (copy of chunk i+1 overlaps chunk i's work), image_transform() runs on the device
+ * (gitb200_preprocess's kernel) straight into the ViT's input, then one batched decode.  Same result as
+ * gitb200_preprocess + gitb200_caption on the same frames.  Synchronous. */
+int gitb200_caption_host_u8(gitb200_ctx* ctx, const uint8_t* frames_host, int n_clips, int n_frames, int height, int width,
+                            int chunk_clips, const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host);
+
 /* ---- student decoder: the decoder half of StudentCandidateV1, model.py:50-187 ---------------------
  * nn.Embedding + PositionalEncoding + post-LN nn.TransformerDecoder (causal / padding-masked self-attention, cross-attention
  * to the F frame tokens of `memory`, ReLU feed-forward) + the vocabulary nn.Linear.  The TinyViT image encoder that

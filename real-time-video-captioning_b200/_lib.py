@@ -71,6 +71,8 @@ SIGNATURES = {
     "gitb200_set_pipeline": (c_int, [c_void_p, c_int]),
     "gitb200_set_sweep_rows": (c_int, [c_void_p, c_int]),
     "gitb200_caption_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p]),
+    "gitb200_caption_host_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(SearchParams), c_void_p,
+                                        c_void_p]),
     "gitb200_forward_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),
     "gitb200_decode_begin": (c_int, [c_void_p, c_int, c_void_p]),

@@ -96,6 +96,7 @@ struct gitb200_ctx {
   Buf<float> fbuf;     // search floats
   Buf<int> pos_arr, ntext_arr, tok_arr;
   Buf<float> stage[2];  // host-path frame staging
+  Buf<uint8_t> stage_u8[2];  // host-path staging of raw uint8 video frames (gitb200_caption_host_u8)
   Buf<int> out_tok;
   Buf<float> out_lp;
   cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
@@ -640,7 +641,7 @@ void free_workspaces(gitb200_ctx* c) {
   for (auto& b : c->kv) fr(b);
   for (auto& b : c->txt_kv) fr(b);
   fr(c->tx); fr(c->tq); fr(c->ta); fr(c->tb); fr(c->tc); fr(c->tf); fr(c->logits); fr(c->partial); fr(c->vf_in_f32);
-  fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]);
+  fr(c->ibuf); fr(c->dbuf); fr(c->fbuf); fr(c->pos_arr); fr(c->ntext_arr); fr(c->tok_arr); fr(c->stage[0]); fr(c->stage[1]); fr(c->stage_u8[0]); fr(c->stage_u8[1]);
   fr(c->out_tok); fr(c->out_lp); fr(c->stats_a); fr(c->stats_b); fr(c->ring);
 }
 
@@ -1247,6 +1248,57 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
     int r = run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp);
     if (r) return r;
   }
+  CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
+  CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
+  CUDA_OK(c, cudaStreamSynchronize(comp));
+  return GITB200_OK;
+}
+
+// Raw video frames from the host: uint8 BGR HWC, as cv2.VideoCapture / cv2.resize deliver them (real_time_inference.py:49-57,
+// dataloader.py:61-75).  A chunk's frames cross PCIe as bytes (height*width*3 per frame instead of 3*R*R*4 after the
+// host-side image_transform), are resized / cropped / normalised by preprocess_kernel into the fp32 staging buffer, and go
+// straight into the ViT; the copy of chunk i+1 overlaps the preprocessing + ViT of chunk i.
+int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_clips, int n_frames, int height, int width,
+                            int chunk_clips, const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host) {
+  if (!c || !frames_host || !sp || !tokens_host || !logprobs_host || n_clips < 1 || n_frames < 1 || height < 1 || width < 1)
+    return fail(c, GITB200_ERR_INVALID, "bad caption_host_u8 argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
+  const int R = c->cfg.resolution;
+  const size_t clip_bytes = (size_t)n_frames * height * width * 3;
+  const size_t clip_elems = (size_t)n_frames * 3 * R * R;
+  const int per_clip_tok = sp->num_keep_best * sp->max_steps;
+  if (!c->copy_stream) {
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  cudaStream_t comp = c->comp_stream;
+  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage_u8[i], (size_t)chunk_clips * clip_bytes);
+  ENSURE(c, c->stage[0], (size_t)chunk_clips * clip_elems);  // one fp32 buffer: preprocess and ViT of a chunk are stream-ordered
+  ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
+  ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
+  int done = 0, ch = 0;
+  while (done < n_clips) {
+    const int b = ch & 1;
+    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+    if (nc > n_clips - done) nc = n_clips - done;
+    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // byte staging buffer free again
+    CUDA_OK(c, cudaMemcpyAsync(c->stage_u8[b].p, frames_host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
+    CUDA_OK(c, preprocess_frames_u8(c->stage_u8[b].p, nc * n_frames, height, width, R, c->stage[0].p, comp));
+    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+    TRY(run_encode(c, c->stage[0].p, nc, n_frames, comp, done, n_clips));
+    done += nc;
+    ++ch;
+  }
+  TRY(run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp));
   CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaStreamSynchronize(comp));

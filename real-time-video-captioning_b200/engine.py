@@ -179,6 +179,20 @@ class Engine:
                                                 _ptr(tokens), _ptr(logprobs)), self.h, "gitb200_caption_host")
         return tokens, logprobs
 
+    def caption_host_u8(self, frames_host: torch.Tensor, sp: SearchConfig, chunk_clips: int = 32):
+        """HOST raw video frames uint8 [N, F, H, W, 3] (OpenCV BGR, pinned recommended) -> HOST tokens, logprobs.
+        image_transform() (dataloader.py:18-32) runs on the device between the byte copy and the ViT; synchronous."""
+        assert not frames_host.is_cuda and frames_host.dtype == torch.uint8 and frames_host.dim() == 5 and frames_host.shape[-1] == 3
+        frames_host = frames_host.contiguous()
+        N, F, H, W = frames_host.shape[:4]
+        tokens = torch.empty(N, sp.num_keep_best, sp.max_steps, dtype=torch.int32).pin_memory()
+        logprobs = torch.empty(N, sp.num_keep_best, dtype=torch.float32).pin_memory()
+        c = sp.to_c()
+        with torch.cuda.device(self.device):
+            check(self.lib.gitb200_caption_host_u8(self.h, _ptr(frames_host), N, F, H, W, chunk_clips, ctypes.byref(c),
+                                                   _ptr(tokens), _ptr(logprobs)), self.h, "gitb200_caption_host_u8")
+        return tokens, logprobs
+
     def forward_logits(self, frames: Optional[torch.Tensor], tokens: torch.Tensor, want_hidden: bool = True,
                        want_features: bool = True):
         """Teacher-forced forward (forward_one_custom, model.py:371-424), batched over clips.

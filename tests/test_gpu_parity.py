@@ -554,6 +554,31 @@ def test_preprocess_feeds_the_encoder(g, setup):
     assert torch.allclose(la, lb, rtol=2e-2, atol=1e-3), (la, lb)
 
 
+def test_raw_uint8_host_path_equals_preprocess_plus_caption(g, setup):
+    """gitb200_caption_host_u8: raw uint8 BGR frames on the HOST -> byte H2D in chunks -> preprocess kernel -> ViT -> decode
+    -> host tokens.  Must equal preprocess_frames + caption on the device (same kernels on the same values), and the
+    oracle-preprocessed frames through the oracle-checked caption path."""
+    from oracle import preprocess_oracle as po
+    cfg, sd, eng = setup[True]
+    raw = torch.randint(0, 256, (5, N_FRAMES, 240, 320, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(19))
+    sp = g.SearchConfig(beam_size=1, max_steps=6)
+    dev = g.preprocess_frames(raw.view(-1, 240, 320, 3).cuda()).view(5, N_FRAMES, 3, 224, 224)
+    td, ld, _ = eng.caption(dev.contiguous(), sp)
+    for chunk in (2, 5):  # chunks of 1 + 2 + 2 clips (double buffering, ragged tail) and 3 + 2
+        th, lh = eng.caption_host_u8(raw.pin_memory(), sp, chunk_clips=chunk)
+        assert torch.equal(td.cpu(), th), (td, th)
+        assert torch.allclose(ld.cpu(), lh, rtol=2e-2, atol=5e-3), (ld.cpu() - lh).abs().max()
+    ref = po.preprocess_frames(raw.view(-1, 240, 320, 3)).view(5, N_FRAMES, 3, 224, 224).cuda()
+    tr, lr, _ = eng.caption(ref.contiguous(), sp)
+    assert torch.equal(tr.cpu(), th)
+    assert torch.allclose(lr.cpu(), lh, rtol=2e-2, atol=5e-3)
+    sp4 = g.SearchConfig(beam_size=4, max_steps=6)
+    t4, l4 = eng.caption_host_u8(raw, sp4, chunk_clips=5)  # pageable host memory works too
+    d4, dl4, _ = eng.caption(dev.contiguous(), sp4)
+    assert torch.allclose(dl4.cpu(), l4, rtol=2e-2, atol=5e-3)
+    assert eng.lib.gitb200_caption_host_u8(eng.h, None, 1, 1, 8, 8, 1, None, None, None) != 0  # loud on bad arguments
+
+
 def test_two_stream_pipeline_equals_single_stream(g, setup):
     """Opt-in: large batches split into chunks that alternate between two streams / workspace sets (decode of one chunk
     overlaps the ViT of the next).  Captions must equal the un-pipelined call on the device and host paths; scores may
