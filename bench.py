@@ -116,6 +116,28 @@ def run_reference_cpu(steps: int, warmup: int, clips_per_step: int = 1):
             "sample": f"{len(times)} steps x {clips_per_step} clip(s), greedy (beam 1, max_steps 15), fp32, after {warmup} warm-up"}
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries chat there too (NCCL prints its version line to stdout under
+    NCCL_DEBUG=VERSION/WARN): from here on file descriptor 1 points at stderr and emit() writes to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -135,6 +157,7 @@ def main():
     ap.add_argument("--sweep-rows", type=int, default=-1, help="token rows per ViT / visual-pass sub-batch (-1: library default 151296 = 128 clips; 0: one sweep)")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     args = ap.parse_args()
+    claim_stdout()
 
     global FRAMES, GFLOP_PER_CLIP
     FRAMES = args.frames
@@ -164,7 +187,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "latency_ms_p50": r["p50_ms"]}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -239,9 +262,9 @@ def main():
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True,
-                              "gemm_ms": g_ms.value, "gemm_tflops": g_fl.value / max(g_ms.value, 1e-9) / 1e9}))
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True,
+                  "gemm_ms": g_ms.value, "gemm_tflops": g_fl.value / max(g_ms.value, 1e-9) / 1e9})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -358,7 +381,7 @@ def main():
             "e2e_raw_frames": e2e_raw,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
             "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -258,7 +258,7 @@ class Engine:
         return tokens.clone(), logprobs.clone()
 
     def set_fold_layernorm(self, enable: bool) -> None:
-        """ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues (default on) or run as separate LayerNorm kernels."""
+        """Opt-in (default off, DESIGN.md dead ends): ViT ln_1/ln_2 folded into the QKV/fc1 GEMM epilogues instead of separate LayerNorm kernels."""
         check(self.lib.gitb200_set_fold_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fold_layernorm")
 
     def set_sweep_rows(self, rows: int) -> None:
