@@ -252,6 +252,8 @@ def main():
     import ctypes
     g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     eng.lib.gitb200_profile_gemm_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n))
+    a_ms, a_by, a_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    eng.lib.gitb200_profile_decode_attention_read(ctypes.byref(a_ms), ctypes.byref(a_by), ctypes.byref(a_n))
     eng.lib.gitb200_profile_gemm(0)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -361,11 +363,27 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05) + gemm_tcgen05_kernel<128> (decode rows)",
                 "achieved": gemm_tflops, "peak": sustained,
                 "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
-                "traffic_note": "avg DRAM bytes per launch of the 4 ViT-layer GEMMs at M=605184 = 512 clips (profiles/r01_gemm2_v3_summary.md)",
+                "traffic_note": "avg DRAM read+write bytes per launch of the 4 ViT-layer GEMMs at M=151296 (one 128-clip sub-batch of the 512-clip step; algorithmic average 1.049 GB; profiles/r01_gemm2_traffic.json)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / (ms if world == 1 else ms) if ms > 0 else None,
                 "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
                 "path_tflops_algorithmic": GFLOP_PER_CLIP * 1e9 * B * args.steps / (ms * 1e-3) / 1e12}
+
+    # second roofline: the HBM-bound kernel of the path (decode-step attention over the visual + text K/V cache)
+    dec_gbs = (a_by.value / (a_ms.value * 1e-3) / 1e9) if a_ms.value > 0 else None
+    dec_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_text_attention_traffic.json")) as fh:
+            dec_traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
+    except Exception:
+        pass
+    roofline_decode = {"bound": "hbm", "kernel": "text_attention_kernel (decode-step attention, visual K/V shared by a clip's beams)",
+                       "achieved": dec_gbs, "peak": hbm, "unit": "GB/s", "frac": (dec_gbs / hbm) if (dec_gbs and hbm) else None,
+                       "traffic": dec_traffic,
+                       "traffic_note": "dram read+write bytes per launch, ncu capture of the first decode step's 6 launches at 512 clips (profiles/r01_text_attention_traffic.json)",
+                       "peak_source": f"{src} hbm_gbs (copy bandwidth)", "launches_timed": a_n.value,
+                       "algorithmic_bytes_per_launch": (a_by.value / a_n.value) if a_n.value else None,
+                       "share_of_step": (a_ms.value / ms) if ms > 0 else None}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -379,7 +397,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Engine.caption_host (gitb200_caption_host): pinned host frames -> host tokens"},
             "e2e_raw_frames": e2e_raw,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
+            "roofline": roofline, "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
             "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream}
     emit(line)
     if world > 1:

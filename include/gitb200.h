@@ -236,6 +236,10 @@ int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, i
  * (enable != 0 resets the counters).  read: summed milliseconds, summed 2*M*N*K flops, launches. */
 void gitb200_profile_gemm(int enable);
 void gitb200_profile_gemm_read(double* ms, double* flops, long long* launches);
+/* Same switch, second counter: the decode-step attention launches (text_attention_kernel, the HBM-bound kernel of the
+ * path): summed CUDA-event time, summed ALGORITHMIC bytes (each clip's visual K/V once + every row's text K/V) and the
+ * number of launches since gitb200_profile_gemm(1). */
+void gitb200_profile_decode_attention_read(double* ms, double* bytes, long long* launches);
 
 /* Number of caption calls served by replaying the captured CUDA graph. */
 long long gitb200_graph_launches(const gitb200_ctx* ctx);

@@ -94,6 +94,7 @@ SIGNATURES = {
     "gitb200_graph_launches": (c_longlong, [c_void_p]),
     "gitb200_profile_gemm": (None, [c_int]),
     "gitb200_profile_gemm_read": (None, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_longlong)]),
+    "gitb200_profile_decode_attention_read": (None, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_longlong)]),
 }
 
 _lib = None

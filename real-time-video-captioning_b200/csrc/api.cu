@@ -486,6 +486,48 @@ int ensure_text(gitb200_ctx* c, int rows, int n_slots, int max_len) {
   return 0;
 }
 
+// Live timing of the decode-step attention launches (the HBM-bound kernel of the path) with CUDA events on the launching
+// stream, switched together with the GEMM profile (gitb200_profile_gemm); read with gitb200_profile_decode_attention_read.
+struct DecAttnProf {
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<double> bytes;
+  size_t used = 0;
+  double ms = 0, by = 0;
+  long long n = 0;
+} g_dap;
+
+int dap_begin(cudaStream_t s) {
+  if (!gemm_profile_enabled()) return -1;
+  if (g_dap.ev.empty()) {
+    g_dap.ev.resize(2 * 2048);
+    g_dap.bytes.resize(2048);
+    for (auto& e : g_dap.ev) cudaEventCreate(&e);
+  }
+  if (g_dap.used >= g_dap.bytes.size()) return -1;
+  const int slot = (int)g_dap.used++;
+  g_dap.bytes[slot] = 0;
+  cudaEventRecord(g_dap.ev[2 * slot], s);
+  return slot;
+}
+
+void dap_end(int slot, cudaStream_t s, double bytes) {
+  cudaEventRecord(g_dap.ev[2 * slot + 1], s);
+  g_dap.bytes[slot] = bytes;
+}
+
+void dap_drain() {
+  for (size_t i = 0; i < g_dap.used; ++i) {
+    float t = 0;
+    if (g_dap.bytes[i] > 0 && cudaEventSynchronize(g_dap.ev[2 * i + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&t, g_dap.ev[2 * i], g_dap.ev[2 * i + 1]) == cudaSuccess) {
+      g_dap.ms += t;
+      g_dap.by += g_dap.bytes[i];
+      ++g_dap.n;
+    }
+  }
+  g_dap.used = 0;
+}
+
 int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
   const gitb200_config& k = c->cfg;
   const int H = k.hidden, rows = t.n_clips * t.rows_per_clip, Nv = c->cur_nv;
@@ -539,7 +581,12 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
     a.txt_kv = c->txt_kv[l].p; a.txt_slots = t.n_slots; a.text_slot_is_clip = t.slot_is_clip;
     a.anc = t.anc; a.anc_ld = t.max_len; a.n_text = t.n_text; a.n_text_const = t.n_text_const; a.max_text = t.max_len;
     a.scale = scale; a.out = c->ta.p; a.ldo = H; a.partial = c->partial.p; a.splits = splits;
+    const int pslot = dap_begin(s);
     CUDA_OK(c, text_attention(a, s));
+    // algorithmic bytes of this launch: every clip's visual K/V once (shared by its beam rows) + the text K/V of every row
+    if (pslot >= 0)
+      dap_end(pslot, s, (double)t.n_clips * Nv * 2 * H * sizeof(bf16) +
+                            (double)rows * (t.n_text ? t.max_len : t.n_text_const) * 2 * H * sizeof(bf16));
     {
       GemmArgs g = linear(c->ta.p, H, L.w_out, H, rows, H, L.b_out, c->tb.p, H);
       g.residual = c->tx.p; g.ldr = H;
@@ -770,7 +817,21 @@ long long gitb200_launch_count(int reset) {
   return v;
 }
 
-void gitb200_profile_gemm(int enable) { gemm_profile_enable(enable); }
+void gitb200_profile_gemm(int enable) {
+  if (enable) {
+    dap_drain();
+    g_dap.ms = g_dap.by = 0;
+    g_dap.n = 0;
+  }
+  gemm_profile_enable(enable);
+}
+
+void gitb200_profile_decode_attention_read(double* ms, double* bytes, long long* launches) {
+  dap_drain();
+  if (ms) *ms = g_dap.ms;
+  if (bytes) *bytes = g_dap.by;
+  if (launches) *launches = g_dap.n;
+}
 long long gitb200_graph_launches(const gitb200_ctx* c) { return c ? c->graph_launches : 0; }
 void gitb200_profile_gemm_read(double* ms, double* flops, long long* launches) {
   double a = 0, b = 0;
