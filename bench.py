@@ -201,13 +201,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    # identical random-init weights on every rank (same seed)
-    from oracle import git_oracle as go  # weight initialiser only (not on the measured path)
-    ocfg = go.GitConfig.from_param(param)
-    sd = go.init_state_dict(ocfg, seed=0, temporal_std=0.02, perturb=True)
-    eng = g.Engine(g.make_config(param, ocfg.sos_index, ocfg.eos_index), local_rank)
-    eng.load_state_dict(sd)
-    del sd
+    # identical random-init weights on every rank (same seed), built through the package's own reference-shaped
+    # constructor (get_git_model, model.py:681-718); nothing under oracle/ is touched by this arm.  Biases, LayerNorm
+    # affines and the temporal embeddings (zeros upstream) are randomised too so that no term of the path is trivially zero.
+    gm = importlib.import_module("real-time-video-captioning_b200.model")
+    tok = gm.SyntheticTokenizer()
+    torch.manual_seed(0)
+    model = gm.get_git_model(tok, param)
+    gen_w = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p_ in model.named_parameters():
+            if name.endswith("bias") or "img_temperal_embedding" in name:
+                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.02)
+            elif p_.dim() == 1 and name.endswith("weight"):  # LayerNorm gains
+                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.1)
+    eng = g.Engine(g.make_config(param, tok.cls_token_id, tok.sep_token_id), local_rank)
+    eng.load_state_dict(model.state_dict())
+    del model
     sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
     B = args.batch
     eng.set_pipeline(args.pipeline)
