@@ -255,6 +255,17 @@ int ln(gitb200_ctx* c, const bf16* x, int rows, int cols, const float* g, const 
   return 0;
 }
 
+// Clips per sub-batch of a sweep over `n_clips` clips of `rows_per_clip` token rows: at most sweep_rows rows, and the
+// sub-batches balanced (32 clips at 24 per sub-batch run as 16 + 16, not 24 + 8: every launch keeps the SMs equally full).
+int sweep_clips(int sweep_rows, int rows_per_clip, int n_clips) {
+  if (sweep_rows <= 0 || n_clips <= 1) return n_clips;
+  int sub = sweep_rows / rows_per_clip;
+  if (sub < 1) sub = 1;
+  if (sub >= n_clips) return n_clips;
+  const int n_sub = (n_clips + sub - 1) / sub;
+  return (n_clips + n_sub - 1) / n_sub;
+}
+
 // ------------------------------------------------------------------ encode
 // clip_offset / total_clips: the visual features of this call land at clip index `clip_offset` of a buffer sized for
 // `total_clips` clips (host path: chunks are encoded as their frames arrive, then decoded together).
@@ -391,9 +402,7 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
   // Clips are independent here, so a large batch walks the layers in sub-batches of ~`sweep_rows` token rows: every
   // row-sized scratch buffer is then allocated for one sub-batch only (4x less at 512 clips; throughput-neutral from
   // 128 clips per sub-batch up).  Row results do not depend on the sub-batch they are computed in (tests: bit-exact).
-  int Bsub = c->sweep_rows > 0 ? c->sweep_rows / Nv : Ball;
-  if (Bsub < 1) Bsub = 1;
-  if (Bsub > Ball) Bsub = Ball;
+  const int Bsub = sweep_clips(c->sweep_rows, Nv, Ball);
   const int Msub = Bsub * Nv;
   ENSURE(c, c->hv, (size_t)Msub * H);
   ENSURE(c, c->hvb, (size_t)Msub * H);
@@ -1032,9 +1041,7 @@ int gitb200_reserve(gitb200_ctx* c, int max_clips, int max_frames, int max_rows_
   const size_t rows = (size_t)max_clips * F * c->T;
   // row-sized scratch is needed for one sub-batch of the sweeps only (gitb200_ctx::sweep_rows); the visual features and
   // the visual K/V cache are per clip and stay whole
-  int sub_clips = c->sweep_rows > 0 ? c->sweep_rows / (F * c->T) : max_clips;
-  if (sub_clips < 1) sub_clips = 1;
-  if (sub_clips > max_clips) sub_clips = max_clips;
+  const int sub_clips = sweep_clips(c->sweep_rows, F * c->T, max_clips);
   const size_t srows = (size_t)sub_clips * F * c->T;
   ENSURE(c, c->patches, (size_t)sub_clips * F * G * G * c->kpad);
   ENSURE(c, c->x, srows * W);
@@ -1061,8 +1068,7 @@ int gitb200_reserve(gitb200_ctx* c, int max_clips, int max_frames, int max_rows_
 static int run_encode_sweeps(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, bool temporal = true) {
   const gitb200_config& k = c->cfg;
   const int F = (temporal && k.num_image_with_embedding > 0 && n_frames > k.num_image_with_embedding) ? k.num_image_with_embedding : n_frames;
-  int sub = c->sweep_rows > 0 ? c->sweep_rows / (F * c->T) : n_clips;
-  if (sub < 1) sub = 1;
+  const int sub = sweep_clips(c->sweep_rows, F * c->T, n_clips);
   if (sub >= n_clips) return run_encode(c, frames, n_clips, n_frames, s, 0, 0, nullptr, temporal);
   const size_t clip_elems = (size_t)n_frames * 3 * k.resolution * k.resolution;
   for (int done = 0; done < n_clips; done += sub) {
