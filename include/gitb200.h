@@ -178,9 +178,10 @@ int gitb200_preprocess(const uint8_t* frames_dev, int n_frames, int height, int 
 /* Host path for RAW video frames (the caller's side is real_time_inference.py:49-57 and the dataset's
  * cv2 frame reads, dataloader.py:61-75): frames_host uint8 [n_clips, n_frames, height, width, 3] BGR HWC (pinned
  * recommended) -> host tokens / log-probs exactly as gitb200_caption_host.  Frames cross PCIe as bytes in chunks of
- * `chunk_clips` clips (copy of chunk i+1 overlaps chunk i's work), image_transform() runs on the device
- * (gitb200_preprocess's kernel) straight into the ViT's input, then one batched decode.  Same result as
- * gitb200_preprocess + gitb200_caption on the same frames.  Synchronous. */
+ * `chunk_clips` clips (copy of chunk i+1 overlaps chunk i's work), image_transform() runs on the device fused into the
+ * patch-embed loader (gitb200_preprocess's arithmetic, written as bf16 straight into the patch matrix of the conv1 GEMM:
+ * no fp32 frames exist on the device), then one batched decode.  Same result, bit for bit, as gitb200_preprocess +
+ * gitb200_caption on the same frames.  Synchronous. */
 int gitb200_caption_host_u8(gitb200_ctx* ctx, const uint8_t* frames_host, int n_clips, int n_frames, int height, int width,
                             int chunk_clips, const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host);
 

@@ -271,8 +271,15 @@ int sweep_clips(int sweep_rows, int rows_per_clip, int n_clips) {
 // `total_clips` clips (host path: chunks are encoded as their frames arrive, then decoded together).
 // frame_out != nullptr: streaming mode -- write ln_post(x) WITHOUT temporal embeddings to frame_out and leave the
 // context's visual features untouched.
+// raw != nullptr: `frames` is ignored and the patch matrix is filled straight from raw uint8 BGR video frames
+// (image_transform() fused into the patch-embed loader, preprocess.cu).
+struct RawFrames {
+  const uint8_t* p;  // [n_clips, n_frames, height, width, 3] on the device
+  int height, width;
+};
+
 int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, cudaStream_t s, int clip_offset = 0, int total_clips = 0,
-               bf16* frame_out = nullptr, bool temporal = true) {
+               bf16* frame_out = nullptr, bool temporal = true, const RawFrames* raw = nullptr) {
   const gitb200_config& k = c->cfg;
   const int W = k.vit_width, T = c->T, G = k.resolution / k.patch;
   // zip() truncation of model.py:380: frames beyond the temporal-embedding list are dropped
@@ -291,7 +298,16 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   else if (c->vf.cap < (size_t)total_clips * F * T * W) return fail(c, GITB200_ERR_STATE, "visual feature buffer too small for chunked encode");
 
   const size_t frame_elems = (size_t)3 * k.resolution * k.resolution;
-  if (F == n_frames) {
+  if (raw != nullptr) {
+    const size_t raw_frame = (size_t)raw->height * raw->width * 3;
+    if (F == n_frames) {
+      CUDA_OK(c, preprocess_frames_u8_to_patches(raw->p, n_clips * F, raw->height, raw->width, k.resolution, k.patch, c->kpad, c->patches.p, s));
+    } else {
+      for (int i = 0; i < n_clips; ++i)
+        CUDA_OK(c, preprocess_frames_u8_to_patches(raw->p + (size_t)i * n_frames * raw_frame, F, raw->height, raw->width, k.resolution,
+                                                   k.patch, c->kpad, c->patches.p + (size_t)i * F * G * G * c->kpad, s));
+    }
+  } else if (F == n_frames) {
     CUDA_OK(c, im2col_patches(frames, n_clips * F, k.resolution, k.patch, c->kpad, c->patches.p, s));
   } else {
     for (int i = 0; i < n_clips; ++i)
@@ -1323,8 +1339,8 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
 
 // Raw video frames from the host: uint8 BGR HWC, as cv2.VideoCapture / cv2.resize deliver them (real_time_inference.py:49-57,
 // dataloader.py:61-75).  A chunk's frames cross PCIe as bytes (height*width*3 per frame instead of 3*R*R*4 after the
-// host-side image_transform), are resized / cropped / normalised by preprocess_kernel into the fp32 staging buffer, and go
-// straight into the ViT; the copy of chunk i+1 overlaps the preprocessing + ViT of chunk i.
+// host-side image_transform) and are resized / cropped / normalised by preprocess_kernel<true> straight into the bf16 patch
+// matrix of the patch-embedding GEMM (no fp32 frames on the device at all); the copy of chunk i+1 overlaps chunk i's ViT.
 int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_clips, int n_frames, int height, int width,
                             int chunk_clips, const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host) {
   if (!c || !frames_host || !sp || !tokens_host || !logprobs_host || n_clips < 1 || n_frames < 1 || height < 1 || width < 1)
@@ -1332,9 +1348,7 @@ int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_cl
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
-  const int R = c->cfg.resolution;
   const size_t clip_bytes = (size_t)n_frames * height * width * 3;
-  const size_t clip_elems = (size_t)n_frames * 3 * R * R;
   const int per_clip_tok = sp->num_keep_best * sp->max_steps;
   if (!c->copy_stream) {
     CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -1346,7 +1360,6 @@ int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_cl
   if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
   cudaStream_t comp = c->comp_stream;
   for (int i = 0; i < 2; ++i) ENSURE(c, c->stage_u8[i], (size_t)chunk_clips * clip_bytes);
-  ENSURE(c, c->stage[0], (size_t)chunk_clips * clip_elems);  // one fp32 buffer: preprocess and ViT of a chunk are stream-ordered
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
   int done = 0, ch = 0;
@@ -1359,9 +1372,9 @@ int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_cl
                                cudaMemcpyHostToDevice, c->copy_stream));
     CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
     CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-    CUDA_OK(c, preprocess_frames_u8(c->stage_u8[b].p, nc * n_frames, height, width, R, c->stage[0].p, comp));
+    const RawFrames raw{c->stage_u8[b].p, height, width};
+    TRY(run_encode(c, nullptr, nc, n_frames, comp, done, n_clips, nullptr, true, &raw));  // its first kernel consumes the bytes
     CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
-    TRY(run_encode(c, c->stage[0].p, nc, n_frames, comp, done, n_clips));
     done += nc;
     ++ch;
   }

@@ -172,6 +172,9 @@ cudaError_t anc_reorder(const int* anc_in, int* anc_out, const int* beam_idx, in
 // uint8 BGR HWC frames [n, H, W, 3] -> fp32 RGB NCHW [n, 3, size, size]: bicubic resize of the smaller edge to `size`,
 // centre crop, CLIP normalisation (the reference's image_transform(), src/utils/dataloader.py:18-32).
 cudaError_t preprocess_frames_u8(const uint8_t* frames, int n, int H, int W, int size, float* out, cudaStream_t stream);
+// same pixels written as bf16 into the patch-embedding GEMM's A matrix (im2col layout, K padded to kpad): no fp32 frames in between
+cudaError_t preprocess_frames_u8_to_patches(const uint8_t* frames, int n, int H, int W, int size, int patch, int kpad,
+                                            bf16* patches, cudaStream_t stream);
 
 // LayerNorm folding at weight-load time: wf[n,k] = bf16(w[n,k] * gamma[k]); colsum[n] = sum_k float(wf[n,k]);
 // bias_f[n] = bias[n] + sum_k w[n,k] * beta[k].

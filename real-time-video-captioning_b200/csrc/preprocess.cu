@@ -18,9 +18,13 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
   c[3] = cubic2(2.f - t, A);
 }
 
+// TO_PATCHES: write the pixel as bf16 straight into the patch matrix the patch-embedding GEMM reads (the im2col layout of
+// elementwise.cu: row = (frame, patch row, patch column), column = c*P*P + ky*P + kx, columns >= 3*P*P zero) instead of
+// fp32 NCHW -- same value, same round-to-nearest cast as im2col_kernel, so the two routes agree bit for bit.
+template <bool TO_PATCHES>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ frames, int n, int H, int W, int nh, int nw, int top, int left, int size,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, bf16* __restrict__ patches, int P, int kpad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = n * size * size;
   if (idx >= total) return;
@@ -54,9 +58,19 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int n, int H, int W, int n
   // BGR -> RGB and CLIP normalisation: output channel c reads input channel 2 - c
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
-  float* o = out + (size_t)f * 3 * size * size + (size_t)oy * size + ox;
+  if (TO_PATCHES) {
+    const int G = size / P;
+    const int gy = oy / P, ky = oy - gy * P, gx = ox / P, kx = ox - gx * P;
+    bf16* o = patches + ((size_t)f * G * G + (size_t)gy * G + gx) * kpad;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) o[(size_t)c * size * size] = (acc[2 - c] - mean[c]) / stdv[c];
+    for (int c = 0; c < 3; ++c) o[c * P * P + ky * P + kx] = __float2bfloat16_rn((acc[2 - c] - mean[c]) / stdv[c]);
+    if (ky == 0 && kx == 0)
+      for (int k = 3 * P * P; k < kpad; ++k) o[k] = __float2bfloat16_rn(0.f);
+  } else {
+    float* o = out + (size_t)f * 3 * size * size + (size_t)oy * size + ox;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[(size_t)c * size * size] = (acc[2 - c] - mean[c]) / stdv[c];
+  }
 }
 
 }  // namespace
@@ -68,7 +82,20 @@ cudaError_t preprocess_frames_u8(const uint8_t* frames, int n, int H, int W, int
   if (H <= W) { nh = size; nw = (int)((double)size * W / H); } else { nh = (int)((double)size * H / W); nw = size; }
   const int top = (int)lrint((nh - size) / 2.0), left = (int)lrint((nw - size) / 2.0);
   const int total = n * size * size;
-  preprocess_kernel<<<(total + 255) / 256, 256, 0, stream>>>(frames, n, H, W, nh, nw, top, left, size, out);
+  preprocess_kernel<false><<<(total + 255) / 256, 256, 0, stream>>>(frames, n, H, W, nh, nw, top, left, size, out, nullptr, 0, 0);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t preprocess_frames_u8_to_patches(const uint8_t* frames, int n, int H, int W, int size, int patch, int kpad,
+                                            bf16* patches, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (H < 1 || W < 1 || size < 1 || patch < 1 || size % patch != 0 || kpad < 3 * patch * patch) return cudaErrorInvalidValue;
+  int nh, nw;
+  if (H <= W) { nh = size; nw = (int)((double)size * W / H); } else { nh = (int)((double)size * H / W); nw = size; }
+  const int top = (int)lrint((nh - size) / 2.0), left = (int)lrint((nw - size) / 2.0);
+  const int total = n * size * size;
+  preprocess_kernel<true><<<(total + 255) / 256, 256, 0, stream>>>(frames, n, H, W, nh, nw, top, left, size, nullptr, patches, patch, kpad);
   note_launch();
   return cudaGetLastError();
 }

@@ -487,6 +487,13 @@ def test_git_large_vit_l14_matches_oracle(g):
                     se, so_ = norm_score(el[0].cpu(), hyp), norm_score(ol[0], hyp)
                     record("git_large_cross_score", clip=b, reorder=reorder, hyp=hyp.tolist(), engine=se, oracle=so_)
                     assert abs(se - so_) < 0.03, (hyp, se, so_)
+    # raw uint8 frames through the fused preprocess -> patch-matrix loader with a 14-pixel patch (K 588 zero-padded to 640)
+    raw = torch.randint(0, 256, (2, 3, 180, 240, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(29))
+    sp1 = g.SearchConfig(beam_size=1, max_steps=5)
+    dev = g.preprocess_frames(raw.view(-1, 180, 240, 3).cuda()).view(2, 3, 3, 224, 224)  # 3 frames: the third is dropped (zip), per-clip loader branch
+    td, ld, _ = eng.caption(dev.contiguous(), sp1)
+    th, lh = eng.caption_host_u8(raw.pin_memory(), sp1, chunk_clips=2)
+    assert torch.equal(td.cpu(), th) and torch.allclose(ld.cpu(), lh, rtol=2e-2, atol=5e-3)
 
 
 def test_cuda_graph_replay_equals_eager(g, setup):
