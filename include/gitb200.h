@@ -164,6 +164,9 @@ int gitb200_decode_reorder(gitb200_ctx* ctx, const int32_t* beam_idx_dev, int po
  * sliding window with per-frame feature reuse). */
 int gitb200_stream_reset(gitb200_ctx* ctx);
 int gitb200_stream_push(gitb200_ctx* ctx, const float* frame_dev, void* stream);
+/* gitb200_stream_push for a raw webcam frame: frame_dev uint8 [height, width, 3] BGR HWC on the device (what
+ * cv2.VideoCapture.read() returns, real_time_inference.py:49-57); image_transform() runs fused into the patch-embed loader. */
+int gitb200_stream_push_u8(gitb200_ctx* ctx, const uint8_t* frame_dev, int height, int width, void* stream);
 int gitb200_stream_frames(const gitb200_ctx* ctx);
 int gitb200_stream_caption(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev,
                            void* stream);

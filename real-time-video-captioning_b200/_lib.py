@@ -80,6 +80,7 @@ SIGNATURES = {
     "gitb200_decode_reorder": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "gitb200_stream_reset": (c_int, [c_void_p]),
     "gitb200_stream_push": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gitb200_stream_push_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "gitb200_stream_frames": (c_int, [c_void_p]),
     "gitb200_stream_caption": (c_int, [c_void_p, POINTER(SearchParams), c_void_p, c_void_p, c_void_p]),
     "gitb200_preprocess": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -1217,6 +1217,30 @@ int gitb200_stream_push(gitb200_ctx* c, const float* frame, void* stream) {
   return GITB200_OK;
 }
 
+// The same for a RAW webcam frame (uint8 BGR HWC on the device, real_time_inference.py:49-57): image_transform() runs
+// fused into the patch-embed loader, so a push is the ViT's own launches and nothing else.
+int gitb200_stream_push_u8(gitb200_ctx* c, const uint8_t* frame, int height, int width, void* stream) {
+  if (!c || !frame || height < 1 || width < 1) return fail(c, GITB200_ERR_INVALID, "bad stream_push_u8 argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  const int cap = c->cfg.num_image_with_embedding;
+  if (cap < 1) return fail(c, GITB200_ERR_STATE, "streaming needs num_image_with_embedding >= 1 (the window length)");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  const size_t per_frame = (size_t)c->T * c->cfg.vit_width;
+  ENSURE(c, c->ring, (size_t)cap * per_frame);
+  {
+    gitb200_ctx::GraphKey key;
+    key.kind = 3; key.p0 = frame; key.i0 = c->ring_head; key.i1 = height; key.i2 = width;
+    bf16* dst = c->ring.p + (size_t)c->ring_head * per_frame;
+    const RawFrames raw{frame, height, width};
+    const int r = run_graphed(c, key, (cudaStream_t)stream, true,
+                              [&]() { return run_encode(c, nullptr, 1, 1, (cudaStream_t)stream, 0, 0, dst, true, &raw); });
+    if (r != 0 && r != 1) return r;
+  }
+  c->ring_head = (c->ring_head + 1) % cap;
+  if (c->ring_count < cap) c->ring_count++;
+  return GITB200_OK;
+}
+
 int gitb200_stream_frames(const gitb200_ctx* c) { return c ? c->ring_count : 0; }
 
 int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int32_t* tokens, float* logprobs, void* stream) {

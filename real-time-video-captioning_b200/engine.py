@@ -243,6 +243,15 @@ class Engine:
         check(self.lib.gitb200_stream_push(self.h, _ptr(frame), self._stream()), self.h, "gitb200_stream_push")
         return int(self.lib.gitb200_stream_frames(self.h))
 
+    def stream_push_u8(self, frame_u8: torch.Tensor) -> int:
+        """Encode one RAW frame uint8 [H, W, 3] (OpenCV BGR, on this device) into the window: image_transform() runs fused
+        into the patch-embed loader.  Keep pushing from the same buffer and the library replays a CUDA graph."""
+        assert frame_u8.is_cuda and frame_u8.dtype == torch.uint8 and frame_u8.dim() == 3 and frame_u8.shape[-1] == 3
+        assert frame_u8.is_contiguous()
+        h, w = frame_u8.shape[:2]
+        check(self.lib.gitb200_stream_push_u8(self.h, _ptr(frame_u8), h, w, self._stream()), self.h, "gitb200_stream_push_u8")
+        return int(self.lib.gitb200_stream_frames(self.h))
+
     def stream_caption(self, sp: SearchConfig):
         # persistent output buffers: identical call signatures let the library replay its captured CUDA graph
         key = (sp.num_keep_best, sp.max_steps)

@@ -686,6 +686,7 @@ class StreamingCaptioner:
         self.search = SearchConfig(beam_size=beam_size, max_steps=max_len + 1, length_penalty=d.length_penalty,
                                    per_node_beam_size=d.per_node_beam_size, num_keep_best=1)
         self._counter = 0
+        self._raw, self._raw_key = None, None
         self.latest_caption = ""
         self.engine.stream_reset()
 
@@ -696,8 +697,14 @@ class StreamingCaptioner:
         if self._counter < self.stride:
             return None
         self._counter = 0
-        x = self._pre(frame_bgr_u8.to(self.engine.device)[None], self.engine.cfg.resolution)
-        held = self.engine.stream_push(x[0])
+        # one persistent device buffer per frame size: the same pointer on every push lets the library replay its CUDA
+        # graph of (fused image_transform + patch embed + ViT) instead of launching the ~90 kernels one by one
+        key = tuple(frame_bgr_u8.shape)
+        if self._raw is None or self._raw_key != key:
+            self._raw = torch.empty(key, dtype=torch.uint8, device=self.engine.device)
+            self._raw_key = key
+        self._raw.copy_(frame_bgr_u8, non_blocking=True)
+        held = self.engine.stream_push_u8(self._raw)
         if held < self.window:
             return None
         tokens, _ = self.engine.stream_caption(self.search)

@@ -706,6 +706,21 @@ def test_streaming_window_equals_clip_caption(g, setup):
     with torch.no_grad():
         ref = so.infer(sd, cfg, go.encode_clip(sd, cfg, clip), beam_size=1, max_steps=6, save_logits=False)
     assert outs[5] == teacher.tokenizer.decode(ref["predictions"][0].tolist(), skip_special_tokens=True)
+    # raw-frame push (image_transform fused into the patch-embed loader) == preprocess kernel + fp32 push, bit for bit;
+    # repeated pushes from the same buffer go through the CUDA-graph replay
+    buf = torch.empty(120, 160, 3, dtype=torch.uint8, device="cuda")
+    for mode in ("u8", "f32", "u8"):
+        eng.stream_reset()
+        for f in raw[:4]:
+            if mode == "u8":
+                buf.copy_(f)
+                eng.stream_push_u8(buf)
+            else:
+                eng.stream_push(g.preprocess_frames(f[None].cuda())[0])
+        tk, lpk = eng.stream_caption(sp)
+        if mode == "u8" and "first" not in locals():
+            first = (tk.clone(), lpk.clone())
+        assert torch.equal(tk, first[0]) and torch.equal(lpk, first[1]), mode
 
 
 @pytest.mark.parametrize("n_clips,n_frames,nb,keep,max_steps", [(1, 1, 1, 1, 2), (1, 1, 8, 3, 5), (5, 2, 2, 2, 4), (2, 1, 4, 1, 20)])
