@@ -754,7 +754,7 @@ def test_full_size_properties_bench_geometry(g):
       * batch invariance: a clip's caption does not depend on what else is in the batch -- 96 clips at once == three calls of
         32 (different GEMM tile counts, different persistent-attention work lists, different decode-attention grids);
       * shard invariance: the contiguous shards a 2-GPU run would take, concatenated, equal the single call (SURVEY 8e);
-      * beam-1 of the beam-search path == the greedy facade."""
+      * sweep invariance: the ViT / visual pass walked in sub-batches of 32 clips or in one sweep (gitb200_set_sweep_rows)."""
     F6 = 6
     cfg = go.GitConfig(num_image_with_embedding=F6)
     sd = go.init_state_dict(cfg, seed=21, temporal_std=0.02, perturb=True)
@@ -779,3 +779,12 @@ def test_full_size_properties_bench_geometry(g):
     ts = torch.cat([eng.caption(frames[a:b].contiguous(), sp)[0] for a, b in shards])
     assert ((ts == t0).all(dim=-1).all(dim=-1)).float().mean().item() >= 0.99
     assert t0.shape == (96, 1, 15) and (t0[:, 0, 0] == cfg.sos_index).all()
+    # sub-batch sweeps at the bench geometry: 3 x 32 clips (37824 rows each) and the single 96-clip sweep are bit-identical
+    try:
+        eng.set_sweep_rows(32 * F6 * 197)
+        t3, l3, _ = eng.caption(frames, sp)
+        eng.set_sweep_rows(0)
+        t4, l4, _ = eng.caption(frames, sp)
+    finally:
+        eng.set_sweep_rows(151296)
+    assert torch.equal(t3, t0) and torch.equal(l3, l0) and torch.equal(t4, t0) and torch.equal(l4, l0)
