@@ -105,6 +105,18 @@ int gitb200_decode(gitb200_ctx* ctx, const gitb200_search_params* sp, int32_t* t
 int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int n_frames,
                     const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
                     void* stream);
+/* The reference leaves its step loop as soon as every clip's search is finished (`if all(done): break`, model.py:640).
+ * The device search counts finished clips; every `every_steps` decode steps (default 4; 0 = never, the call then stays
+ * fully asynchronous) the host reads that count (4 bytes + one stream synchronisation) and stops enqueueing steps when
+ * it equals n_clips.  Finished clips never change again, so tokens / scores are identical either way; only calls that
+ * are being captured into a CUDA graph always run all steps.  gitb200_last_decode_steps: steps the last decode enqueued
+ * (= len(saved_logits) of the reference; rows of logits_dev beyond it are not written). */
+int gitb200_set_early_exit(gitb200_ctx* ctx, int every_steps);
+int gitb200_last_decode_steps(const gitb200_ctx* ctx);
+/* gitb200_caption calls of up to `max_clips` clips are captured into CUDA graphs (default 8: the launch-bound latency
+ * mode).  Larger values also graph throughput-sized batches once gitb200_reserve has pinned the workspaces. */
+int gitb200_set_graph_max_clips(gitb200_ctx* ctx, int max_clips);
+
 /* Opt-in (default off): ViT ln_1 / ln_2 folded into the following QKV / fc1 GEMM: the GEMM reads the raw residual stream, its
  * weights carry gamma, its bias carries W*beta, and its epilogue applies rstd*(acc - mean*colsum) from row statistics
  * emitted by the previous residual GEMM's epilogue.  0 restores the separate LayerNorm kernels (same result within the

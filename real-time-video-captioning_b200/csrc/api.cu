@@ -117,8 +117,14 @@ struct gitb200_ctx {
   struct GraphEntry {
     GraphKey key;
     cudaGraphExec_t exec = nullptr;  // nullptr: seen once, not captured yet
+    unsigned long long gen = 0;      // workspace generation the graph was captured under
   };
   std::vector<GraphEntry> graphs;
+  // A captured graph bakes in the workspace pointers (x / qkv / kv / txt_kv / ibuf ...) and the launch sequence the
+  // switches select.  Whenever a workspace is actually reallocated (ensure(): cudaFree + cudaMalloc for a larger call or
+  // gitb200_reserve) or a switch that changes the launch sequence flips (fold_ln, sweep_rows, pipeline), the generation
+  // moves on and every graph captured under an older generation is destroyed before it can be replayed.
+  unsigned long long ws_gen = 0;
   bool graphs_enabled = true;
   long long graph_launches = 0;
 
@@ -146,6 +152,12 @@ struct gitb200_ctx {
   // forward-hook taps on image_encoder.transformer.resblocks[i] (model.py:847): outputs copied out by the next encodes
   std::vector<int> tap_layers;
   float* tap_out = nullptr;
+
+  // decode loop early exit (model.py:640): poll the device's done count every N steps (0 = never: fully asynchronous)
+  int early_exit_every = 4;
+  int* h_done = nullptr;             // pinned
+  int last_decode_steps = 0;         // decode steps the last gitb200_decode / _caption call enqueued
+  int graph_max_clips = 8;           // calls of up to this many clips are captured into CUDA graphs (latency mode)
 
   // current state
   int cur_clips = 0, cur_nv = 0;     // visual features held in vf
@@ -182,7 +194,10 @@ int fail(gitb200_ctx* c, int code, const char* fmt, ...) {
 template <typename T>
 int ensure(gitb200_ctx* c, Buf<T>& b, size_t n) {
   if (b.cap >= n) return 0;
-  if (b.p) CUDA_OK(c, cudaFree(b.p));
+  if (b.p) {
+    CUDA_OK(c, cudaFree(b.p));
+    if (c) c->ws_gen++;  // captured graphs hold the freed pointer: they are stale from here on (see gitb200_ctx::ws_gen)
+  }
   b.p = nullptr;
   b.cap = 0;
   CUDA_OK(c, cudaMalloc(&b.p, n * sizeof(T)));
@@ -406,6 +421,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   c->cur_clips = clip_offset + n_clips;
   c->cur_nv = F * T;
   c->visual_pass_done = false;
+  c->step_rows_per_clip = 0;  // a step-wise decoding state set up for the previous features is void
   return 0;
 }
 
@@ -655,7 +671,7 @@ int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unuse
   if (nb < 1 || nb > 8 || sp.per_node_beam_size < 1 || nb * sp.per_node_beam_size > 16 || nk < 1 || nk > 15 || ml < 2)
     return fail(c, GITB200_ERR_INVALID, "unsupported search parameters (beam %d, per-node %d, keep %d, max_steps %d)", nb,
                 sp.per_node_beam_size, nk, ml);
-  const size_t n_int = (size_t)rows * ml * 4 + (size_t)n_clips * 2 + rows + (size_t)n_clips * (nk + 1) * (1 + ml);
+  const size_t n_int = (size_t)rows * ml * 4 + (size_t)n_clips * 2 + 1 + rows + (size_t)n_clips * (nk + 1) * (1 + ml);
   ENSURE(c, c->ibuf, n_int);
   ENSURE(c, c->dbuf, (size_t)n_clips * (nk + 2));
   ENSURE(c, c->fbuf, (size_t)rows);
@@ -668,6 +684,7 @@ int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unuse
   st->anc_tmp = ip; ip += (size_t)rows * ml;
   st->done = ip; ip += n_clips;
   st->hyp_count = ip; ip += n_clips;
+  st->done_count = ip; ip += 1;
   st->cur_tok = ip; ip += rows;
   st->hyp_len = ip; ip += (size_t)n_clips * (nk + 1);
   st->hyp_tok = ip;
@@ -689,6 +706,17 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
   if (!logits_out) ENSURE(c, c->logits, (size_t)rows * c->vocab_pad);
   CUDA_OK(c, search_init(st, k.sos, s));
   int parity = 0;
+  // model.py:640 `if all(done): break`: every `early_exit_every` steps the host reads the device's count of finished clips
+  // (4 bytes, one stream synchronisation) and stops enqueueing decode steps once every clip is done.  Finished clips no
+  // longer change, so the result is the same as running all steps; skipped while the stream is being captured into a graph.
+  bool poll_done = c->early_exit_every > 0;
+  if (poll_done) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) poll_done = false;
+    cudaGetLastError();
+    if (poll_done && !c->h_done) CUDA_OK(c, cudaMallocHost(&c->h_done, sizeof(int)));
+  }
+  c->last_decode_steps = 0;
   for (int t = 0; t + 1 < sp.max_steps; ++t) {  // model.py:518: while cur_len < max_length, cur_len = t + 1
     TextPass tp;
     tp.n_clips = B; tp.rows_per_clip = nb; tp.max_len = sp.max_steps;
@@ -701,6 +729,12 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
     TRY(run_text_pass(c, tp, s));
     CUDA_OK(c, search_step(st, tp.logits, t + 1, parity, s));
     parity ^= 1;
+    c->last_decode_steps = t + 1;
+    if (poll_done && (t + 1) % c->early_exit_every == 0 && t + 2 < sp.max_steps) {
+      CUDA_OK(c, cudaMemcpyAsync(c->h_done, st.done_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(c, cudaStreamSynchronize(s));
+      if (*c->h_done >= B) break;
+    }
   }
   CUDA_OK(c, search_finalize(st, tokens_out, logprobs_out, s));
   return 0;
@@ -792,6 +826,15 @@ bool graph_stream_ok(cudaStream_t s) { return s != nullptr && s != cudaStreamLeg
 template <class Body>
 int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s, bool eligible, Body&& body) {
   if (!eligible || !c->graphs_enabled || !c->tap_layers.empty() || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
+  // drop every graph captured before the last workspace reallocation / launch-sequence switch
+  for (size_t i = 0; i < c->graphs.size();) {
+    if (c->graphs[i].gen != c->ws_gen) {
+      if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
+      c->graphs.erase(c->graphs.begin() + i);
+    } else {
+      ++i;
+    }
+  }
   gitb200_ctx::GraphEntry* ent = nullptr;
   for (auto& g : c->graphs)
     if (g.key == key) ent = &g;
@@ -808,13 +851,23 @@ int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s
     }
     gitb200_ctx::GraphEntry e;
     e.key = key;
+    const int r = body();  // every workspace gets sized by this eager run
+    e.gen = c->ws_gen;     // (read after the run: its own first-time allocations do not count against it)
     c->graphs.push_back(e);
-    return body();  // every workspace gets sized by this eager run
+    return r;
   }
   cudaGraph_t graph = nullptr;
+  const unsigned long long gen0 = c->ws_gen;
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
     const int r = body();
     const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (c->ws_gen != gen0) {
+      // a workspace moved while capturing (cannot happen after the sizing run, but never keep such a graph): run eagerly
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ent->gen = c->ws_gen;
+      return body();
+    }
     if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
       cudaGraphDestroy(graph);
       CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
@@ -917,6 +970,7 @@ void gitb200_destroy(gitb200_ctx* c) {
   if (c->ev_enc0) cudaEventDestroy(c->ev_enc0);
   for (auto& g : c->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (c->h_done) cudaFreeHost(c->h_done);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
   for (int i = 0; i < 2; ++i) {
@@ -1096,6 +1150,7 @@ static int run_encode_sweeps(gitb200_ctx* c, const float* frames, int n_clips, i
 
 int gitb200_set_sweep_rows(gitb200_ctx* c, int rows) {
   if (!c || rows < 0) return fail(c, GITB200_ERR_INVALID, "gitb200_set_sweep_rows: rows must be >= 0");
+  if (c->sweep_rows != rows) c->ws_gen++;  // captured graphs replay the old sub-batch walk
   c->sweep_rows = rows;
   if (c->twin) c->twin->sweep_rows = rows;
   return GITB200_OK;
@@ -1143,6 +1198,7 @@ int gitb200_set_visual_features(gitb200_ctx* c, const float* vf, int n_clips, in
   c->cur_clips = n_clips;
   c->cur_nv = nv;
   c->visual_pass_done = false;
+  c->step_rows_per_clip = 0;
   return GITB200_OK;
 }
 
@@ -1167,7 +1223,7 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
   // Latency mode: a small batch is launch-bound (~850 kernels per caption), so the second call with the same
   // buffers / shapes on a capturable stream is recorded into a CUDA graph and later calls replay it.
   cudaStream_t s = (cudaStream_t)stream;
-  if (n_clips > 0 && n_clips <= 8 && frames && tokens && logprobs && c->finalized) {
+  if (n_clips > 0 && n_clips <= c->graph_max_clips && frames && tokens && logprobs && c->finalized) {
     gitb200_ctx::GraphKey key;
     key.kind = 0; key.p0 = frames; key.p1 = tokens; key.p2 = logprobs; key.i0 = n_clips; key.i1 = n_frames;
     key.i2 = logits != nullptr; key.sp = *sp;
@@ -1175,7 +1231,8 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
     const int r = run_graphed(c, key, s, logits == nullptr, [&]() { return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream); });
     if (r == 1) {  // replayed: host-side state the eager path would have left behind
       const int F = (c->cfg.num_image_with_embedding > 0 && n_frames > c->cfg.num_image_with_embedding) ? c->cfg.num_image_with_embedding : n_frames;
-      c->cur_clips = n_clips; c->cur_nv = F * c->T; c->visual_pass_done = true; c->visual_pass_full = 0;
+      c->cur_clips = n_clips; c->cur_nv = F * c->T; c->visual_pass_done = true; c->visual_pass_full = 0; c->step_rows_per_clip = 0;
+      c->last_decode_steps = sp->max_steps - 1;
       return GITB200_OK;
     }
     return r;
@@ -1258,10 +1315,11 @@ int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int3
     c->cur_clips = 1;
     c->cur_nv = n * T;
     c->visual_pass_done = false;
+    c->step_rows_per_clip = 0;
     return run_decode(c, *sp, tokens, logprobs, nullptr, s);
   });
   if (r == 1) {
-    c->cur_clips = 1; c->cur_nv = n * T; c->visual_pass_done = true; c->visual_pass_full = 0;
+    c->cur_clips = 1; c->cur_nv = n * T; c->visual_pass_done = true; c->visual_pass_full = 0; c->step_rows_per_clip = 0;
     return GITB200_OK;
   }
   return r;
@@ -1269,13 +1327,29 @@ int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int3
 
 int gitb200_set_fold_layernorm(gitb200_ctx* c, int enable) {
   if (!c) return GITB200_ERR_INVALID;
+  if (c->fold_ln != (enable != 0)) c->ws_gen++;  // captured graphs replay the other launch sequence
   c->fold_ln = enable != 0;
   if (c->twin) c->twin->fold_ln = c->fold_ln;
   return GITB200_OK;
 }
 
+int gitb200_set_early_exit(gitb200_ctx* c, int every_steps) {
+  if (!c || every_steps < 0) return fail(c, GITB200_ERR_INVALID, "gitb200_set_early_exit: every_steps must be >= 0");
+  c->early_exit_every = every_steps;
+  return GITB200_OK;
+}
+
+int gitb200_last_decode_steps(const gitb200_ctx* c) { return c ? c->last_decode_steps : 0; }
+
+int gitb200_set_graph_max_clips(gitb200_ctx* c, int max_clips) {
+  if (!c || max_clips < 0) return fail(c, GITB200_ERR_INVALID, "gitb200_set_graph_max_clips: max_clips must be >= 0");
+  c->graph_max_clips = max_clips;
+  return GITB200_OK;
+}
+
 int gitb200_set_pipeline(gitb200_ctx* c, int chunk_clips) {
   if (!c) return GITB200_ERR_INVALID;
+  if (c->pipeline_chunk != chunk_clips) c->ws_gen++;
   c->pipeline_chunk = chunk_clips;
   return GITB200_OK;
 }

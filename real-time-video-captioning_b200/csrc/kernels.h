@@ -144,6 +144,7 @@ struct SearchState {
   int* tokens_tmp;    // [n_rows, max_len]
   float* beam_scores; // [n_rows]
   int* done;          // [n_clips]
+  int* done_count;    // [1] number of clips whose search is finished (model.py:640 `if all(done): break`)
   int* anc;           // [n_rows, max_len] ancestor slot per text position
   int* anc_tmp;
   int* cur_tok;       // [n_rows] token fed to the next step

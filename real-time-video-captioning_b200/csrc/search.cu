@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(SS_THREADS) search_step_kernel(SearchState st,
     }
     st.hyp_count[clip] = cnt;
     st.worst[clip] = worst;
+    if (is_done && !st.done[clip]) atomicAdd(st.done_count, 1);  // the host polls this to leave the step loop early
     st.done[clip] = is_done;
   }
   __syncthreads();
@@ -230,6 +231,7 @@ __global__ void search_init_kernel(SearchState st, int sos) {
       st.anc_tmp[(size_t)row * st.max_len + t] = row;
     }
   }
+  if (row == 0) *st.done_count = 0;
   if (row < st.n_clips) {
     st.done[row] = 0;
     st.hyp_count[row] = 0;

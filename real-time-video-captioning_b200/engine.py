@@ -66,6 +66,8 @@ class Engine:
         self.ld = self.lib.gitb200_logits_ld(h)
         self.finalized = False
         self._cur_nv = 0
+        self._cur_clips = 0      # clips whose visual features the context holds
+        self._step_rows = 0      # rows per clip of the step-wise decoding state (decode_begin)
 
     def close(self):
         if getattr(self, "h", None):
@@ -104,7 +106,7 @@ class Engine:
         Fe = min(F, n) if n > 0 else F
         out = torch.empty(B, Fe * self.T, self.cfg.vit_width, dtype=torch.float32, device=self.device) if want_features else None
         check(self.lib.gitb200_encode(self.h, _ptr(frames), B, F, _ptr(out), self._stream()), self.h, "gitb200_encode")
-        self._cur_nv = Fe * self.T
+        self._cur_nv, self._cur_clips, self._step_rows = Fe * self.T, B, 0
         return out
 
     def encode_images(self, images: torch.Tensor, want_features: bool = True) -> Optional[torch.Tensor]:
@@ -114,7 +116,7 @@ class Engine:
         B = images.shape[0]
         out = torch.empty(B, self.T, self.cfg.vit_width, dtype=torch.float32, device=self.device) if want_features else None
         check(self.lib.gitb200_encode_images(self.h, _ptr(images), B, _ptr(out), self._stream()), self.h, "gitb200_encode_images")
-        self._cur_nv = self.T
+        self._cur_nv, self._cur_clips, self._step_rows = self.T, B, 0
         return out
 
     def set_vit_taps(self, layers, n_clips: int = 0, n_frames: int = 0) -> Optional[torch.Tensor]:
@@ -138,7 +140,7 @@ class Engine:
         vf = vf.to(torch.float32).contiguous()
         check(self.lib.gitb200_set_visual_features(self.h, _ptr(vf), vf.shape[0], vf.shape[1], self._stream()), self.h,
               "gitb200_set_visual_features")
-        self._cur_nv = vf.shape[1]
+        self._cur_nv, self._cur_clips, self._step_rows = vf.shape[1], vf.shape[0], 0
 
     def decode(self, n_clips: int, sp: SearchConfig, save_logits: bool = False):
         """Search on the current visual features: (tokens int32 [B, keep, max_steps], logprobs [B, keep],
@@ -150,6 +152,8 @@ class Engine:
         c = sp.to_c()
         check(self.lib.gitb200_decode(self.h, ctypes.byref(c), _ptr(tokens), _ptr(logprobs), _ptr(logits), self._stream()),
               self.h, "gitb200_decode")
+        if logits is not None:  # the step loop may have stopped early (`if all(done): break`, model.py:640)
+            logits = logits[: self.last_decode_steps()]
         return tokens, logprobs, logits
 
     def caption(self, frames: torch.Tensor, sp: SearchConfig, save_logits: bool = False):
@@ -163,6 +167,10 @@ class Engine:
         c = sp.to_c()
         check(self.lib.gitb200_caption(self.h, _ptr(frames), B, F, ctypes.byref(c), _ptr(tokens), _ptr(logprobs),
                                        _ptr(logits), self._stream()), self.h, "gitb200_caption")
+        n = self.cfg.num_image_with_embedding
+        self._cur_nv, self._cur_clips, self._step_rows = (min(F, n) if n > 0 else F) * self.T, B, 0
+        if logits is not None:
+            logits = logits[: self.last_decode_steps()]
         return tokens, logprobs, logits
 
     def caption_host(self, frames_host: torch.Tensor, sp: SearchConfig, chunk_clips: int = 32):
@@ -177,6 +185,8 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.gitb200_caption_host(self.h, _ptr(frames_host), N, F, chunk_clips, ctypes.byref(c),
                                                 _ptr(tokens), _ptr(logprobs)), self.h, "gitb200_caption_host")
+        n = self.cfg.num_image_with_embedding
+        self._cur_nv, self._cur_clips, self._step_rows = (min(F, n) if n > 0 else F) * self.T, N, 0
         return tokens, logprobs
 
     def caption_host_u8(self, frames_host: torch.Tensor, sp: SearchConfig, chunk_clips: int = 32):
@@ -191,6 +201,8 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.gitb200_caption_host_u8(self.h, _ptr(frames_host), N, F, H, W, chunk_clips, ctypes.byref(c),
                                                    _ptr(tokens), _ptr(logprobs)), self.h, "gitb200_caption_host_u8")
+        n = self.cfg.num_image_with_embedding
+        self._cur_nv, self._cur_clips, self._step_rows = (min(F, n) if n > 0 else F) * self.T, N, 0
         return tokens, logprobs
 
     def forward_logits(self, frames: Optional[torch.Tensor], tokens: torch.Tensor, want_hidden: bool = True,
@@ -209,7 +221,9 @@ class Engine:
         else:
             F = 0
             nv = self._cur_nv
-        self._cur_nv = nv
+        if frames is None and B != self._cur_clips:
+            raise GitB200Error(f"forward_logits: {B} token rows for the {self._cur_clips} clips whose features are resident")
+        self._cur_nv, self._cur_clips, self._step_rows = nv, B, 0
         logits = torch.empty(B * L, self.ld, dtype=torch.float32, device=self.device)
         hidden = torch.empty(B, self.cfg.dec_layers + 1, nv + L, self.cfg.hidden, dtype=torch.float32,
                              device=self.device) if want_hidden else None
@@ -221,15 +235,22 @@ class Engine:
     # ---- step-wise decoding for a generic search loop
     def decode_begin(self, rows_per_clip: int) -> None:
         check(self.lib.gitb200_decode_begin(self.h, rows_per_clip, self._stream()), self.h, "gitb200_decode_begin")
+        self._step_rows = rows_per_clip
 
     def decode_step(self, tokens: torch.Tensor, pos: int) -> torch.Tensor:
         tok = tokens.to(device=self.device, dtype=torch.int32).contiguous()
+        # the C side indexes cur_clips * rows_per_clip rows of `tokens` / `logits`: a mismatch would read out of bounds
+        if self._step_rows < 1 or tok.numel() != self._cur_clips * self._step_rows:
+            raise GitB200Error(f"decode_step: {tok.numel()} token rows, but decode_begin set up {self._cur_clips} clips x "
+                               f"{self._step_rows} rows")
         logits = torch.empty(tok.numel(), self.ld, dtype=torch.float32, device=self.device)
         check(self.lib.gitb200_decode_step(self.h, _ptr(tok), pos, _ptr(logits), self._stream()), self.h, "gitb200_decode_step")
         return logits[:, : self.cfg.vocab]
 
     def decode_reorder(self, beam_idx: torch.Tensor, pos: int) -> None:
         idx = beam_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        if idx.numel() != self._cur_clips * self._step_rows:
+            raise GitB200Error("decode_reorder: beam_idx must have one entry per decode row")
         check(self.lib.gitb200_decode_reorder(self.h, _ptr(idx), pos, self._stream()), self.h, "gitb200_decode_reorder")
 
     # ---- streaming window (real_time_inference.py:38-61)
@@ -264,6 +285,7 @@ class Engine:
         c = sp.to_c()
         check(self.lib.gitb200_stream_caption(self.h, ctypes.byref(c), _ptr(tokens), _ptr(logprobs), self._stream()), self.h,
               "gitb200_stream_caption")
+        self._cur_clips, self._cur_nv, self._step_rows = 1, int(self.lib.gitb200_stream_frames(self.h)) * self.T, 0
         return tokens.clone(), logprobs.clone()
 
     def set_fold_layernorm(self, enable: bool) -> None:
@@ -273,6 +295,17 @@ class Engine:
     def set_sweep_rows(self, rows: int) -> None:
         """Token rows per sub-batch of the ViT / visual-pass sweeps of a large batch (0 = one sweep; results are identical)."""
         check(self.lib.gitb200_set_sweep_rows(self.h, rows), self.h, "gitb200_set_sweep_rows")
+
+    def set_early_exit(self, every_steps: int) -> None:
+        """Poll the device's finished-clip count every N decode steps and stop early (`if all(done): break`, model.py:640);
+        0 = never (fully asynchronous decode)."""
+        check(self.lib.gitb200_set_early_exit(self.h, every_steps), self.h, "gitb200_set_early_exit")
+
+    def last_decode_steps(self) -> int:
+        return int(self.lib.gitb200_last_decode_steps(self.h))
+
+    def set_graph_max_clips(self, max_clips: int) -> None:
+        check(self.lib.gitb200_set_graph_max_clips(self.h, max_clips), self.h, "gitb200_set_graph_max_clips")
 
     def set_pipeline(self, chunk_clips: int) -> None:
         """Clips per chunk of the two-stream encode/decode pipeline (0 = off, -1 = automatic)."""

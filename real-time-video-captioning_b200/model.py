@@ -267,7 +267,10 @@ class GeneratorWithBeamSearchV2:
                             reorder_cache)
 
     def search(self, input_ids, step: Callable, num_keep_best=1, do_sample=False, top_k=None, top_p=None,
-               num_return_sequences=1):
+               num_return_sequences=1, on_reorder: Optional[Callable] = None):
+        """``on_reorder(beam_idx, pos)`` (not in the reference, whose cache re-ordering is commented out at
+        model.py:623-634) is called after every step with the parents chosen for the next rows and the text position
+        just decoded, so that a K/V cache behind ``step`` can follow the beams (``cache_reorder='correct'``)."""
         if num_return_sequences != 1:
             input_ids = input_ids[:, None, :].expand(input_ids.shape[0], num_return_sequences, input_ids.shape[1])
             input_ids = input_ids.reshape(-1, input_ids.shape[-1])
@@ -323,6 +326,8 @@ class GeneratorWithBeamSearchV2:
             beam_words = input_ids.new_tensor([x[1] for x in nxt])
             beam_idx = input_ids.new_tensor([x[2] for x in nxt])
             input_ids = torch.cat([input_ids[beam_idx, :], beam_words.unsqueeze(1)], dim=-1)
+            if on_reorder is not None:
+                on_reorder(beam_idx, cur_len - 1)
             cur_len += 1
             if all(done):
                 break
@@ -369,6 +374,7 @@ class GenerativeImageTextModel(nn.Module):
         self._vf_token = None          # visual-feature tensor currently resident in the engine
         self._step_pos = 0
         self.cache_reorder = "reference"  # or "correct" 
+        self._force_host_search = False   # tests: take the generic host `search` loop even where the fused one applies
 
     # ---- engine plumbing
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -499,6 +505,8 @@ class GenerativeImageTextModel(nn.Module):
             if self._vf_token is not visual_features:
                 eng.set_visual_features(visual_features.to(eng.device))
                 self._vf_token = visual_features
+            if rows % B != 0:
+                raise ValueError(f"decoding_step: {rows} caption rows for {B} clips")
             eng.decode_begin(rows // B)
             for p in range(partial_captions.shape[1] - 1):  # prefix tokens fill the cache
                 eng.decode_step(partial_captions[:, p], p)
@@ -513,7 +521,8 @@ class GenerativeImageTextModel(nn.Module):
         eng = self.engine()
         fast = (isinstance(self.decoder, GeneratorWithBeamSearchV2) and "prefix" not in batch
                 and not search_param.get("do_sample", False) and search_param.get("num_return_sequences", 1) == 1
-                and self.decoder.repetition_penalty == 1.0 and visual_features_valid is None)
+                and self.decoder.repetition_penalty == 1.0 and visual_features_valid is None
+                and not self._force_host_search)
         self.prev_encoded_layers = None
         if fast:
             if self._vf_token is not visual_features:
@@ -533,6 +542,9 @@ class GenerativeImageTextModel(nn.Module):
                 start = batch["prefix"].long().to(eng.device)
             step = functools.partial(self.decoding_step, visual_features, visual_features_valid,
                                      batch.get("bi_valid_mask_caption"))
+            if self.cache_reorder == "correct" and isinstance(self.decoder, GeneratorWithBeamSearchV2):
+                # the K/V cache follows the beams exactly like the fused device search does under the same setting
+                search_param = dict(search_param, on_reorder=lambda beam_idx, pos: eng.decode_reorder(beam_idx, pos))
             predicted, logprobs, logits_dict = self.decoder.search(start, step, **search_param)
             if "prefix" in batch:
                 predicted = predicted[:, start.shape[1]:]
@@ -593,13 +605,26 @@ class GenerativeImageTextTeacher(nn.Module):
         self.model = get_git_model(self.tokenizer, self.param)
         if pretrained_weights is not None:
             ckpt = torch.load(pretrained_weights, map_location="cpu")["model"]      # model.py:736-737
-            self.model.load_state_dict(ckpt, strict=False)                           # upstream loader is tolerant
+            self._load_checked(ckpt)
         elif state_dict is not None:
-            self.model.load_state_dict(state_dict, strict=False)
+            self._load_checked(state_dict)
         for p in self.model.parameters():                                            # model.py:741-742
             p.requires_grad = False
         self.model.eval()                                                            # model.py:745
         self.model.to(device)
+
+    def _load_checked(self, sd) -> None:
+        """The upstream loader (model.py:738) is tolerant; a silently half-loaded teacher would caption garbage, so every
+        parameter of the path must be present (``image_encoder.proj`` and a tied ``textual.output.weight`` are the only
+        benign differences, both handled by the model's load_state_dict) and unknown keys are reported."""
+        res = self.model.load_state_dict(sd, strict=False)
+        if res.missing_keys:
+            raise KeyError(f"checkpoint lacks {len(res.missing_keys)} parameter(s) of the GIT path, e.g. {res.missing_keys[:5]}: "
+                           "they would stay at their random initialisation")
+        if res.unexpected_keys:
+            import warnings
+            warnings.warn(f"checkpoint holds {len(res.unexpected_keys)} key(s) the GIT path does not use, e.g. "
+                          f"{res.unexpected_keys[:5]}")
 
     @classmethod
     def from_random_init(cls, param: dict, state_dict=None, device="cuda", tokenizer=None):
@@ -615,6 +640,7 @@ class GenerativeImageTextTeacher(nn.Module):
         frames = x.to(eng.device).float()
         layers, taps = m._arm_vit_taps(eng, frames.shape[0], frames.shape[1])
         logits, vf, hidden = eng.forward_logits(frames, y, want_hidden=True, want_features=True)
+        m._vf_token = None  # the engine now holds these clips' features, not the tensor a previous infer() was given
         m._fire_vit_hooks(eng, layers, taps)
         m._fire_decoder_hooks(hidden)
         n = frames.shape[0]
@@ -623,26 +649,37 @@ class GenerativeImageTextTeacher(nn.Module):
     @torch.no_grad()
     def forward(self, x):
         """model.py:762-793: one result dict per clip with predictions / logprobs / logits_dict / visual_features /
-        output / cap."""
+        output / cap.  The reference's per-clip post-processing (:771-789) runs batched: ONE device->host copy of the
+        token matrix, one gather + argmax + gather over all clips and steps; the per-clip entries are views."""
         m = self.model
         eng = m.engine()
-        frames = x.to(eng.device).float()
+        frames = x.to(eng.device, non_blocking=True).float()
         n = frames.shape[0]
         nb = m.decoder.beam_size
         res = m({"image": [frames[:, f] for f in range(frames.shape[1])]})
-        all_logits = res["logits_dict"].device_tensor()                   # [steps, n*nb, V]
+        ld = res["logits_dict"]
+        all_logits = ld.device_tensor()                                   # [steps, n*nb, V] (view of the padded buffer)
+        steps, V = all_logits.shape[0], all_logits.shape[-1]
+        pred = res["predictions"]                                         # [n, max_steps] int64 on the device
+        pred_host = pred.cpu()                                            # the only synchronising copy of the call
+        caps = [self.tokenizer.decode(row, skip_special_tokens=True) for row in pred_host.tolist()]          # :771
+        ks = [min(len(c.split(" ")), steps) for c in caps]                                                   # :772
+        K = max(ks) if ks else 0
+        # [n, K, nb, V]: distribution of every beam row for each of the first K predicted words of every clip       # :776
+        dist = all_logits[:K].view(K, n, nb, V).permute(1, 0, 2, 3)
+        words = pred[:, 1:K + 1]                                                                              # :780
+        if words.shape[1] < K:  # max_steps - 1 scored steps, max_steps - 1 words after SOS: cannot happen; guard anyway
+            K = words.shape[1]
+            dist = dist[:, :K]
+        at_word = torch.gather(dist, 3, words[:, :, None, None].expand(n, K, nb, 1)).squeeze(3)              # [n, K, nb]
+        idx = at_word.argmax(dim=2)                                                                           # :784
+        picked = torch.gather(dist, 2, idx[:, :, None, None].expand(n, K, 1, V)).squeeze(2)                  # :787  [n, K, V]
+        dev_logits = ld._dev.view(steps, n, nb, -1)
         out = []
         for i in range(n):
-            pred = res["predictions"][i:i + 1]
-            cap = self.tokenizer.decode(pred[0].tolist(), skip_special_tokens=True)                # :771
-            k = min(len(cap.split(" ")), all_logits.shape[0])                                       # :772
-            dist = all_logits[:k, i * nb:(i + 1) * nb]                                              # :776  [k, nb, V]
-            words = pred[0, 1:k + 1].to(dist.device)                                                # :780
-            idx = torch.gather(dist, 2, words[:, None, None].expand(-1, nb, -1)).squeeze(-1).argmax(dim=1)   # :784
-            picked = torch.gather(dist, 1, idx[:, None, None].expand(-1, -1, dist.shape[-1])).squeeze(1)[None]  # :787
-            out.append({"predictions": pred, "logprobs": res["logprobs"][i:i + 1],
-                        "logits_dict": LazyLogits(res["logits_dict"]._dev[:, i * nb:(i + 1) * nb], eng.cfg.vocab),
-                        "visual_features": res["visual_features"][i:i + 1], "output": picked, "cap": cap})
+            out.append({"predictions": pred[i:i + 1], "logprobs": res["logprobs"][i:i + 1],
+                        "logits_dict": LazyLogits(dev_logits[:, i], eng.cfg.vocab),
+                        "visual_features": res["visual_features"][i:i + 1], "output": picked[i:i + 1, :ks[i]], "cap": caps[i]})
         return out
 
     # ---- the generate facade the reference's scripts call on their model (inference.py:51, real_time_inference.py:58)
@@ -704,6 +741,7 @@ class StreamingCaptioner:
             self._raw = torch.empty(key, dtype=torch.uint8, device=self.engine.device)
             self._raw_key = key
         self._raw.copy_(frame_bgr_u8, non_blocking=True)
+        self.teacher.model._vf_token = None  # the window's features replace whatever an earlier infer() left resident
         held = self.engine.stream_push_u8(self._raw)
         if held < self.window:
             return None
