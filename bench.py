@@ -13,6 +13,12 @@ the reference's search defaults with beam 1) and the device-side search.  Worklo
 Timing: W warm-up steps, then K steps bracketed by barrier + cuda synchronize, timed with CUDA events on the launching
 stream, max over ranks.  Each step reads a different resident batch of frames and streams > 4 GB of activations, far
 beyond the 126 MB L2, so no explicit L2 flush is needed between iterations (config.l2 states this).
+
+N > 1: every rank captions its own shard through the product's dist.caption_sharded; the token gather (the path's only
+collective) is enqueued asynchronously behind each step and all gathers are waited for once, inside the timed region.
+
+Besides the headline workload the default run times short legs of the other BASELINE.json configurations (key
+"configs": beam 4 / max 20, GIT-large 6- and 24-frame) and the drop-in GenerativeImageTextTeacher.forward end to end.
 """
 from __future__ import annotations
 
@@ -138,6 +144,143 @@ def emit(line: dict) -> None:
         os.write(_JSON_FD, data)
 
 
+def pin_rank_to_cores(local_rank: int, world: int):
+    """Give every rank of a node its own slice of the host cores (launch threads, pinned-copy staging and the Python
+    post-processing of eight ranks otherwise share whatever cores the scheduler picks)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(world, 1)
+        if world > 1 and per >= 2:
+            mine = cores[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return len(mine)
+        return len(cores)
+    except Exception:
+        return None
+
+
+def roofline_model_clips_per_s(gflop_per_clip, kv_mb_per_clip, batch, max_steps, tc_tflops, hbm_gbs):
+    """1 / (TC_FLOP / P_tc + (max_steps - 2) cached steps x (W_bytes / batch + KV_bytes) / BW)."""
+    t = gflop_per_clip * 1e9 / (tc_tflops * 1e12) + (max_steps - 2) * (131.8e6 / batch + kv_mb_per_clip * 1e6) / (hbm_gbs * 1e9)
+    return 1.0 / t
+
+
+def build_engine(g, gm, torch, param, local_rank, seed=0):
+    """Random-init weights through the package's own reference-shaped constructor (get_git_model, model.py:681-718); biases,
+    LayerNorm affines and temporal embeddings (zeros upstream) randomised so that no term of the path is trivially zero."""
+    tok = gm.SyntheticTokenizer()
+    torch.manual_seed(seed)
+    model = gm.get_git_model(tok, param)
+    gen_w = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p_ in model.named_parameters():
+            if name.endswith("bias") or "img_temperal_embedding" in name:
+                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.02)
+            elif p_.dim() == 1 and name.endswith("weight"):  # LayerNorm gains
+                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.1)
+    eng = g.Engine(g.make_config(param, tok.cls_token_id, tok.sep_token_id), local_rank)
+    eng.load_state_dict(model.state_dict())
+    return eng, model
+
+
+def timed_leg(torch, dist, eng, frames_sets, sp, steps, warmup, world, dev, caption_sharded):
+    """K steps of eng.caption over resident frame batches (+ the asynchronous token gather when world > 1): ms total,
+    max over ranks."""
+    B = frames_sets[0].shape[0]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        fr = frames_sets[i % len(frames_sets)]
+        return caption_sharded(lambda b, e: eng.caption(fr, sp)[:2], world * B, async_op=True, tail=(sp.num_keep_best, sp.max_steps))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for h in [step(i) for i in range(warmup)]:
+        h.wait()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    handles = [step(i) for i in range(steps)]
+    for h in handles:
+        h.wait()
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item(), handles
+
+
+def config_leg(g, gm, torch, dist, name, param, B, frames_n, sp, steps, warmup, world, rank, local_rank, dev, gflop, kv_mb, peaks):
+    """One short leg of another BASELINE.json configuration on its own engine."""
+    eng, model = build_engine(g, gm, torch, param, local_rank)
+    del model
+    eng.reserve(B, frames_n, sp.beam_size, sp.max_steps)
+    gen = torch.Generator(device=dev).manual_seed(300 + rank)
+    sets = [torch.randn(B, frames_n, 3, RES, RES, device=dev, generator=gen) for _ in range(2)]
+    caption_sharded = importlib.import_module("real-time-video-captioning_b200.dist").caption_sharded
+    ms, _ = timed_leg(torch, dist, eng, sets, sp, steps, warmup, world, dev, caption_sharded)
+    out = {"clips_per_gpu_per_step": B, "frames": frames_n, "beam_size": sp.beam_size, "max_steps": sp.max_steps, "steps": steps,
+           "warmup": warmup, "ms_per_step": ms / steps, "value": world * B * steps / (ms * 1e-3), "unit": UNIT,
+           "algorithmic_gflop_per_clip": gflop, "path_tflops_algorithmic": gflop * 1e9 * B * steps / (ms * 1e-3) / 1e12}
+    sustained, burst, hbm, _ = peaks
+    out["path_frac"] = out["path_tflops_algorithmic"] / sustained
+    out["model_frac"] = (B * steps / (ms * 1e-3)) / roofline_model_clips_per_s(gflop, kv_mb, B, sp.max_steps, sustained, hbm)
+    if name.startswith("large") and sp.max_steps > 2:
+        # BASELINE.json configs[3] is an encode-heavy PREFILL sweep: encode + projection + the first decode step only
+        sp2 = g.SearchConfig(beam_size=1, max_steps=2, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
+        ms2, _ = timed_leg(torch, dist, eng, sets, sp2, steps, 1, world, dev, caption_sharded)
+        out["prefill_only"] = {"max_steps": 2, "ms_per_step": ms2 / steps, "value": world * B * steps / (ms2 * 1e-3), "unit": UNIT,
+                               "path_tflops_algorithmic": gflop * 1e9 * B * steps / (ms2 * 1e-3) / 1e12}
+    del sets
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=2):
+    """The drop-in itself: GenerativeImageTextTeacher.forward(x) (model.py:762-793) on a pinned HOST batch -- encode, beam-4 /
+    max_steps-15 search (the reference's own settings, model.py:702-708), saved logits, per-clip result dicts with `output`
+    and `cap` -- timed end to end by the wall clock, beside Engine.caption_host with the same search settings."""
+    teacher = gm.GenerativeImageTextTeacher.from_random_init(param, device=dev)
+    eng = teacher.model.engine()
+    d = teacher.model.decoder
+    sp = g.SearchConfig(beam_size=d.beam_size, max_steps=d.max_steps, length_penalty=d.length_penalty,
+                        per_node_beam_size=d.per_node_beam_size, num_keep_best=1)
+    eng.reserve(B, FRAMES, sp.beam_size, sp.max_steps)
+    x = torch.randn(B, FRAMES, 3, RES, RES, generator=torch.Generator().manual_seed(70 + rank)).pin_memory()
+
+    def wall(fn):
+        fn()  # warm-up
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), r
+
+    t_teacher, res = wall(lambda: teacher(x))
+    t_engine, _ = wall(lambda: eng.caption_host(x, sp, chunk_clips=64))
+    out = {"api": "GenerativeImageTextTeacher.forward(x): pinned host frames -> list of per-clip dicts (predictions, logprobs, logits_dict, visual_features, output, cap)",
+           "clips_per_gpu_per_step": B, "beam_size": sp.beam_size, "max_steps": sp.max_steps, "steps": steps,
+           "value": world * B * steps / t_teacher, "unit": UNIT, "h2d_bytes_per_step": x.numel() * 4,
+           "d2h_bytes_per_step": B * sp.max_steps * 8,
+           "engine_caption_host_same_search": world * B * steps / t_engine,
+           "teacher_over_engine": t_engine / t_teacher, "result_clips": len(res), "result_keys": sorted(res[0].keys())}
+    del teacher, x, res
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +299,9 @@ def main():
     ap.add_argument("--fold-ln", action="store_true", help="opt-in: ViT LayerNorms folded into the QKV / fc1 GEMM epilogues (DESIGN.md dead ends)")
     ap.add_argument("--sweep-rows", type=int, default=-1, help="token rows per ViT / visual-pass sub-batch (-1: library default 151296 = 128 clips; 0: one sweep)")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
+    ap.add_argument("--no-config-legs", action="store_true", help="skip the short legs of the other BASELINE.json configurations and the teacher-forward leg")
+    ap.add_argument("--early-exit", type=int, default=-1, help="poll the device's finished-clip count every N decode steps (-1: library default 4; 0: never)")
+    ap.add_argument("--graph", action="store_true", help="A/B: capture the whole batch step into a CUDA graph and replay it (one frame set, no early-exit polling)")
     args = ap.parse_args()
     claim_stdout()
 
@@ -194,29 +340,20 @@ def main():
     import torch.distributed as dist
 
     g = importlib.import_module("real-time-video-captioning_b200")
+    gm = importlib.import_module("real-time-video-captioning_b200.model")
+    caption_sharded = importlib.import_module("real-time-video-captioning_b200.dist").caption_sharded
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gitb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    cores_mine = pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    config["host_cores_per_rank"] = cores_mine
+    config["token_gather"] = "one packed all_gather_into_tensor per step, enqueued asynchronously (dist.caption_sharded), all waited for at the end of the timed region" if world > 1 else "none (1 rank)"
 
-    # identical random-init weights on every rank (same seed), built through the package's own reference-shaped
-    # constructor (get_git_model, model.py:681-718); nothing under oracle/ is touched by this arm.  Biases, LayerNorm
-    # affines and the temporal embeddings (zeros upstream) are randomised too so that no term of the path is trivially zero.
-    gm = importlib.import_module("real-time-video-captioning_b200.model")
-    tok = gm.SyntheticTokenizer()
-    torch.manual_seed(0)
-    model = gm.get_git_model(tok, param)
-    gen_w = torch.Generator().manual_seed(1)
-    with torch.no_grad():
-        for name, p_ in model.named_parameters():
-            if name.endswith("bias") or "img_temperal_embedding" in name:
-                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.02)
-            elif p_.dim() == 1 and name.endswith("weight"):  # LayerNorm gains
-                p_.add_(torch.randn(p_.shape, generator=gen_w) * 0.1)
-    eng = g.Engine(g.make_config(param, tok.cls_token_id, tok.sep_token_id), local_rank)
-    eng.load_state_dict(model.state_dict())
+    # identical random-init weights on every rank (same seed); nothing under oracle/ is touched by this arm
+    eng, model = build_engine(g, gm, torch, param, local_rank)
     del model
     sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
     B = args.batch
@@ -225,40 +362,67 @@ def main():
         eng.set_sweep_rows(args.sweep_rows)
     if args.fold_ln:
         eng.set_fold_layernorm(True)
+    if args.early_exit >= 0:
+        eng.set_early_exit(args.early_exit)
     if args.pipeline == 0:
         eng.reserve(B, FRAMES, args.beam, args.max_steps)
+    if args.graph:
+        eng.set_graph_max_clips(B)
+        eng.set_early_exit(0)  # a captured step cannot poll the host
+        torch.cuda.set_stream(torch.cuda.Stream(dev))  # graphs need a capturable (non-default) stream
+    config["cuda_graph_step"] = bool(args.graph)
 
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    n_sets = 2  # alternate between resident frame batches
+    n_sets = 2 if not args.graph else 1  # a graph replays one set of buffers
     frames = [torch.randn(B, FRAMES, 3, RES, RES, device=dev, generator=gen) for _ in range(n_sets)]
     stream = torch.cuda.current_stream(dev)
+    out_bufs = None
+    if args.graph:  # persistent output buffers: identical call signatures replay the captured graph
+        import ctypes as _c
+        out_bufs = (torch.empty(B, 1, args.max_steps, dtype=torch.int32, device=dev), torch.empty(B, 1, dtype=torch.float32, device=dev))
+        csp_g = sp.to_c()
+
+    def caption_local(i):
+        if out_bufs is None:
+            return eng.caption(frames[i % n_sets], sp)[:2]
+        rc = eng.lib.gitb200_caption(eng.h, _c.c_void_p(frames[0].data_ptr()), B, FRAMES, _c.byref(csp_g), _c.c_void_p(out_bufs[0].data_ptr()),
+                                     _c.c_void_p(out_bufs[1].data_ptr()), None, _c.c_void_p(stream.cuda_stream))
+        assert rc == 0, eng.lib.gitb200_last_error(eng.h)
+        return out_bufs
 
     def step(i):
-        tok, lp, _ = eng.caption(frames[i % n_sets], sp)
-        if world > 1:  # C2: gather the caption tokens of all ranks (the path's only collective)
-            out = [torch.empty_like(tok) for _ in range(world)]
-            dist.all_gather(out, tok)
-        return tok
+        # C2: the caption tokens of all ranks are gathered (the path's only collective) -- asynchronously, one packed buffer
+        return caption_sharded(lambda b, e: caption_local(i), world * B, async_op=True, tail=(1, args.max_steps))
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    eng.launch_count(reset=True)
+    per_step_launches = 0
     for i in range(args.warmup):
-        step(i)
+        step(i).wait()
+        if i == 0:
+            per_step_launches = eng.launch_count()  # an eager step: what a graph replay re-issues without passing the counter
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     eng.launch_count(reset=True)
-    eng.lib.gitb200_profile_gemm(1)
+    graph0 = int(eng.lib.gitb200_graph_launches(eng.h))
+    if not args.graph:
+        eng.lib.gitb200_profile_gemm(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
-        step(i)
+    handles = [step(i) for i in range(args.steps)]
+    for h in handles:
+        h.wait()
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count()
+    graph_step_replays = int(eng.lib.gitb200_graph_launches(eng.h)) - graph0
+    if args.graph and graph_step_replays > 0:  # a replay re-issues the captured launches without passing the library's counter
+        launches += graph_step_replays * per_step_launches
     import ctypes
     g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     eng.lib.gitb200_profile_gemm_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n))
@@ -271,98 +435,121 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     value = world * B * args.steps / (ms * 1e-3)
+    # the gathered matrix must hold this rank's own result at this rank's shard (clip order preserved)
+    gathered_ok = None
+    if world > 1:
+        all_tok, all_lp = handles[-1].wait()
+        mine_tok, _ = caption_local(args.steps - 1)
+        gathered_ok = bool(all_tok.shape[0] == world * B and torch.equal(all_tok[rank * B:(rank + 1) * B], mine_tok.to(torch.int32)))
+        assert gathered_ok, "gathered tokens differ from the local shard"
 
     if args.quick:
         if rank == 0:
             emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                  "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True,
+                  "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "graph_step_replays": graph_step_replays,
                   "gemm_ms": g_ms.value, "gemm_tflops": g_fl.value / max(g_ms.value, 1e-9) / 1e9})
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- e2e: same metric through the public host-buffer API (pinned host frames in, host tokens out)
-    host_frames = torch.randn(B, FRAMES, 3, RES, RES, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
-    eng.caption_host(host_frames, sp, chunk_clips=args.chunk)  # warm-up (allocates staging buffers)
-    sync_all()
-    e2e_steps = max(2, min(args.steps, 6))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        tok_h, lp_h = eng.caption_host(host_frames, sp, chunk_clips=args.chunk)  # synchronous
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / t.item()
-    h2d = host_frames.numel() * 4
-    d2h = tok_h.numel() * 4 + lp_h.numel() * 4
-    del host_frames
+    def wall_leg(fn, n):
+        fn()  # warm-up (allocates staging buffers)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            r = fn()
+        sync_all()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * n / t.item(), r
 
-    # ---- the same from RAW video frames (uint8 BGR 240x320, MSR-VTT's frame size): bytes over PCIe, image_transform() on the GPU
+    e2e_steps = max(2, min(args.steps, 6))
+    # ---- e2e: the same metric through the public host-buffer API, from RAW video frames (uint8 BGR 240x320, MSR-VTT's frame
+    # size, what cv2.VideoCapture delivers: dataloader.py:61-75): bytes over PCIe, image_transform() on the GPU, host tokens out
     raw_frames = torch.randint(0, 256, (B, FRAMES, 240, 320, 3), dtype=torch.uint8,
                                generator=torch.Generator().manual_seed(17 + rank)).pin_memory()
-    eng.caption_host_u8(raw_frames, sp, chunk_clips=args.chunk)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.caption_host_u8(raw_frames, sp, chunk_clips=args.chunk)
-    sync_all()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_raw = {"value": world * B * e2e_steps / t.item(), "unit": UNIT, "h2d_bytes_per_step": raw_frames.numel(),
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "Engine.caption_host_u8 (gitb200_caption_host_u8): pinned host uint8 BGR 240x320 frames -> GPU image_transform -> host tokens"}
+    e2e_value, (tok_h, lp_h) = wall_leg(lambda: eng.caption_host_u8(raw_frames, sp, chunk_clips=args.chunk), e2e_steps)
+    d2h = tok_h.numel() * 4 + lp_h.numel() * 4
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": raw_frames.numel(), "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "Engine.caption_host_u8 (gitb200_caption_host_u8): pinned host uint8 BGR 240x320 frames -> GPU image_transform -> host tokens"}
     del raw_frames
+    # ---- the same from frames the host has already preprocessed (fp32 224x224: 4x the bytes over PCIe)
+    host_frames = torch.randn(B, FRAMES, 3, RES, RES, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+    e2e_f32_value, _ = wall_leg(lambda: eng.caption_host(host_frames, sp, chunk_clips=args.chunk), e2e_steps)
+    e2e_f32 = {"value": e2e_f32_value, "unit": UNIT, "h2d_bytes_per_step": host_frames.numel() * 4, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "api": "Engine.caption_host (gitb200_caption_host): pinned host fp32 frames -> host tokens"}
+    del host_frames
+
+    # ---- single-clip latency (p50) on rank 0: same buffers every call on a side stream, as a real-time caller would
+    # do (the library replays a CUDA graph of the ~850 launches from the third identical call on)
+    p50 = p50_stream = graph_replays = None
+    if rank == 0:
+        one = frames[0][:1].contiguous()
+        lat = []
+        side = torch.cuda.Stream(dev)
+        import ctypes as _ct
+        tok1 = torch.empty(1, 1, args.max_steps, dtype=torch.int32, device=dev)
+        lp1 = torch.empty(1, 1, dtype=torch.float32, device=dev)
+        csp = sp.to_c()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(side):
+            for i in range(30):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(side)
+                rc = eng.lib.gitb200_caption(eng.h, _ct.c_void_p(one.data_ptr()), 1, FRAMES, _ct.byref(csp), _ct.c_void_p(tok1.data_ptr()),
+                                             _ct.c_void_p(lp1.data_ptr()), None, _ct.c_void_p(side.cuda_stream))
+                assert rc == 0, eng.lib.gitb200_last_error(eng.h)
+                b.record(side)
+                b.synchronize()
+                if i >= 8:
+                    lat.append(a.elapsed_time(b))
+        p50 = statistics.median(lat)
+        graph_replays = int(eng.lib.gitb200_graph_launches(eng.h))
+        # streaming caller (real_time_inference.py loop): the 6-frame window is already encoded frame by frame; what stands
+        # between a new frame and its caption is ONE frame's ViT + the decoder
+        lat_s = []
+        with torch.cuda.stream(side):
+            eng.stream_reset()
+            for f in range(FRAMES):
+                eng.stream_push(one[0, f])
+            for i in range(40):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(side)
+                eng.stream_push(one[0, i % FRAMES])
+                eng.stream_caption(sp)
+                b.record(side)
+                b.synchronize()
+                if i >= 18:  # every (frame slot, window start) signature has been captured by then
+                    lat_s.append(a.elapsed_time(b))
+        p50_stream = statistics.median(lat_s)
+    del frames
+    eng.close()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations (short legs, every rank) and the drop-in teacher wrapper
+    peaks = measured_peaks()
+    sustained, burst, hbm, src = peaks
+    legs = {}
+    if not args.no_config_legs and args.model == "base" and FRAMES == 6:
+        base_param = {"num_image_with_embedding": 6}
+        large6 = {"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024, "num_image_with_embedding": 6}
+        large24 = {"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024, "num_image_with_embedding": 24}
+        greedy = g.SearchConfig(beam_size=1, max_steps=15, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
+        beam4 = g.SearchConfig(beam_size=4, max_steps=20, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
+        legs["beam4_max20"] = dict(config_leg(g, gm, torch, dist, "beam4_max20", base_param, 256, 6, beam4, 3, 2, world, rank, local_rank, dev,
+                                              338.42, 21.8, peaks), workload="BASELINE.json configs[2]: GIT-base beam 4 / max 20 tokens, visual K/V shared by a clip's beams, clip-sharded")
+        legs["large_f6"] = dict(config_leg(g, gm, torch, dist, "large_f6", large6, 128, 6, greedy, 3, 2, world, rank, local_rank, dev,
+                                           1149.51, 28.4, peaks), workload="GIT-large (ViT-L/14) 6-frame clips: the shipped teacher config (parameter.yaml), greedy max 15")
+        legs["large_f24"] = dict(config_leg(g, gm, torch, dist, "large_f24", large24, 32, 24, greedy, 3, 2, world, rank, local_rank, dev,
+                                            5123.70, 113.7, peaks), workload="BASELINE.json configs[3]: GIT-large (ViT-L/14) 24-frame clips, greedy max 15 + prefill-only sweep")
+        legs["e2e_teacher_forward"] = teacher_forward_leg(g, gm, torch, dist, base_param, 256, world, rank, dev)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- single-clip latency (p50) on rank 0: same buffers every call on a side stream, as a real-time caller would
-    # do (the library replays a CUDA graph of the ~850 launches from the third identical call on)
-    one = frames[0][:1].contiguous()
-    lat = []
-    side = torch.cuda.Stream(dev)
-    import ctypes as _ct
-    tok1 = torch.empty(1, 1, args.max_steps, dtype=torch.int32, device=dev)
-    lp1 = torch.empty(1, 1, dtype=torch.float32, device=dev)
-    csp = sp.to_c()
-    torch.cuda.synchronize(dev)
-    with torch.cuda.stream(side):
-        for i in range(30):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(side)
-            rc = eng.lib.gitb200_caption(eng.h, _ct.c_void_p(one.data_ptr()), 1, FRAMES, _ct.byref(csp), _ct.c_void_p(tok1.data_ptr()),
-                                         _ct.c_void_p(lp1.data_ptr()), None, _ct.c_void_p(side.cuda_stream))
-            assert rc == 0, eng.lib.gitb200_last_error(eng.h)
-            b.record(side)
-            b.synchronize()
-            if i >= 8:
-                lat.append(a.elapsed_time(b))
-    p50 = statistics.median(lat)
-    graph_replays = int(eng.lib.gitb200_graph_launches(eng.h))
-    # streaming caller (real_time_inference.py loop): the 6-frame window is already encoded frame by frame; what stands
-    # between a new frame and its caption is ONE frame's ViT + the decoder
-    lat_s = []
-    with torch.cuda.stream(side):
-        eng.stream_reset()
-        for f in range(FRAMES):
-            eng.stream_push(one[0, f])
-        for i in range(40):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(side)
-            eng.stream_push(one[0, i % FRAMES])
-            eng.stream_caption(sp)
-            b.record(side)
-            b.synchronize()
-            if i >= 18:  # every (frame slot, window start) signature has been captured by then
-                lat_s.append(a.elapsed_time(b))
-    p50_stream = statistics.median(lat_s)
-
-    sustained, burst, hbm, src = measured_peaks()
     gemm_tflops = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
@@ -370,14 +557,21 @@ def main():
             traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
     except Exception:
         pass
+    path_tflops = GFLOP_PER_CLIP * 1e9 * B * args.steps / (ms * 1e-3) / 1e12
+    kv_mb = {("base", 6): 21.8, ("large", 6): 28.4, ("large", 24): 113.7}.get((args.model, FRAMES), float("nan"))
+    model_clips = roofline_model_clips_per_s(GFLOP_PER_CLIP, kv_mb, B, args.max_steps, sustained, hbm)
     roofline = {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05) + gemm_tcgen05_kernel<128> (decode rows)",
                 "achieved": gemm_tflops, "peak": sustained,
                 "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
                 "traffic_note": "avg DRAM read+write bytes per launch of the 4 ViT-layer GEMMs at M=151296 (one 128-clip sub-batch of the 512-clip step; algorithmic average 1.049 GB; profiles/r01_gemm2_traffic.json)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / (ms if world == 1 else ms) if ms > 0 else None,
+                "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / ms if ms > 0 else None,
                 "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
-                "path_tflops_algorithmic": GFLOP_PER_CLIP * 1e9 * B * args.steps / (ms * 1e-3) / 1e12}
+                "path_tflops_algorithmic": path_tflops,
+                # whole path against the tensor peak alone, and against BASELINE.md section 3's tensor + HBM model
+                "path_frac": path_tflops / sustained,
+                "model_clips_per_s_per_gpu": model_clips,
+                "model_frac": (B * args.steps / (ms * 1e-3)) / model_clips}
 
     # second roofline: the HBM-bound kernel of the path (decode-step attention over the visual + text K/V cache)
     dec_gbs = (a_by.value / (a_ms.value * 1e-3) / 1e9) if a_ms.value > 0 else None
@@ -404,11 +598,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "Engine.caption_host (gitb200_caption_host): pinned host frames -> host tokens"},
-            "e2e_raw_frames": e2e_raw,
+            "e2e": e2e, "e2e_fp32_frames": e2e_f32, "gathered_tokens_match_local_shard": gathered_ok,
             "roofline": roofline, "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
-            "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream}
+            "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream,
+            "configs": legs}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

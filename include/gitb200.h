@@ -147,6 +147,14 @@ int gitb200_set_pipeline(gitb200_ctx* ctx, int chunk_clips);
  * logprobs are copied back; returns after everything has completed (synchronous). */
 int gitb200_caption_host(gitb200_ctx* ctx, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
                          const gitb200_search_params* sp, int32_t* tokens_host, float* logprobs_host);
+/* Host frames in, DEVICE results out -- what GenerativeImageTextModel.forward returns for a batch handed over on the host
+ * (model.py:768-780: predictions, logprobs, the per-step logits of logits_dict, visual_features).  Same chunked,
+ * copy-overlapped encode as gitb200_caption_host; logits_dev (fp32 [max_steps-1, n_clips*beam, logits_ld]) and
+ * visual_features_dev (fp32 [n_clips, F*T, vit_width]) are optional.  Asynchronous: the work runs on the context's own
+ * streams and `stream` is made to wait for the results; frames_host must stay valid until then. */
+int gitb200_caption_from_host(gitb200_ctx* ctx, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
+                              const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
+                              float* visual_features_dev, void* stream);
 
 /* ---- teacher-forced logits: forward_one_custom, model.py:371-424 ------------------------------
  * tokens_dev: int32 [n_clips, L].  If frames_dev == NULL the current visual features are used.

@@ -100,7 +100,7 @@ struct gitb200_ctx {
   Buf<int> out_tok;
   Buf<float> out_lp;
   cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
-  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_user = nullptr;
 
   // CUDA graphs for the launch-bound small-batch calls (latency mode): a call signature is captured on its second
   // occurrence and replayed afterwards.  kind: 0 caption, 1 stream_push, 2 stream_caption.
@@ -971,6 +971,7 @@ void gitb200_destroy(gitb200_ctx* c) {
   for (auto& g : c->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->ev_user) cudaEventDestroy(c->ev_user);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
   for (int i = 0; i < 2; ++i) {
@@ -1432,6 +1433,55 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
   CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaStreamSynchronize(comp));
+  return GITB200_OK;
+}
+
+// Host frames in, DEVICE results out: the chunked, copy-overlapped encode of gitb200_caption_host, then one decode whose
+// tokens / log-probabilities / per-step logits / visual features stay on the device (what GenerativeImageTextModel.forward
+// returns, model.py:768-780).  Work runs on the context's private streams; `stream` (the caller's) waits for the results.
+int gitb200_caption_from_host(gitb200_ctx* c, const float* frames_host, int n_clips, int n_frames, int chunk_clips,
+                              const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, float* logits_dev,
+                              float* vf_dev, void* stream) {
+  if (!c || !frames_host || !sp || !tokens_dev || !logprobs_dev || n_clips < 1 || n_frames < 1)
+    return fail(c, GITB200_ERR_INVALID, "bad caption_from_host argument");
+  if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
+  CUDA_OK(c, cudaSetDevice(c->device));
+  if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
+  const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
+  if (!c->copy_stream) {
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  if (!c->ev_user) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+  cudaStream_t comp = c->comp_stream, user = (cudaStream_t)stream;
+  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
+  // the caller's earlier work on its stream (e.g. the allocation of the output tensors) is ordered before ours
+  CUDA_OK(c, cudaEventRecord(c->ev_user, user));
+  CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_user, 0));
+  CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_user, 0));
+  int done = 0, ch = 0;
+  while (done < n_clips) {
+    const int b = ch & 1;
+    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+    if (nc > n_clips - done) nc = n_clips - done;
+    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
+    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
+    TRY(run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips));
+    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+    done += nc;
+    ++ch;
+  }
+  if (vf_dev) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_dev, c->cfg.vit_width, comp));
+  TRY(run_decode(c, *sp, tokens_dev, logprobs_dev, logits_dev, comp));
+  CUDA_OK(c, cudaEventRecord(c->ev_user, comp));
+  CUDA_OK(c, cudaStreamWaitEvent(user, c->ev_user, 0));
   return GITB200_OK;
 }
 

@@ -189,6 +189,32 @@ class Engine:
         self._cur_nv, self._cur_clips, self._step_rows = (min(F, n) if n > 0 else F) * self.T, N, 0
         return tokens, logprobs
 
+    def caption_from_host(self, frames_host: torch.Tensor, sp: SearchConfig, chunk_clips: int = 64, save_logits: bool = False,
+                          want_features: bool = False):
+        """HOST frames fp32 [N, F, 3, R, R] -> DEVICE (tokens, logprobs, logits | None, visual features | None): the host->device
+        copy of chunk i+1 overlaps the ViT of chunk i; nothing is copied back.  Asynchronous on the current stream; the caller
+        must keep ``frames_host`` alive until that stream has caught up (any read of the results does that)."""
+        assert not frames_host.is_cuda and frames_host.dtype == torch.float32 and frames_host.dim() == 5
+        frames_host = frames_host.contiguous()
+        N, F = frames_host.shape[:2]
+        n = self.cfg.num_image_with_embedding
+        nv = (min(F, n) if n > 0 else F) * self.T
+        tokens = torch.empty(N, sp.num_keep_best, sp.max_steps, dtype=torch.int32, device=self.device)
+        logprobs = torch.empty(N, sp.num_keep_best, dtype=torch.float32, device=self.device)
+        logits = torch.empty(sp.max_steps - 1, N * sp.beam_size, self.ld, dtype=torch.float32,
+                             device=self.device) if save_logits else None
+        vf = torch.empty(N, nv, self.cfg.vit_width, dtype=torch.float32, device=self.device) if want_features else None
+        c = sp.to_c()
+        with torch.cuda.device(self.device):
+            check(self.lib.gitb200_caption_from_host(self.h, _ptr(frames_host), N, F, chunk_clips, ctypes.byref(c), _ptr(tokens),
+                                                     _ptr(logprobs), _ptr(logits), _ptr(vf), self._stream()), self.h,
+                  "gitb200_caption_from_host")
+        self._cur_nv, self._cur_clips, self._step_rows = nv, N, 0
+        self._host_frames_in_flight = frames_host  # keeps the source alive while the copies are in flight
+        if logits is not None:
+            logits = logits[: self.last_decode_steps()]
+        return tokens, logprobs, logits, vf
+
     def caption_host_u8(self, frames_host: torch.Tensor, sp: SearchConfig, chunk_clips: int = 32):
         """HOST raw video frames uint8 [N, F, H, W, 3] (OpenCV BGR, pinned recommended) -> HOST tokens, logprobs.
         image_transform() (dataloader.py:18-32) runs on the device between the byte copy and the ViT; synchronous."""

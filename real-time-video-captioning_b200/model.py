@@ -496,6 +496,22 @@ class GenerativeImageTextModel(nn.Module):
             self._vf_token = vf
             return self.infer(batch, vf, None)
 
+    @torch.no_grad()
+    def forward_host_frames(self, frames_host: torch.Tensor, chunk_clips: int = 64):
+        """``forward`` for a batch of clips that still lives on the HOST (fp32 [B, F, 3, R, R]): same result dict, but the
+        frames cross PCIe in chunks whose copies overlap the ViT of the previous chunk (gitb200_caption_from_host)
+        instead of one blocking ``.to(device)`` in front of everything."""
+        if self.training:
+            raise NotImplementedError("the GIT teacher is frozen (model.py:741-745); training forward is out of scope")
+        eng = self.engine()
+        sc = self.decoder.search_config(1, self.cache_reorder == "correct")
+        tokens, logprobs, logits, vf = eng.caption_from_host(frames_host, sc, chunk_clips=chunk_clips, save_logits=True,
+                                                             want_features=True)
+        self.prev_encoded_layers = None
+        self._vf_token = vf
+        return {"predictions": tokens.long().squeeze(1), "logprobs": logprobs, "logits_dict": LazyLogits(logits, eng.cfg.vocab),
+                "visual_features": vf}
+
     def decoding_step(self, visual_features, visual_features_valid, bi_valid_mask_caption, partial_captions):
         """Upstream CaptioningModel.decoding_step with use_history_for_infer: scores of the last position."""
         eng = self.engine()
@@ -653,10 +669,15 @@ class GenerativeImageTextTeacher(nn.Module):
         token matrix, one gather + argmax + gather over all clips and steps; the per-clip entries are views."""
         m = self.model
         eng = m.engine()
-        frames = x.to(eng.device, non_blocking=True).float()
-        n = frames.shape[0]
+        n = x.shape[0]
         nb = m.decoder.beam_size
-        res = m({"image": [frames[:, f] for f in range(frames.shape[1])]})
+        fast = (isinstance(m.decoder, GeneratorWithBeamSearchV2) and m.decoder.repetition_penalty == 1.0
+                and not m._force_host_search and not m._hooked_resblocks())
+        if not x.is_cuda and x.dtype == torch.float32 and fast:
+            res = m.forward_host_frames(x)          # host batch: chunked copies overlapped with the ViT
+        else:
+            frames = x.to(eng.device).float()
+            res = m({"image": [frames[:, f] for f in range(frames.shape[1])]})
         ld = res["logits_dict"]
         all_logits = ld.device_tensor()                                   # [steps, n*nb, V] (view of the padded buffer)
         steps, V = all_logits.shape[0], all_logits.shape[-1]

@@ -48,16 +48,22 @@ def to_hf_state_dict(sd, cfg):
     return out
 
 
-@pytest.mark.slow
-def test_oracle_matches_hf_git_forward():
+@pytest.mark.parametrize("encoder", ["CLIPViT_B_16", "CLIPViT_L_14"])
+def test_oracle_matches_hf_git_forward(encoder):
+    """Both vision towers the reference can be configured with (model.py:682-685): ViT-B/16 (GIT-base, BASELINE configs
+    1-3) and ViT-L/14 (the shipped teacher, data/teacher_configs/GIT_LARGE_MSRVTT/parameter.yaml; BASELINE configs 4-5)."""
     from transformers import GitConfig as HFGitConfig, GitForCausalLM
 
     torch.manual_seed(0)
     F_, L = 2, 5
     # HF uses one LayerNorm eps (1e-12) for embeddings too: align the oracle for this comparison only.
-    cfg = go.GitConfig(num_image_with_embedding=F_, embedding_ln_eps=1e-12)
+    large = encoder == "CLIPViT_L_14"
+    cfg = go.GitConfig(num_image_with_embedding=F_, embedding_ln_eps=1e-12, image_encoder_type=encoder,
+                       visual_feature_size=1024 if large else 768)
     sd = go.init_state_dict(cfg, seed=3, temporal_std=0.02, perturb=True)
-    hf_cfg = HFGitConfig(num_image_with_embedding=F_, layer_norm_eps=1e-12, tie_word_embeddings=False)
+    vision = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, patch_size=14,
+                  image_size=224) if large else {}
+    hf_cfg = HFGitConfig(num_image_with_embedding=F_, layer_norm_eps=1e-12, tie_word_embeddings=False, vision_config=vision or None)
     hf = GitForCausalLM(hf_cfg).eval()
     missing, unexpected = hf.load_state_dict(to_hf_state_dict(sd, cfg), strict=False)
     missing = [m for m in missing if "position_ids" not in m]
@@ -72,7 +78,7 @@ def test_oracle_matches_hf_git_forward():
         hf_vis = torch.cat([hf.git.image_encoder(frames[i:i + 1]).last_hidden_state + hf.git.img_temporal_embedding[i]
                             for i in range(F_)], dim=1)
     nv = vf.shape[1]
-    assert nv == F_ * 197
+    assert nv == F_ * (257 if large else 197)
     assert torch.allclose(vf, hf_vis, atol=2e-4, rtol=1e-4), (vf - hf_vis).abs().max()
     hf_logits = hf_out.logits
     if hf_logits.shape[1] == nv + L:  # HF returns every row; upstream slices the text rows
