@@ -228,6 +228,28 @@ const char* gitb200_student_last_error(const gitb200_student* s);
 int gitb200_student_load_weight(gitb200_student* s, const char* name, const float* data, int ndim, const int64_t* shape);
 int gitb200_student_finalize(gitb200_student* s);
 int gitb200_student_logits_ld(const gitb200_student* s); /* vocabulary rounded up to 256 */
+/* ---- distillation training step of the student decoder (BASELINE.json configs[4]; DistillationTrainer.training_step,
+ * model.py:880-983, optimizer model.py:1105, DDP train.py:217-221) -------------------------------------------------------
+ * loss = KLDivLoss(batchmean)(log_softmax(student/T), softmax(teacher/T)) * T^2 + CrossEntropyLoss(ignore_index=0)(student[:, :-1],
+ * y[:, 1:]).  Parameters live in ONE flat fp32 vector (padded to the GEMM tile multiples; the vocabulary head first); the
+ * caller supplies a gradient vector of the same length (n = return value of _train_begin) and all-reduces it between
+ * _train_backward and _train_apply -- [0, head_floats) may be reduced as soon as phase 0 has been enqueued, while phase 1
+ * runs.  Dropout is not applied (parity oracle: torch.autograd on the same modules with dropout off).
+ *   _set_training(1) before the weights are loaded keeps their fp32 values for the master copy;
+ *   _train_forward: tokens_dev int32 [B, L], memory_dev fp32 [B, M, d_model], teacher_logits_dev fp32 [B*L, ld_teacher]
+ *                   -> loss_dev fp32 [3] = (total, KL, CE); activations are kept for the backward pass;
+ *   _train_backward: phase 0 = vocabulary head, phase 1 = decoder layers + embedding (+ d loss / d memory fp32 [B, M, d_model]);
+ *   _train_apply: torch.optim.Adam on grads * grad_scale, then the bf16 operand copies are refreshed;
+ *   _train_export: parameter (which = 0) or gradient (which = 1) `name` in the reference's tensor shape. */
+int gitb200_student_set_training(gitb200_student* s, int enable);
+long long gitb200_student_train_begin(gitb200_student* s, float lr, float beta1, float beta2, float eps);
+long long gitb200_student_train_head_floats(const gitb200_student* s);
+int gitb200_student_train_forward(gitb200_student* s, const int32_t* tokens_dev, const float* memory_dev, const float* teacher_logits_dev,
+                                  int ld_teacher, int B, int L, int M, float temperature, float* loss_dev, void* stream);
+int gitb200_student_train_backward(gitb200_student* s, int phase, float* grads_dev, float* d_memory_dev, void* stream);
+int gitb200_student_train_apply(gitb200_student* s, const float* grads_dev, float grad_scale, void* stream);
+int gitb200_student_train_export(gitb200_student* s, const char* name, int which, const float* grads_dev, float* out_dev, void* stream);
+
 /* forward_decoder(y, memory), model.py:135-154: tokens_dev int32 [B, L], memory_dev fp32 [B, M, d_model] ->
  * logits_dev fp32 [B*L, logits_ld] (teacher-forced, every position). */
 int gitb200_student_forward_decoder(gitb200_student* s, const int32_t* tokens_dev, const float* memory_dev, int B, int L, int M,

@@ -92,6 +92,44 @@ class StudentDecoderOracle(nn.Module):
         return tgt
 
 
+def forward_decoder_train(m: StudentDecoderOracle, y: torch.Tensor, memory: torch.Tensor) -> torch.Tensor:
+    """``forward_decoder`` (model.py:135-154) with autograd enabled -- the same statements; dropout is off (module in eval
+    mode): the CUDA training step does not apply dropout either."""
+    cfg = m.cfg
+    pad_mask = y == cfg.pad_token_id
+    tgt_mask = torch.triu(torch.ones(y.shape[1], y.shape[1]), diagonal=1).bool()
+    tgt_embed = m.embed(y)
+    tgt_embed = tgt_embed + m.pe[:, : y.size(1)]
+    tgt_embed = tgt_embed / torch.sqrt(torch.tensor(m.embed.embedding_dim))
+    out = m.decoder(tgt=tgt_embed, memory=memory, tgt_mask=tgt_mask, tgt_key_padding_mask=pad_mask, tgt_is_causal=True)
+    return m.linear(out)
+
+
+def distillation_loss(student_logits: torch.Tensor, teacher_logits: torch.Tensor, y: torch.Tensor, temperature: float = 1.0):
+    """DistillationTrainer.training_step's active losses (model.py:919-935, :983): (kl + ce, kl, ce)."""
+    kl = nn.KLDivLoss(reduction="batchmean")((student_logits / temperature).log_softmax(dim=-1),
+                                             (teacher_logits / temperature).softmax(dim=-1)) * temperature ** 2   # :922-928
+    y_target = y[:, 1:].reshape(-1)                                                                                 # :931-932
+    y_pred = student_logits[:, :-1].reshape(-1, student_logits.size(-1))                                            # :933-934
+    ce = nn.CrossEntropyLoss(ignore_index=0)(y_pred, y_target)                                                      # :935
+    return kl + ce, kl, ce                                                                                          # :983
+
+
+def distillation_step(m: StudentDecoderOracle, y: torch.Tensor, memory: torch.Tensor, teacher_logits: torch.Tensor,
+                      temperature: float = 1.0):
+    """One training step's loss and gradients by torch.autograd on the stock modules: ({'loss','kl','ce'}, grads by
+    reference state-dict key, d loss / d memory)."""
+    for p in m.parameters():
+        p.grad = None
+    memory = memory.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        logits = forward_decoder_train(m, y, memory)
+        loss, kl, ce = distillation_loss(logits, teacher_logits, y, temperature)
+        loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if not k.startswith("decoder_layer.") and p.grad is not None}
+    return {"loss": loss.item(), "kl": kl.item(), "ce": ce.item(), "logits": logits.detach()}, grads, memory.grad.detach().clone()
+
+
 def beam_search_from_memory(forward_decoder, memory: torch.Tensor, cls_token_id: int, max_len: int = 10, k: int = 3) -> torch.Tensor:
     """StudentCandidateV1.beam_search (model.py:189-316) after ``forward_image_enc``, statement by statement, with
     ``forward_decoder`` passed in (the oracle module's, or a scripted stand-in in the host-logic tests).  Quirks kept:

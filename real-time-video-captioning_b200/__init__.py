@@ -11,10 +11,11 @@ from .engine import Engine, SearchConfig, make_config, preprocess_frames, VIT_CO
 from .model import (BeamHypotheses, CLIPVisionTower, GenerativeImageTextModel, GenerativeImageTextTeacher,  # noqa: F401
                     GeneratorWithBeamSearchV2, LazyLogits, StreamingCaptioner, SyntheticTokenizer, TransformerDecoderTextualHead,
                     get_git_model)
-from .student import StudentCandidateV1  # noqa: F401
+from .student import DistillationTrainer, StudentCandidateV1  # noqa: F401
 from .metrics import calculate_bleu_score_corpus  # noqa: F401
-from .dist import shard_range, caption_sharded  # noqa: F401
+from .dist import all_reduce_bucket, caption_sharded, finish_all_reduce, shard_range  # noqa: F401
 
 __all__ = ["Engine", "SearchConfig", "GenerativeImageTextModel", "GenerativeImageTextTeacher",
            "GeneratorWithBeamSearchV2", "get_git_model", "calculate_bleu_score_corpus", "shard_range",
-           "caption_sharded", "GitB200Error", "StudentCandidateV1"]
+           "caption_sharded", "GitB200Error", "StudentCandidateV1", "DistillationTrainer", "all_reduce_bucket",
+           "finish_all_reduce"]

@@ -58,6 +58,13 @@ SIGNATURES = {
     "gitb200_student_last_error": (c_char_p, [c_void_p]),
     "gitb200_student_load_weight": (c_int, [c_void_p, c_char_p, c_void_p, c_int, POINTER(c_int64)]),
     "gitb200_student_finalize": (c_int, [c_void_p]),
+    "gitb200_student_set_training": (c_int, [c_void_p, c_int]),
+    "gitb200_student_train_begin": (c_longlong, [c_void_p, c_float, c_float, c_float, c_float]),
+    "gitb200_student_train_head_floats": (c_longlong, [c_void_p]),
+    "gitb200_student_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "gitb200_student_train_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gitb200_student_train_apply": (c_int, [c_void_p, c_void_p, c_float, c_void_p]),
+    "gitb200_student_train_export": (c_int, [c_void_p, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gitb200_student_logits_ld": (c_int, [c_void_p]),
     "gitb200_student_forward_decoder": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gitb200_student_greedy_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -9,62 +9,11 @@
 // multiples: d_model 576 -> 640); the small glue kernels below are plain CUDA-core kernels (a few KB per row).
 // The QKV projection writes straight into the per-layer cache [B][Lmax][3*dp] (GEMM output leading dimension =
 // Lmax*3*dp, base offset pos*3*dp), so no K/V scatter kernel exists.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
+#include "student_internal.cuh"
 
-#include <map>
-#include <string>
-#include <vector>
+using namespace sdet;
 
-#include "../../include/gitb200.h"
-#include "common.cuh"
-#include "kernels.h"
-
-namespace {
-
-struct SLayer {
-  bf16 *w_sa_in, *w_sa_out, *w_ca_q, *w_ca_kv, *w_ca_out, *w_ff1, *w_ff2;
-  float *b_sa_in, *b_sa_out, *b_ca_q, *b_ca_kv, *b_ca_out, *b_ff1, *b_ff2;
-  float *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
-};
-struct RawW {
-  float* p = nullptr;
-  std::vector<int64_t> shape;
-  size_t numel() const {
-    size_t n = 1;
-    for (auto d : shape) n *= (size_t)d;
-    return n;
-  }
-};
-template <typename T>
-struct SBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-};
-
-}  // namespace
-
-struct gitb200_student {
-  gitb200_student_config cfg;
-  int device = 0;
-  std::string err;
-  bool finalized = false;
-  std::map<std::string, RawW> raw;
-  std::vector<void*> allocs;
-  int dp = 0, fp = 0, vp = 0, hd = 0;  // padded d_model / d_ffn / vocab, head dim
-  float *embed = nullptr, *pe = nullptr, *b_vocab = nullptr;
-  bf16* w_vocab = nullptr;
-  std::vector<SLayer> layers;
-  // workspaces
-  SBuf<bf16> x, y, a, q2, h, mem;
-  std::vector<SBuf<bf16>> cache, memkv;
-  SBuf<float> logits;
-  SBuf<int> toks;
-};
-
-namespace {
+namespace sdet {
 
 std::string g_student_err;
 
@@ -78,31 +27,10 @@ int sfail(gitb200_student* c, int code, const char* fmt, ...) {
   else g_student_err = buf;
   return code;
 }
-#define S_CUDA_OK(c, expr)                                                                                            \
-  do {                                                                                                                \
-    cudaError_t e_ = (expr);                                                                                          \
-    if (e_ != cudaSuccess)                                                                                            \
-      return sfail(c, GITB200_ERR_CUDA, "%s failed: %s [%s] (%s:%d)", #expr, cudaGetErrorString(e_), gemm_last_error(), \
-                   __FILE__, __LINE__);                                                                               \
-  } while (0)
-#define S_TRY(expr)      \
-  do {                   \
-    int r_ = (expr);     \
-    if (r_) return r_;   \
-  } while (0)
 
-template <typename T>
-int sensure(gitb200_student* c, SBuf<T>& b, size_t n) {
-  if (b.cap >= n) return 0;
-  if (b.p) S_CUDA_OK(c, cudaFree(b.p));
-  b.p = nullptr;
-  b.cap = 0;
-  S_CUDA_OK(c, cudaMalloc(&b.p, n * sizeof(T)));
-  S_CUDA_OK(c, cudaMemset(b.p, 0, n * sizeof(T)));  // padded columns are never written by the glue kernels: keep them finite
-  b.cap = n;
-  return 0;
-}
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+}  // namespace sdet
+
+namespace {
 
 // ------------------------------------------------------------------ kernels
 // x[r, :] = (embed[tok(r)] + pe[pos(r)]) / sqrt(d)        (model.py:144-148: the scaling is applied AFTER adding pe)
@@ -249,6 +177,10 @@ __global__ void student_copy_tokens_kernel(const int* __restrict__ src, int src_
 }
 
 // ------------------------------------------------------------------ host helpers
+}  // namespace
+
+namespace sdet {
+
 int s_gemm(gitb200_student* c, const bf16* A, int lda, const bf16* W, int K, int M, int N, const float* bias, const bf16* residual,
            int ldr, int act, bf16* out, int ldo, float* out32, int ldo32, cudaStream_t s) {
   GemmArgs g;
@@ -263,6 +195,26 @@ int s_ln(gitb200_student* c, const bf16* x, int ldx, int rows, const float* g, c
   S_CUDA_OK(c, cudaGetLastError());
   return 0;
 }
+// teacher-forced embedding of all L positions of every sequence (pos0 = 0)
+int s_embed(gitb200_student* c, const int* tokens, int tok_ld, int L, int rows, bf16* out, cudaStream_t s) {
+  student_embed_kernel<<<rows, 128, 0, s>>>(tokens, tok_ld, 0, L, 0, rows, c->embed, c->pe, c->cfg.d_model, c->cfg.vocab,
+                                            1.0f / sqrtf((float)c->cfg.d_model), out, c->dp);
+  note_launch();
+  S_CUDA_OK(c, cudaGetLastError());
+  return 0;
+}
+int s_attn(gitb200_student* c, const bf16* q, int ldq, int Lq, const bf16* kv, int kv_rows, int ldkv, int k_off, int v_off, int n_keys,
+           int causal, const int* tokens, int tok_ld, int rows, bf16* out, int ldo, cudaStream_t s) {
+  student_attn_kernel<<<dim3(rows, c->cfg.n_head), 32, 0, s>>>(q, ldq, Lq, 0, kv, kv_rows, ldkv, k_off, v_off, n_keys, causal, tokens, tok_ld,
+                                                               c->cfg.pad, c->hd, 1.0f / sqrtf((float)c->hd), out, ldo);
+  note_launch();
+  S_CUDA_OK(c, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdet
+
+namespace {
 
 const RawW* sfind(gitb200_student* c, const std::string& n) {
   auto it = c->raw.find(n);
@@ -407,6 +359,7 @@ void gitb200_student_destroy(gitb200_student* c) {
   for (auto& b : c->memkv) cudaFree(b.p);
   cudaFree(c->logits.p);
   cudaFree(c->toks.p);
+  sdet::student_train_destroy(c);
   delete c;
 }
 
@@ -489,8 +442,10 @@ int gitb200_student_finalize(gitb200_student* c) {
   S_TRY(s_w(c, "linear.weight", 0, k.vocab, d, c->w_vocab, c->vp));
   S_TRY(s_v(c, "linear.bias", 0, k.vocab, c->b_vocab));
   S_CUDA_OK(c, cudaDeviceSynchronize());
-  for (auto& kv : c->raw) cudaFree(kv.second.p);
-  c->raw.clear();
+  if (!c->keep_raw) {
+    for (auto& kv : c->raw) cudaFree(kv.second.p);
+    c->raw.clear();
+  }
   c->finalized = true;
   return GITB200_OK;
 }

@@ -93,3 +93,22 @@ def caption_sharded(caption_fn: Callable[[int, int], Tuple[torch.Tensor, torch.T
     work = dist.all_gather_into_tensor(packed, mine, group=group, async_op=async_op)
     handle = GatherHandle(work if async_op else None, packed, n_clips, keep, length)
     return handle if async_op else handle.wait()
+
+
+def all_reduce_bucket(flat: torch.Tensor, begin: int, end: int, group=None):
+    """Start the SUM all-reduce of ``flat[begin:end]`` (a view: reduced in place) and return the work handle, or None when
+    no process group is initialised.  The distillation step (reference: Lightning DDP, train.py:217-221)
+    calls it once for the vocabulary-head bucket as soon as that part of the backward pass is enqueued and once for the
+    rest, so the first reduction overlaps the remaining backward kernels; ``finish_all_reduce`` waits for both."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1 or end <= begin:
+        return None
+    return dist.all_reduce(flat[begin:end], op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
+def finish_all_reduce(handles, group=None) -> float:
+    """Wait for the bucket reductions; returns the factor that turns the summed gradients into the DDP average."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    for h in handles:
+        if h is not None:
+            h.wait()
+    return 1.0 / world

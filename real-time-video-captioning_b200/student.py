@@ -9,7 +9,8 @@ The nn.Module tree only holds parameters; there is no torch forward and no CPU p
 
 The TinyViT image encoder (timm ``features_only`` model, :35-48) is not rebuilt: pass ``image_encoder=`` (any module that
 returns the list of stage feature maps like timm's) or call ``greedy_decode_from_memory`` / ``forward_decoder`` with the
-``memory`` tensor [B, F, d_model] directly.  Training (``DistillationTrainer``) is out of scope.
+``memory`` tensor [B, F, d_model] directly.  ``enable_training`` / ``distillation_step`` / ``DistillationTrainer`` run the
+reference's distillation step (model.py:880-983) for the decoder on the same library (csrc/student_train.cu).
 """
 from __future__ import annotations
 
@@ -99,6 +100,10 @@ class StudentCandidateV1(nn.Module):
         self._lib = None
         self._stale = True
         self._dev = None
+        self._train_cfg = None      # (lr, beta1, beta2, eps) once enable_training() was called
+        self._grads = None          # flat fp32 gradient vector (torch owns it so that torch.distributed can reduce it in place)
+        self._head_floats = 0
+        self._params_dirty = False  # the optimizer has moved the library's master weights past the nn.Parameters
 
     # ---- engine plumbing
     def load_state_dict(self, state_dict, strict: bool = False, **kw):
@@ -109,6 +114,8 @@ class StudentCandidateV1(nn.Module):
         return out
 
     def _apply(self, fn, *a, **k):
+        if getattr(self, "_params_dirty", False):
+            self.sync_parameters()  # the trained master weights must not be lost when the module is moved / cast
         self._stale = True
         return super()._apply(fn, *a, **k)
 
@@ -124,6 +131,8 @@ class StudentCandidateV1(nn.Module):
                             self.pos_enc.pe.shape[1], self.cls_token_id, self.sep_token_id, 0, 1e-5)
         h = ctypes.c_void_p()
         _check(lib.gitb200_student_create(ctypes.byref(cfg), p.device.index or 0, ctypes.byref(h)), lib, None, "gitb200_student_create")
+        if self._train_cfg is not None:
+            _check(lib.gitb200_student_set_training(h, 1), lib, h, "gitb200_student_set_training")
         weights = {k: v for k, v in self.state_dict().items() if k.startswith(("decoder.layers.", "embed.", "linear."))}
         weights["pos_enc.pe"] = self.pos_enc.pe[0]
         for name, t in weights.items():
@@ -133,6 +142,13 @@ class StudentCandidateV1(nn.Module):
         _check(lib.gitb200_student_finalize(h), lib, h, "gitb200_student_finalize")
         self._h, self._lib, self._stale, self._dev = h, lib, False, p.device
         self._ld = lib.gitb200_student_logits_ld(h)
+        if self._train_cfg is not None:
+            n = int(lib.gitb200_student_train_begin(h, *[ctypes.c_float(v) for v in self._train_cfg]))
+            if n <= 0:
+                raise GitB200Error("gitb200_student_train_begin: " + lib.gitb200_student_last_error(h).decode())
+            self._grads = torch.zeros(n, dtype=torch.float32, device=p.device)
+            self._head_floats = int(lib.gitb200_student_train_head_floats(h))
+            self._params_dirty = False
         return h
 
     def close(self):
@@ -225,7 +241,108 @@ class StudentCandidateV1(nn.Module):
         _, memory = self.forward_image_enc(src)
         return self.greedy_decode_from_memory(memory, max_len)
 
+    # ---- distillation training of the decoder half (DistillationTrainer.training_step, model.py:880-983)
+    def enable_training(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """Switch the library context to training mode: fp32 master weights + torch.optim.Adam state (model.py:1105:
+        ``Adam(student.parameters(), lr)``) next to the bf16 operand copies.  Dropout is not applied."""
+        self._train_cfg = (float(lr), float(betas[0]), float(betas[1]), float(eps))
+        self._stale = True
+
+    def distillation_step(self, y: torch.Tensor, memory: torch.Tensor, teacher_logits: torch.Tensor, temperature: float = 1.0,
+                          apply: bool = True, group=None, want_memory_grad: bool = False):
+        """One training step on this rank's micro-batch: forward_decoder(y, memory) -> KL(batchmean) * T^2 + CE(ignore 0)
+        (model.py:922-935, :983) -> backward -> gradient all-reduce over ``group`` (DDP average; the vocabulary-head bucket is
+        reduced while the decoder layers are still in their backward pass) -> Adam.  Returns {'loss','kl','ce'} (device
+        scalars, this rank's micro-batch) and, on request, d loss / d memory [B, M, d_model] for an external image encoder."""
+        if self._train_cfg is None:
+            raise RuntimeError("call enable_training() first")
+        from .dist import all_reduce_bucket, finish_all_reduce
+        h = self._engine()
+        lib = self._lib
+        tok = y.to(device=self._dev, dtype=torch.int32).contiguous()
+        mem = memory.to(device=self._dev, dtype=torch.float32).contiguous()
+        tl = teacher_logits.to(device=self._dev, dtype=torch.float32)
+        B, L = tok.shape
+        tl = tl.reshape(B * L, tl.shape[-1])
+        if tl.stride(-1) != 1 or tl.stride(0) % 4 != 0:
+            tl = tl.contiguous()
+        if mem.shape[0] != B or mem.shape[2] != self.d_model:
+            raise ValueError("memory must be [B, F, d_model]")
+        if tl.shape[-1] < self.embed.num_embeddings:
+            raise ValueError("teacher logits must cover the student's vocabulary")
+        loss = torch.empty(3, dtype=torch.float32, device=self._dev)
+        dmem = torch.empty_like(mem) if want_memory_grad else None
+        s = self._stream()
+        _check(lib.gitb200_student_train_forward(h, _ptr(tok), _ptr(mem), _ptr(tl), tl.stride(0), B, L, mem.shape[1],
+                                                 ctypes.c_float(temperature), _ptr(loss), s), lib, h, "gitb200_student_train_forward")
+        g = self._grads
+        _check(lib.gitb200_student_train_backward(h, 0, _ptr(g), None, s), lib, h, "gitb200_student_train_backward(head)")
+        w0 = all_reduce_bucket(g, 0, self._head_floats, group)            # overlaps phase 1
+        _check(lib.gitb200_student_train_backward(h, 1, _ptr(g), _ptr(dmem), s), lib, h, "gitb200_student_train_backward(layers)")
+        w1 = all_reduce_bucket(g, self._head_floats, g.numel(), group)
+        scale = finish_all_reduce([w0, w1], group)
+        if apply:
+            _check(lib.gitb200_student_train_apply(h, _ptr(g), ctypes.c_float(scale), s), lib, h, "gitb200_student_train_apply")
+            self._params_dirty = True
+        out = {"loss": loss[0], "kl": loss[1], "ce": loss[2]}
+        if want_memory_grad:
+            out["d_memory"] = dmem
+        return out
+
+    def _export(self, name: str, which: int) -> torch.Tensor:
+        p = dict(self.named_parameters())[name]
+        out = torch.empty(p.shape, dtype=torch.float32, device=self._dev)
+        _check(self._lib.gitb200_student_train_export(self._h, name.encode(), which, _ptr(self._grads), _ptr(out), self._stream()),
+               self._lib, self._h, f"gitb200_student_train_export({name})")
+        return out
+
+    def gradients(self):
+        """Gradients of the last distillation_step (after the all-reduce, before the 1/world scaling) under the reference's
+        state-dict keys."""
+        self._engine()
+        return {k: self._export(k, 1) for k, _ in self.named_parameters() if k.startswith(("decoder.layers.", "embed.", "linear."))}
+
+    def sync_parameters(self) -> None:
+        """Copy the optimizer's fp32 master weights back into the nn.Parameters (``state_dict()`` does this on its own)."""
+        if self._h is None or not self._params_dirty:
+            return
+        with torch.no_grad():
+            for k, p in self.named_parameters():
+                if k.startswith(("decoder.layers.", "embed.", "linear.")):
+                    p.copy_(self._export(k, 0))
+        self._params_dirty = False
+        self._stale = False  # the copy above went through Parameter.copy_, not through _apply
+
+    def state_dict(self, *a, **k):
+        self.sync_parameters()
+        return super().state_dict(*a, **k)
+
     def forward(self, x, y):
         """model.py:107-114: feature maps of the image encoder + the decoder logits."""
         fmaps, memory = self.forward_image_enc(x)
         return list(fmaps) + [self.forward_decoder(y, memory)]
+
+
+class DistillationTrainer:
+    """DistillationTrainer.training_step (model.py:880-983) for what this library holds of the student: the frozen GIT teacher
+    gives the teacher-forced logits (``forward_output_logits``, :896), the student's DECODER is trained on KL + CE (:983) with
+    Adam (:1105) and a DDP gradient all-reduce (train.py:217-221).  The student's TinyViT image encoder is not part of the
+    library: ``batch['memory']`` ([B, F, d_model], what ``forward_image_enc`` returns at :128) is supplied by the caller, and
+    ``d_memory`` comes back for it.  No Lightning: call ``training_step`` from your own loop."""
+
+    def __init__(self, teacher, student: StudentCandidateV1, lr: float = 1e-4, temperature: float = 1.0, group=None):
+        self.teacher, self.student, self.temperature, self.group = teacher, student, temperature, group
+        student.enable_training(lr=lr)
+
+    @torch.no_grad()
+    def teacher_logits(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        out_teacher, _, _ = self.teacher.forward_output_logits(x, y)      # model.py:896
+        return torch.cat(out_teacher, dim=0)                               # :919  [B, L, V]
+
+    def training_step(self, batch, batch_idx: int = 0):
+        x, y, memory = batch["frames"], batch["caption"], batch["memory"]
+        t_logits = self.teacher_logits(x, y)
+        out = self.student.distillation_step(y, memory, t_logits, temperature=self.temperature, group=self.group,
+                                             want_memory_grad=True)
+        self.last = out
+        return out["loss"]

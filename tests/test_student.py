@@ -185,3 +185,169 @@ def test_student_beam_search_on_the_gpu_decoder():
 
     sigma = m.forward_decoder(ref[:, :-1], mem).std().item()
     assert (seq_score(ref) - seq_score(out) < 5 * 0.15 * sigma).all()
+
+
+# ------------------------------------------------------------------------------------------ distillation training step
+def _train_inputs(cfg, B, L, F, seed, pads=True):
+    gen = torch.Generator().manual_seed(seed)
+    y = torch.randint(1000, cfg.vocab_length, (B, L), generator=gen)
+    y[:, 0] = cfg.cls_token_id
+    if pads and L > 4:  # padded tails: masked keys (masking.py:14) and ignored CE targets (ignore_index=0, model.py:935)
+        y[0, L - 3:] = 0
+        y[B - 1, L - 1:] = 0
+    mem = torch.randn(B, F, cfg.d_model, generator=gen)
+    teacher = torch.randn(B, L, cfg.vocab_length, generator=gen) * 1.5
+    return y, mem, teacher
+
+
+def record(name, **vals):
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_metrics.jsonl"), "a") as fh:
+        fh.write(json.dumps({"test": name, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in vals.items()}}) + "\n")
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,F,temperature", [(8, 20, 6, 1.0), (3, 7, 2, 2.0)])
+def test_distillation_step_gradients_match_autograd(B, L, F, temperature):
+    """BASELINE.json configs[4] (8 clips x 20 caption tokens per GPU, student decoder of config.py:76-84): loss and every
+    parameter gradient of gitb200_student_train_forward / _backward against torch.autograd on the stock nn modules the
+    reference instantiates (oracle/student_oracle.py: KLDivLoss(batchmean) * T^2 + CrossEntropyLoss(ignore_index=0),
+    model.py:922-935, :983).  bf16 activations / activation gradients, fp32 weight gradients: relative Frobenius error
+    < 3e-2 over all parameters together, < 6e-2 for any single tensor."""
+    cfg = st.StudentConfig()
+    m, s = _gpu_student(cfg, seed=21)
+    y, mem, teacher = _train_inputs(cfg, B, L, F, seed=B * 10 + L)
+    info, ref_grads, ref_dmem = st.distillation_step(m, y, mem, teacher, temperature)
+    s.enable_training(lr=1e-4)
+    out = s.distillation_step(y, mem, teacher, temperature=temperature, apply=False, want_memory_grad=True)
+    loss, kl, ce = out["loss"].item(), out["kl"].item(), out["ce"].item()
+    assert abs(loss - (kl + ce)) < 1e-5 * abs(loss)
+    assert abs(kl - info["kl"]) < 2e-2 * abs(info["kl"]) and abs(ce - info["ce"]) < 2e-2 * abs(info["ce"]), (kl, info["kl"], ce, info["ce"])
+    grads = {k: v.cpu() for k, v in s.gradients().items()}
+    assert set(grads) == set(ref_grads)
+    worst, num, den = ("", 0.0), 0.0, 0.0
+    for k, ref in ref_grads.items():
+        e = _rel(grads[k], ref)
+        num += (grads[k].double() - ref.double()).pow(2).sum().item()
+        den += ref.double().pow(2).sum().item()
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < 6e-2, (k, e)
+    total = (num / den) ** 0.5
+    e_mem = _rel(out["d_memory"].cpu(), ref_dmem)
+    record("distillation_step_grads", B=B, L=L, temperature=temperature, loss=loss, ref_loss=info["loss"], all_params_rel_fro=total,
+           worst_tensor=worst[0], worst_rel_fro=worst[1], d_memory_rel_fro=e_mem)
+    assert total < 3e-2, total
+    assert e_mem < 6e-2, e_mem
+    # rows of the embedding table that do not occur in y get exactly zero gradient
+    unused = torch.ones(cfg.vocab_length, dtype=torch.bool)
+    unused[y.flatten()] = False
+    assert (grads["embed.weight"][unused] == 0).all()
+
+
+@pytest.mark.gpu
+def test_distillation_adam_step_matches_torch_optim_and_loss_goes_down():
+    """gitb200_student_train_apply == torch.optim.Adam(lr=1e-4) (model.py:1105) fed the SAME gradients, for three steps; the
+    refreshed bf16 operand copies are live (the forward after the step uses them): the loss on a fixed batch decreases; the
+    inference entry points keep working on the trained weights and state_dict() returns them."""
+    cfg = st.StudentConfig()
+    m, s = _gpu_student(cfg, seed=22)
+    y, mem, teacher = _train_inputs(cfg, 8, 20, 6, seed=5)
+    s.enable_training(lr=1e-4)
+    names = [k for k, _ in s.named_parameters() if k.startswith(("decoder.layers.", "embed.", "linear."))]
+    ref_params = {k: p.detach().clone().cuda().requires_grad_(True) for k, p in s.named_parameters() if k in names}
+    opt = torch.optim.Adam(list(ref_params.values()), lr=1e-4)
+    losses = []
+    for step in range(3):
+        out = s.distillation_step(y, mem, teacher, apply=False)
+        losses.append(out["loss"].item())
+        g = s.gradients()
+        import ctypes
+        rc = s._lib.gitb200_student_train_apply(s._h, ctypes.c_void_p(s._grads.data_ptr()), ctypes.c_float(1.0), s._stream())
+        assert rc == 0
+        s._params_dirty = True
+        for k in names:
+            ref_params[k].grad = g[k].clone()
+        opt.step()
+        for k in names:
+            got = s._export(k, 0)
+            assert torch.allclose(got, ref_params[k].detach(), atol=2e-7, rtol=1e-5), (step, k, (got - ref_params[k]).abs().max().item())
+    for _ in range(12):
+        out = s.distillation_step(y, mem, teacher)
+        losses.append(out["loss"].item())
+    assert losses[-1] < losses[0] - 0.05, losses
+    sd = s.state_dict()
+    assert not torch.equal(sd["linear.bias"].cpu(), st.state_dict_of(m)["linear.bias"])   # trained weights, not the initial ones
+    logits = s.forward_decoder(y, mem)                                                    # inference path on the trained weights
+    m2 = st.init_student(cfg, seed=22)
+    m2.load_state_dict({k: v.cpu() for k, v in sd.items() if k in st.state_dict_of(m2)}, strict=False)
+    ref = m2.forward_decoder(y, mem)
+    sigma = ref.std().item()
+    assert (logits.cpu() - ref).abs().max().item() < 0.15 * sigma
+
+
+@pytest.mark.gpu
+def test_distillation_trainer_step_with_the_git_teacher():
+    """DistillationTrainer.training_step (model.py:880-983) end to end for the decoder: the frozen GIT teacher's teacher-forced
+    logits (forward_output_logits, :896) feed the KL term; one step returns a finite loss equal to the oracle's on the same
+    teacher logits."""
+    tcfg_param = {"num_image_with_embedding": 2}
+    teacher = g.GenerativeImageTextTeacher.from_random_init(tcfg_param)
+    cfg = st.StudentConfig()
+    m, s = _gpu_student(cfg, seed=23)
+    trainer = g.DistillationTrainer(teacher, s, lr=1e-4)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2, 3, 224, 224, generator=gen)
+    y = torch.randint(1000, 30000, (2, 6), generator=gen)
+    y[:, 0] = 101
+    mem = torch.randn(2, 2, cfg.d_model, generator=gen)
+    t_logits = trainer.teacher_logits(x, y)
+    assert t_logits.shape == (2, 6, 30522)
+    info, _, _ = st.distillation_step(m, y, mem, t_logits.cpu().float())
+    loss = trainer.training_step({"frames": x, "caption": y, "memory": mem})
+    assert torch.isfinite(loss) and abs(loss.item() - info["loss"]) < 2e-2 * abs(info["loss"]), (loss.item(), info["loss"])
+    assert trainer.last["d_memory"].shape == mem.shape
+
+
+def _allreduce_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    h0 = g.all_reduce_bucket(flat, 0, 4)        # the "vocabulary head" bucket first ...
+    h1 = g.all_reduce_bucket(flat, 4, 10)       # ... then the rest, both in flight
+    scale = g.finish_all_reduce([h0, h1])
+    q.put((rank, (flat * scale).tolist()))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_all_reduce_to_the_ddp_average_on_two_gloo_ranks():
+    """The distillation step's collective: two in-place bucket all-reduces + the 1/world scaling = the DDP
+    gradient average, on a world of 2 (gloo, CPU)."""
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [i * 1.5 for i in range(10)]   # (1 + 2) / 2 * i
+    for rank, vals in out:
+        assert vals == want, (rank, vals)
+    assert g.finish_all_reduce([None, None]) == 1.0 and g.all_reduce_bucket(torch.zeros(4), 0, 4) is None   # no process group: no-ops
