@@ -241,7 +241,7 @@ def config_leg(g, gm, torch, dist, name, param, B, frames_n, sp, steps, warmup, 
     return out
 
 
-def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=2):
+def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=3):
     """The drop-in itself: GenerativeImageTextTeacher.forward(x) (model.py:762-793) on a pinned HOST batch -- encode, beam-4 /
     max_steps-15 search (the reference's own settings, model.py:702-708), saved logits, per-clip result dicts with `output`
     and `cap` -- timed end to end by the wall clock, beside Engine.caption_host with the same search settings."""
@@ -259,7 +259,9 @@ def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=2)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        r = None
         for _ in range(steps):
+            del r  # a caller that keeps the previous batch's 3 GB of results alive makes every call cudaMalloc a new set
             r = fn()
         torch.cuda.synchronize(dev)
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -267,8 +269,8 @@ def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=2)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), r
 
-    t_teacher, res = wall(lambda: teacher(x))
     t_engine, _ = wall(lambda: eng.caption_host(x, sp, chunk_clips=64))
+    t_teacher, res = wall(lambda: teacher(x))
     out = {"api": "GenerativeImageTextTeacher.forward(x): pinned host frames -> list of per-clip dicts (predictions, logprobs, logits_dict, visual_features, output, cap)",
            "clips_per_gpu_per_step": B, "beam_size": sp.beam_size, "max_steps": sp.max_steps, "steps": steps,
            "value": world * B * steps / t_teacher, "unit": UNIT, "h2d_bytes_per_step": x.numel() * 4,
