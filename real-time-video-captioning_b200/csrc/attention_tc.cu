@@ -7,9 +7,14 @@
 // the two partial results are merged once at the end (the split-K identity of softmax).  Per block j (g = j & 1):
 //     S_j = Q K_j^T           tcgen05.mma  M=128, N<=64, K=64 (Q, K: K-major 128B-swizzled TMA tiles)  -> TMEM S[g]
 //     P_j = exp2(S_j*c - m_g) 4 warps, one query row per thread (tcgen05.ld 32x32b.x32), packed f32x2 FMA / add,
-//                             P written as the bf16 K-major A operand into 128B-swizzled shared memory P[g]
-//     O_g += P_j V_j          tcgen05.mma  M=128, N=64, K<=64 (V: the TMA tile used as an MN-major B operand), the
-//                             accumulation stays in TMEM
+//                             P written as bf16 pairs straight back into TENSOR MEMORY (tcgen05.st, 32 columns per group)
+//     O_g += P_j V_j          tcgen05.mma with the A operand FROM TMEM (the "TS" form: lane = query row, one 32-bit column =
+//                             two consecutive keys), M=128, N=64, K<=64 (V: the TMA tile used as an MN-major B operand);
+//                             the accumulation stays in TMEM
+// P never touches shared memory (round 1 staged it there: 8 swizzled st.shared.v4 per row, a fence.proxy.async and a barrier
+// on every block of every group's serial chain, 32 KB of the CTA's shared memory).  TMEM map of a CTA (256 columns, two CTAs
+// per SM): S [0,64) -- ONE score buffer, handed to the two groups alternately: a group keeps it only for the ~150 cycles of
+// its tcgen05.ld --, O[0] [64,128), O[1] [128,192), P[0] [192,224), P[1] [224,256).
 // The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in
 // practice during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases
 // P_j.  No per-block read-back of O, no cross-warp max exchange, no named barrier inside the loop.
@@ -38,18 +43,18 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;   // query rows per CTA = TMEM lanes
 constexpr int BKV = 64;   // keys per block
-constexpr int K_STAGES = 3, V_STAGES = 4;
+constexpr int K_STAGES = 4, V_STAGES = 6;  // P no longer lives in shared memory: its 32 KB went into deeper K / V rings
 constexpr int Q_BYTES = BQ * 128;         // 16 KB
 constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB
-constexpr int P_BYTES = BQ * 128;         // 16 KB: P[128 x 64 keys] bf16, one buffer per softmax group
 constexpr int N_BARRIERS = 2 + 2 * K_STAGES + 2 * V_STAGES + 8;
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES + 256 /*barriers + tmem slot*/ +
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 256 /*barriers + tmem slot*/ +
                            2 * BQ * 8 /*(m, l) exchange*/;
 constexpr int NUM_SM_WARPS = 8;   // warps 4-7: softmax group 0, warps 8-11: group 1; TMEM lane quarter = warp & 3
 constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: S issuer + TMEM owner, warps 2 / 3: P V issuers
 constexpr int SERVICE_REGS = 32, SOFTMAX_REGS = 104;  // setmaxnreg split: the increase is served from the CTA's OWN pool (what its service
                                                       // warps released; more than that deadlocks), so 128 x 32 + 256 x 104 = 30720 = the launch allocation 384 x 80
-constexpr int TMEM_COLS = 256;    // S[0]: [0,64), S[1]: [64,128), O[0]: [128,192), O[1]: [192,256)
+constexpr int TMEM_COLS = 256;    // S: [0,64), O[0]: [64,128), O[1]: [128,192), P[0]: [192,224), P[1]: [224,256)
+constexpr uint32_t TM_S = 0, TM_O = 64, TM_P = 192;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P never exceeds 2^8 before the running max moves
 
 // V tile [keys][64 dims] (rows of 128 B, 128B swizzle) read as an MN-major B operand (N = dims, K = keys):
@@ -81,7 +86,30 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[TMEM] * B[smem desc]: the A operand (bf16, K-major: lane = row, 32-bit column = two consecutive K elements)
+// is read from tensor memory.  Warp-uniform issue like ptx::umma_bf16_elect.
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -142,17 +170,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t sQ = smem_base;
   auto sK = [&](int s) { return smem_base + Q_BYTES + s * KV_TILE_BYTES; };
   auto sV = [&](int s) { return smem_base + Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
-  auto sP = [&](int g) { return smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + g * P_BYTES; };
-  const uint32_t bar_base = smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 2 * P_BYTES;
+  const uint32_t bar_base = smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
   const uint32_t q_full = bar_base, q_empty = bar_base + 8u;
   auto k_full = [&](int s) { return bar_base + 8u * (2 + s); };
   auto k_empty = [&](int s) { return bar_base + 8u * (2 + K_STAGES + s); };
   auto v_full = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + s); };
   auto v_empty = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + V_STAGES + s); };
   const uint32_t bar_g = bar_base + 8u * (2 + 2 * K_STAGES + 2 * V_STAGES);
-  auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S[g] holds a new block
-  auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S[g] has been read into registers
-  auto p_full = [&](int g) { return bar_g + 8u * (4 + g); };  // group g -> its P V issuer: P[g] written (and O[g] rescaled)
+  auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S holds a new block of this group
+  auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S has been read into registers
+  auto p_full = [&](int g) { return bar_g + 8u * (4 + g); };  // group g -> its P V issuer: P[g] written to TMEM (and O[g] rescaled)
   auto o_full = [&](int g) { return bar_g + 8u * (6 + g); };  // MMA -> group g: O[g] += P V finished, P[g] is free
   const uint32_t tmem_slot = bar_base + 8u * N_BARRIERS;
   const uint32_t sML = bar_base + 256;  // float2 [2 groups][128 rows]: (m, l) of each group's partial softmax
@@ -204,7 +231,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tmem_base = ptx::warp_uniform(tmem_base);
   // register split (inside each role's branch, so that ptxas budgets the role's code accordingly): the four service warps
   // (TMA, S issue, two P V issuers) hand registers to the eight softmax warps
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base + TM_S, tO = tmem_base + TM_O, tP = tmem_base + TM_P;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
@@ -232,19 +259,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
     const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
     uint32_t kc = 0;             // key blocks issued so far (all items)
-    uint32_t fills0 = 0, fills1 = 0;  // fills of S[0] / S[1] so far
+    uint32_t fills0 = 0, fills1 = 0;  // blocks handed to group 0 / group 1 so far
+    int prev_g = -1;             // group that received the previous block (it holds the single S buffer until it has read it)
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       ptx::mbar_wait(q_full, (uint32_t)(it & 1));
       ptx::tc_fence_after();
       for (int j = 0; j < n_blocks; ++j, ++kc) {
         const int g = j & 1;
-        const uint32_t fills = g ? fills1 : fills0;
-        if (fills > 0) {  // the previous block of this buffer (possibly of the previous item) has left S[g]
-          ptx::mbar_wait(s_free(g), (fills - 1) & 1u);
+        if (prev_g >= 0) {  // the previous block (possibly of the previous item) has left S for its group's registers
+          ptx::mbar_wait(s_free(prev_g), ((prev_g ? fills1 : fills0) - 1) & 1u);
           ptx::tc_fence_after();
         }
-        // S_j = Q K_j^T over the head dim (4 steps of 16) into S[j & 1]
+        // S_j = Q K_j^T over the head dim (4 steps of 16)
         const int ks = kc % K_STAGES;
         const int nk = min(BKV, group_len - j * BKV);
         const int nk16 = (nk + 15) & ~15;
@@ -257,12 +284,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t id_s = idesc_qk(nk16);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16_elect(tS + (uint32_t)(g * 64), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
+          ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
         if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
         ptx::umma_commit_elect(k_empty(ks));  // K_j is dead once S_j has been computed
         ptx::umma_commit_elect(s_full(g));
         if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
         if (g) ++fills1; else ++fills0;
+        prev_g = g;
       }
       ptx::umma_commit_elect(q_empty);  // Q may be replaced once every S product of this item has completed
     }
@@ -273,7 +301,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // issue slots spinning; issuing from a softmax warp made that warp 800 cycles per block slower than its three peers).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
     const int g = warp - 2;
-    const uint64_t dp = ptx::umma_desc_sw128_kmajor(sP(g));
+    const uint32_t tPg = tP + (uint32_t)(g * 32);
     uint32_t done = 0;
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -289,9 +317,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // V_j is resident: the S issuer waited for it before S_j
         const uint32_t acc0 = j == g ? 0u : 1u;               // the group's first block of an item starts a new O
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 32 B along its rows, V advances 2 atoms
+        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 8 TMEM columns (bf16 pairs), V advances 2 atoms
           if (k * 16 < nk16)
-            ptx::umma_bf16_elect(tO + (uint32_t)(g * 64), dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
+            umma_bf16_ts_elect(tO + (uint32_t)(g * 64), tPg + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
         if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
         ptx::umma_commit_elect(v_empty(vs));
         ptx::umma_commit_elect(o_full(g));
@@ -305,9 +333,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int grp = (warp - 4) >> 2;    // 0: even key blocks, 1: odd key blocks
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tSg = tS + (uint32_t)(grp * 64) + lane_off;
+    const uint32_t tSg = tS + lane_off;
     const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
-    const uint32_t sPg = sP(grp) + (uint32_t)r * 128u;
+    const uint32_t tPg = tP + (uint32_t)(grp * 32) + lane_off;
     const bool has1 = n_blocks > 1;
     uint32_t done = 0;  // key blocks this group has processed so far (all items): phase of s_full / o_full
     int it = 0;
@@ -340,9 +368,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int i = 0; i < 64; ++i)
           if (i >= nk) s[i] = -INFINITY;
       }
-      float mx = fmaxf(s[0], s[1]);
+      // row maximum as a tree (8 independent 3-input chains, then 3 levels): ~6 dependent steps instead of 32
+      float m8[8];
 #pragma unroll
-      for (int i = 2; i < 64; i += 2) mx = fmaxf(mx, fmaxf(s[i], s[i + 1]));
+      for (int i = 0; i < 8; ++i) m8[i] = fmaxf(s[i], fmaxf(s[8 + i], s[16 + i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m8[i] = fmaxf(m8[i], fmaxf(s[24 + i], s[32 + i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m8[i] = fmaxf(m8[i], fmaxf(s[40 + i], fmaxf(s[48 + i], s[56 + i])));
+      const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       const float m_blk = mx * scale_log2;  // scale > 0: max commutes with it
       // lazy running max: move it only when this block would push P above 2^RESCALE_THRESHOLD
       const bool need = m_blk > m_run + RESCALE_THRESHOLD;  // always true on the group's first block (m_run = -inf)
@@ -358,6 +392,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float2 nm2 = make_float2(-m_run, -m_run);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
       uint32_t pk[32];
+      if (TAIL) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk[i] = 0u;
+      }
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
         if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;  // chunks beyond the issued 16-key steps are never read
@@ -399,14 +437,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st_wait();
         }
       }
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;
-        const uint32_t addr = sPg + (uint32_t)((c8 ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[c8 * 4 + 0]), "r"(pk[c8 * 4 + 1]), "r"(pk[c8 * 4 + 2]),
-                     "r"(pk[c8 * 4 + 3])
-                     : "memory");
-      }
+      // P_j -> TMEM: register i of the row = keys (2i, 2i+1) = column i of P[grp] (columns beyond the tail's issued 16-key
+      // steps are never read by the product)
+      tmem_st_32x32b_x32(tPg, pk);
       } else {
       if (!first) {
         // P[grp] / O[grp] are free once the previous product of this group has completed
@@ -430,23 +463,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float2 nm2 = make_float2(-m_run, -m_run);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) break;  // chunks beyond the issued 16-key steps are never read
-        float2 t0 = __ffma2_rn(make_float2(s[c8 * 8 + 0], s[c8 * 8 + 1]), sc2, nm2);
-        float2 t1 = __ffma2_rn(make_float2(s[c8 * 8 + 2], s[c8 * 8 + 3]), sc2, nm2);
-        float2 t2 = __ffma2_rn(make_float2(s[c8 * 8 + 4], s[c8 * 8 + 5]), sc2, nm2);
-        float2 t3 = __ffma2_rn(make_float2(s[c8 * 8 + 6], s[c8 * 8 + 7]), sc2, nm2);
-        if (ATTN_POLY_PAIRS >= 4) t0 = ex2_poly2(t0); else { t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y); }
-        if (ATTN_POLY_PAIRS >= 3) t1 = ex2_poly2(t1); else { t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y); }
-        if (ATTN_POLY_PAIRS >= 2) t2 = ex2_poly2(t2); else { t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y); }
-        if (ATTN_POLY_PAIRS >= 1) t3 = ex2_poly2(t3); else { t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y); }
-        sum_a = __fadd2_rn(sum_a, t0);
-        sum_b = __fadd2_rn(sum_b, t1);
-        sum_a = __fadd2_rn(sum_a, t2);
-        sum_b = __fadd2_rn(sum_b, t3);
-        const uint32_t p0 = pack_bf16(t0.x, t0.y), p1 = pack_bf16(t1.x, t1.y), p2 = pack_bf16(t2.x, t2.y), p3 = pack_bf16(t3.x, t3.y);
-        const uint32_t addr = sPg + (uint32_t)((c8 ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+      for (int half = 0; half < 2; ++half) {   // 32 keys = 16 TMEM columns per tcgen05.st: only 16 packed words are live at a time
+        if (TAIL && half * 32 >= ((nk + 15) & ~15)) break;
+        uint32_t pk[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int c8 = half * 4 + c4;
+          if (TAIL && c8 * 8 >= ((nk + 15) & ~15)) {  // beyond the issued 16-key steps: never read
+            pk[c4 * 4 + 0] = pk[c4 * 4 + 1] = pk[c4 * 4 + 2] = pk[c4 * 4 + 3] = 0u;
+            continue;
+          }
+          float2 t0 = __ffma2_rn(make_float2(s[c8 * 8 + 0], s[c8 * 8 + 1]), sc2, nm2);
+          float2 t1 = __ffma2_rn(make_float2(s[c8 * 8 + 2], s[c8 * 8 + 3]), sc2, nm2);
+          float2 t2 = __ffma2_rn(make_float2(s[c8 * 8 + 4], s[c8 * 8 + 5]), sc2, nm2);
+          float2 t3 = __ffma2_rn(make_float2(s[c8 * 8 + 6], s[c8 * 8 + 7]), sc2, nm2);
+          if (ATTN_POLY_PAIRS >= 4) t0 = ex2_poly2(t0); else { t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y); }
+          if (ATTN_POLY_PAIRS >= 3) t1 = ex2_poly2(t1); else { t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y); }
+          if (ATTN_POLY_PAIRS >= 2) t2 = ex2_poly2(t2); else { t2.x = ex2_approx(t2.x); t2.y = ex2_approx(t2.y); }
+          if (ATTN_POLY_PAIRS >= 1) t3 = ex2_poly2(t3); else { t3.x = ex2_approx(t3.x); t3.y = ex2_approx(t3.y); }
+          sum_a = __fadd2_rn(sum_a, t0);
+          sum_b = __fadd2_rn(sum_b, t1);
+          sum_a = __fadd2_rn(sum_a, t2);
+          sum_b = __fadd2_rn(sum_b, t3);
+          pk[c4 * 4 + 0] = pack_bf16(t0.x, t0.y);
+          pk[c4 * 4 + 1] = pack_bf16(t1.x, t1.y);
+          pk[c4 * 4 + 2] = pack_bf16(t2.x, t2.y);
+          pk[c4 * 4 + 3] = pack_bf16(t3.x, t3.y);
+        }
+        tmem_st_32x32b_x16(tPg + (uint32_t)(half * 16), pk);
       }
       sum_a = __fadd2_rn(sum_a, sum_b);
       l_run = fmaf(l_run, alpha, sum_a.x + sum_a.y);
@@ -474,8 +518,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           ptx::mbar_arrive_elect(s_free(grp));
           if (!first) ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
         }
-        ptx::fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-        ptx::tc_fence_before();    // O rescale (tcgen05.st) ordered before the MMA that accumulates into O
+        tmem_st_wait();            // P (and a rescaled O) have landed in tensor memory ...
+        ptx::tc_fence_before();    // ... and are ordered before the MMA that reads / accumulates them
         __syncwarp();
         ptx::mbar_arrive_elect(p_full(grp));  // one arrival per warp: the group's P V issuer takes it from here
         __syncwarp();

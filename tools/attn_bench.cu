@@ -5,7 +5,11 @@
 #include <cstdlib>
 #include <vector>
 
+#ifdef ATTN_SRC  // A/B against an older revision of the kernel: -DATTN_SRC='"/tmp/old/attention_tc_v5.cu"' -I real-time-video-captioning_b200/csrc
+#include ATTN_SRC
+#else
 #include "../real-time-video-captioning_b200/csrc/attention_tc.cu"
+#endif
 
 static void run(const char* name, int n_groups, int glen, int heads, int iters) {
   const size_t rows = (size_t)n_groups * glen, W = (size_t)heads * 64;
@@ -63,7 +67,10 @@ static void run(const char* name, int n_groups, int glen, int heads, int iters) 
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 64;
   const int which = argc > 2 ? atoi(argv[2]) : 3;
-  if (which & 1) run("vit", B * 6, 197, 12, 10);
-  if (which & 2) run("dec", B, 1182, 12, 10);
+  const int iters = argc > 3 ? atoi(argv[3]) : 10;
+  if (which & 1) run("vit", B * 6, 197, 12, iters);
+  if (which & 2) run("dec", B, 1182, 12, iters);
+  if (which & 4) run("vit-L", B * 6, 257, 16, iters);
+  if (which & 8) run("dec-L24", B / 8 > 0 ? B / 8 : 1, 6168, 12, iters);
   return 0;
 }
