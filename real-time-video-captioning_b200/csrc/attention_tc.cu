@@ -1,32 +1,30 @@
 // tcgen05 flash attention over fixed-length row groups (ViT frames, K10: the decoder's visual block).
 //
-// One CTA = one (group, head, 128-query tile); two CTAs share an SM.  The keys of a group are cut into 64-key blocks
-// and the blocks are dealt alternately to TWO softmax warpgroups (even blocks -> group 0, odd blocks -> group 1).
-// Each warpgroup runs its own, completely independent online softmax for its blocks -- private running max m_g,
-// private row sum l_g and a private output accumulator O_g in TMEM -- so the two never exchange anything per block;
-// the two partial results are merged once at the end (the split-K identity of softmax).  Per block j (g = j & 1):
-//     S_j = Q K_j^T           tcgen05.mma  M=128, N<=64, K=64 (Q, K: K-major 128B-swizzled TMA tiles)  -> TMEM S[g]
-//     P_j = exp2(S_j*c - m_g) 4 warps, one query row per thread (tcgen05.ld 32x32b.x32), packed f32x2 FMA / add,
-//                             P written as bf16 pairs straight back into TENSOR MEMORY (tcgen05.st, 32 columns per group)
+// Work item = one (group, head, 128-query tile).  A CTA (two per SM) is persistent and keeps TWO items in flight: softmax
+// warpgroup g (4 warps, one query row per thread) owns item 2 * pair + g from its first key block to its output rows -- its
+// own Q tile, running max m_g / row sum l_g, output accumulator O[g] and probability buffer P[g], both in tensor memory.
+// The two groups never merge, exchange or wait for each other.  Per 64-key block j of a group's item:
+//     S_j = Q K_j^T           tcgen05.mma  M=128, N<=64, K=64 (Q, K: K-major 128B-swizzled TMA tiles)  -> TMEM S
+//     P_j = exp2(S_j*c - m_g) one query row per thread (tcgen05.ld 32x32b.x32), packed f32x2 FMA / add, P written as bf16
+//                             pairs straight back into TENSOR MEMORY (tcgen05.st, 32 columns per group)
 //     O_g += P_j V_j          tcgen05.mma with the A operand FROM TMEM (the "TS" form: lane = query row, one 32-bit column =
 //                             two consecutive keys), M=128, N=64, K<=64 (V: the TMA tile used as an MN-major B operand);
 //                             the accumulation stays in TMEM
-// P never touches shared memory (round 1 staged it there: 8 swizzled st.shared.v4 per row, a fence.proxy.async and a barrier
-// on every block of every group's serial chain, 32 KB of the CTA's shared memory).  TMEM map of a CTA (256 columns, two CTAs
-// per SM): S [0,64) -- ONE score buffer, handed to the two groups alternately: a group keeps it only for the ~150 cycles of
-// its tcgen05.ld --, O[0] [64,128), O[1] [128,192), P[0] [192,224), P[1] [224,256).
-// The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in
-// practice during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases
-// P_j.  No per-block read-back of O, no cross-warp max exchange, no named barrier inside the loop.
-// Warp 1 issues S_{j+2} as soon as group g reports that S[g] has been read into registers; the product O_g += P_j V_j
-// is issued by a thread of the warpgroup that wrote P_j (the one on TMEM lane quarter 0), so neither warpgroup ever
-// waits for the other and no thread polls.  K and V live in separate TMA rings (K_j is dead as soon as S_j
-// completes, V_j only after the PV product).
-// The last key block of a group issues only the 16-key steps that hold valid keys (197 = 3*64 + 5 -> N = 16).
+// TMEM map of a CTA (256 columns): S [0,64) -- ONE score buffer handed to the two groups alternately; a group keeps it only
+// for the ~100 cycles of its tcgen05.ld --, O[0] [64,128), O[1] [128,192), P[0] [192,224), P[1] [224,256).
+// The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in practice
+// during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases P_j.  No
+// per-block read-back of O, no cross-warp max exchange, no named barrier anywhere.
+// 12 warps: TMA producer (K / V tiles of the two items alternate in the rings), S issuer (operands first, then the
+// hand-over of the score buffer, then 4 UTCHMMA), one P V issuer per group (blocking wait on the group's p_full), 2 x 4
+// softmax warps (setmaxnreg 32 / 104).  The last key block of a group issues only the 16-key steps that hold valid keys
+// (197 = 3*64 + 5 -> N = 16); for >= 512 keys the exponentials run before the wait on the group's previous product and one
+// pair of every eight goes through a polynomial on the FMA pipe.
 //
-// History (profiles/): mma.sync kernel 123-222 TFLOP/s; first tcgen05 version (two threads per row, per-block O
-// read-back, shared-memory max exchange) 176 / 405 TFLOP/s at 11 issued instructions per exp2; this version issues
-// ~3.5 per exp2 and is bound by the exp2 (XU) rate.
+// History (profiles/): mma.sync kernel 123-222 TFLOP/s; first tcgen05 version (two threads per row, per-block O read-back,
+// shared-memory max exchange) 176 / 405 (ViT / decoder shape); round 1 final (two groups on alternate blocks of ONE item,
+// P staged in shared memory, partial softmaxes merged per item) 268 / 657; round 2: P in TMEM + TS-form MMA 290 / 670, then
+// one item per group (this file): see profiles/r02_attention_summary.md.
 #include <cuda.h>
 #include <math.h>
 
@@ -43,12 +41,13 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;   // query rows per CTA = TMEM lanes
 constexpr int BKV = 64;   // keys per block
-constexpr int K_STAGES = 4, V_STAGES = 6;  // P no longer lives in shared memory: its 32 KB went into deeper K / V rings
+constexpr int K_STAGES = 4, V_STAGES = 5;  // tiles of the two items in flight alternate in the rings (P no longer lives in shared memory)
 constexpr int Q_BYTES = BQ * 128;         // 16 KB
 constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB
-constexpr int N_BARRIERS = 2 + 2 * K_STAGES + 2 * V_STAGES + 8;
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 256 /*barriers + tmem slot*/ +
-                           2 * BQ * 8 /*(m, l) exchange*/;
+constexpr int N_BARRIERS = 4 + 2 * K_STAGES + 2 * V_STAGES + 8;
+constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 256 /*barriers + tmem slot*/;
+static_assert(8 * N_BARRIERS + 4 <= 256, "barrier block");
+static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 constexpr int NUM_SM_WARPS = 8;   // warps 4-7: softmax group 0, warps 8-11: group 1; TMEM lane quarter = warp & 3
 constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: S issuer + TMEM owner, warps 2 / 3: P V issuers
 constexpr int SERVICE_REGS = 32, SOFTMAX_REGS = 104;  // setmaxnreg split: the increase is served from the CTA's OWN pool (what its service
@@ -139,13 +138,6 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
   return r;
 }
-__device__ __forceinline__ void merge_bar_sync() {  // named barrier 1: all softmax warps
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * 8) : "memory");
-}
-__device__ __forceinline__ void merge_bar_sync2() {  // named barrier 4: all softmax warps, end of a work item
-  asm volatile("bar.sync 4, %0;" ::"n"(32 * 8) : "memory");
-}
-
 #ifndef ATTN_TRACE_ITEM
 #define ATTN_TRACE_ITEM 0
 #endif
@@ -167,33 +159,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     bf16* __restrict__ out, int ldo, int group_len, int heads, int n_groups, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);
-  const uint32_t sQ = smem_base;
-  auto sK = [&](int s) { return smem_base + Q_BYTES + s * KV_TILE_BYTES; };
-  auto sV = [&](int s) { return smem_base + Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
-  const uint32_t bar_base = smem_base + Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
-  const uint32_t q_full = bar_base, q_empty = bar_base + 8u;
-  auto k_full = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto k_empty = [&](int s) { return bar_base + 8u * (2 + K_STAGES + s); };
-  auto v_full = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + s); };
-  auto v_empty = [&](int s) { return bar_base + 8u * (2 + 2 * K_STAGES + V_STAGES + s); };
-  const uint32_t bar_g = bar_base + 8u * (2 + 2 * K_STAGES + 2 * V_STAGES);
-  auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S holds a new block of this group
+  auto sQ = [&](int g) { return smem_base + g * Q_BYTES; };
+  auto sK = [&](int s) { return smem_base + 2 * Q_BYTES + s * KV_TILE_BYTES; };
+  auto sV = [&](int s) { return smem_base + 2 * Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
+  const uint32_t bar_base = smem_base + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
+  auto q_full = [&](int g) { return bar_base + 8u * g; };
+  auto q_empty = [&](int g) { return bar_base + 8u * (2 + g); };
+  auto k_full = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (4 + K_STAGES + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (4 + 2 * K_STAGES + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (4 + 2 * K_STAGES + V_STAGES + s); };
+  const uint32_t bar_g = bar_base + 8u * (4 + 2 * K_STAGES + 2 * V_STAGES);
+  auto s_full = [&](int g) { return bar_g + 8u * g; };        // MMA -> softmax group g: S holds a new block of this group's item
   auto s_free = [&](int g) { return bar_g + 8u * (2 + g); };  // group g -> MMA: S has been read into registers
   auto p_full = [&](int g) { return bar_g + 8u * (4 + g); };  // group g -> its P V issuer: P[g] written to TMEM (and O[g] rescaled)
   auto o_full = [&](int g) { return bar_g + 8u * (6 + g); };  // MMA -> group g: O[g] += P V finished, P[g] is free
   const uint32_t tmem_slot = bar_base + 8u * N_BARRIERS;
-  const uint32_t sML = bar_base + 256;  // float2 [2 groups][128 rows]: (m, l) of each group's partial softmax
 
   const int warp = __shfl_sync(0xffffffffu, (int)threadIdx.x / 32, 0);
   const int lane = threadIdx.x & 31;
   const int width = heads * HD;
   const int n_blocks = (group_len + BKV - 1) / BKV;
-  // PERSISTENT: the CTA walks work items (query tile, head, group) with stride gridDim.x.  Barriers, TMEM and the K / V
-  // rings live across items, so the TMA producer and the S issuer run ahead into the next item while the softmax groups
-  // still finish the current one -- the ~3 us of per-CTA start-up (barrier init, TMEM allocation, first TMA round trip)
-  // and tear-down that a 4-block ViT tile used to pay once per tile is paid once per CTA.
+  // PERSISTENT, TWO ITEMS IN FLIGHT: the CTA walks PAIRS of work items (item = query tile x head x group) with stride
+  // gridDim.x; softmax group g owns item 2 * pair + g from its first key block to its output rows -- its own Q tile, running
+  // max / sum, O accumulator and P buffer -- so the two groups never merge, exchange or wait for each other (round 1 dealt
+  // the key blocks of ONE item alternately to the two groups and merged two partial softmaxes per item: two named barriers,
+  // a shared-memory exchange and cross reads of both accumulators per item, ~1000 cycles of a 4-block ViT item's ~6700).
+  // An item's result depends on nothing but its own data: bit-identical wherever it sits in the batch.
   const int n_qt = (group_len + BQ - 1) / BQ;
   const int n_items = n_qt * heads * n_groups;
+  const int n_pairs = (n_items + 1) / 2;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
@@ -201,8 +196,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   if (warp == 1) {
     if (lane == 0) {
-      ptx::mbar_init(q_full, 1);
-      ptx::mbar_init(q_empty, 1);
+      for (int g = 0; g < 2; ++g) {
+        ptx::mbar_init(q_full(g), 1);
+        ptx::mbar_init(q_empty(g), 1);
+      }
       for (int s = 0; s < K_STAGES; ++s) {
         ptx::mbar_init(k_full(s), 1);
         ptx::mbar_init(k_empty(s), 1);
@@ -236,93 +233,102 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
-    uint32_t kc = 0;  // key blocks loaded so far (all items): ring stage / phase of K and V follow from it
+    uint32_t kc = 0;  // K / V tiles loaded so far (all pairs, both items interleaved): ring stage / phase follow from it
     int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int qt = w % n_qt, h = (w / n_qt) % heads, g_idx = w / (n_qt * heads);
-      const int row0 = g_idx * group_len;
-      ptx::mbar_wait(q_empty, (uint32_t)((it & 1) ^ 1));  // every S product of the previous item has read Q
-      ptx::mbar_arrive_expect_tx_elect(q_full, Q_BYTES);
-      ptx::tma_load_2d_elect(sQ, &tmap_q, q_full, h * HD, row0 + qt * BQ);
-      for (int j = 0; j < n_blocks; ++j, ++kc) {
-        const int ks = kc % K_STAGES, vs = kc % V_STAGES;
-        ptx::mbar_wait(k_empty(ks), (uint32_t)(((kc / K_STAGES) & 1) ^ 1));
-        ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
-        ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h * HD, row0 + j * BKV);
-        ptx::mbar_wait(v_empty(vs), (uint32_t)(((kc / V_STAGES) & 1) ^ 1));
-        ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
-        ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h * HD, row0 + j * BKV);
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+      const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
+      int h2[2], row2[2];
+      for (int g = 0; g < n_it; ++g) {
+        const int w = 2 * p + g;
+        const int qt = w % n_qt;
+        h2[g] = (w / n_qt) % heads;
+        row2[g] = (w / (n_qt * heads)) * group_len;
+        ptx::mbar_wait(q_empty(g), (uint32_t)((it & 1) ^ 1));  // every S product of this group's previous item has read Q[g]
+        ptx::mbar_arrive_expect_tx_elect(q_full(g), Q_BYTES);
+        ptx::tma_load_2d_elect(sQ(g), &tmap_q, q_full(g), h2[g] * HD, row2[g] + qt * BQ);
+      }
+      for (int j = 0; j < n_blocks; ++j) {
+        for (int g = 0; g < n_it; ++g, ++kc) {
+          const int ks = kc % K_STAGES, vs = kc % V_STAGES;
+          ptx::mbar_wait(k_empty(ks), (uint32_t)(((kc / K_STAGES) & 1) ^ 1));
+          ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
+          ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h2[g] * HD, row2[g] + j * BKV);
+          ptx::mbar_wait(v_empty(vs), (uint32_t)(((kc / V_STAGES) & 1) ^ 1));
+          ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
+          ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h2[g] * HD, row2[g] + j * BKV);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ S issuer (whole warp, elected lane issues)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
-    const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ);
-    uint32_t kc = 0;             // key blocks issued so far (all items)
+    uint32_t kc = 0;                  // K / V tiles consumed so far
     uint32_t fills0 = 0, fills1 = 0;  // blocks handed to group 0 / group 1 so far
-    int prev_g = -1;             // group that received the previous block (it holds the single S buffer until it has read it)
+    int prev_g = -1;                  // group that received the previous block: it holds the single S buffer until it has read it
     int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      ptx::mbar_wait(q_full, (uint32_t)(it & 1));
-      ptx::tc_fence_after();
-      for (int j = 0; j < n_blocks; ++j, ++kc) {
-        const int g = j & 1;
-        if (prev_g >= 0) {  // the previous block (possibly of the previous item) has left S for its group's registers
-          ptx::mbar_wait(s_free(prev_g), ((prev_g ? fills1 : fills0) - 1) & 1u);
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+      const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
+      for (int j = 0; j < n_blocks; ++j) {
+        for (int g = 0; g < n_it; ++g, ++kc) {
+          const int ks = kc % K_STAGES;
+          const int nk = min(BKV, group_len - j * BKV);
+          const int nk16 = (nk + 15) & ~15;
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 0 + 6 * g);
+          // operands first (they have usually landed long ago), THEN the hand-over of the score buffer: nothing but the
+          // issue itself stands between "the previous block has left S" and the next product
+          if (j == 0) ptx::mbar_wait(q_full(g), (uint32_t)(it & 1));
+          ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
+          ptx::mbar_wait(v_full(kc % V_STAGES), (kc / V_STAGES) & 1u);  // s_full then also means "this block's V has landed"
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 1 + 6 * g);
+          if (prev_g >= 0) ptx::mbar_wait(s_free(prev_g), ((prev_g ? fills1 : fills0) - 1) & 1u);
           ptx::tc_fence_after();
-        }
-        // S_j = Q K_j^T over the head dim (4 steps of 16)
-        const int ks = kc % K_STAGES;
-        const int nk = min(BKV, group_len - j * BKV);
-        const int nk16 = (nk + 15) & ~15;
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 0);
-        ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
-        ptx::mbar_wait(v_full(kc % V_STAGES), (kc / V_STAGES) & 1u);  // s_full(j) then also means "V_j has landed"
-        ptx::tc_fence_after();
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 1);
-        const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
-        const uint32_t id_s = idesc_qk(nk16);
+          const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ(g));
+          const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
+          const uint32_t id_s = idesc_qk(nk16);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
-        ptx::umma_commit_elect(k_empty(ks));  // K_j is dead once S_j has been computed
-        ptx::umma_commit_elect(s_full(g));
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
-        if (g) ++fills1; else ++fills0;
-        prev_g = g;
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 2 + 6 * g);
+          ptx::umma_commit_elect(s_full(g));
+          ptx::umma_commit_elect(k_empty(ks));  // K is dead once the product has been computed
+          if (j + 1 == n_blocks) ptx::umma_commit_elect(q_empty(g));  // ... and so is Q[g] after the item's last block
+          if (it == ATTN_TRACE_ITEM) TRACE(j, 3 + 6 * g);
+          if (g) ++fills1; else ++fills0;
+          prev_g = g;
+        }
       }
-      ptx::umma_commit_elect(q_empty);  // Q may be replaced once every S product of this item has completed
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------ P V issuer of softmax group g = warp - 2 (whole warp,
     // elected lane issues): O[g] (+)= P_j V_j as soon as the four warps of the group have delivered P_j.  One issuer per
-    // group: each follows a single event stream with blocking waits (a shared, polling issuer spent 40 % of the kernel's
-    // issue slots spinning; issuing from a softmax warp made that warp 800 cycles per block slower than its three peers).
+    // group: each follows a single event stream with blocking waits.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
     const int g = warp - 2;
     const uint32_t tPg = tP + (uint32_t)(g * 32);
     uint32_t done = 0;
     int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const uint32_t kc0 = (uint32_t)it * (uint32_t)n_blocks;  // key blocks of earlier items: V ring position
-      for (int j = g; j < n_blocks; j += 2, ++done) {
-        const int vs = (int)((kc0 + (uint32_t)j) % V_STAGES);
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+      const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
+      if (g >= n_it) continue;
+      // V ring position of this item's block j: every earlier pair was complete (only the last pair of the grid can be half)
+      const uint32_t kc0 = (uint32_t)it * 2u * (uint32_t)n_blocks;
+      for (int j = 0; j < n_blocks; ++j, ++done) {
+        const int vs = (int)((kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j)) % V_STAGES);
         const int nk = min(BKV, group_len - j * BKV);
         const int nk16 = (nk + 15) & ~15;
         if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
         ptx::mbar_wait(p_full(g), done & 1u);
         ptx::tc_fence_after();
         if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
-        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // V_j is resident: the S issuer waited for it before S_j
-        const uint32_t acc0 = j == g ? 0u : 1u;               // the group's first block of an item starts a new O
+        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // resident: the S issuer waited for it before this block's S
+        const uint32_t acc0 = j == 0 ? 0u : 1u;               // the item's first block starts a new O
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 8 TMEM columns (bf16 pairs), V advances 2 atoms
           if (k * 16 < nk16)
             umma_bf16_ts_elect(tO + (uint32_t)(g * 64), tPg + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
         if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
-        ptx::umma_commit_elect(v_empty(vs));
         ptx::umma_commit_elect(o_full(g));
+        ptx::umma_commit_elect(v_empty(vs));
         if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
       }
     }
@@ -330,13 +336,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ------------------------------------------------------------ softmax warpgroups: one thread per query row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
     const int quarter = warp & 3;
-    const int grp = (warp - 4) >> 2;    // 0: even key blocks, 1: odd key blocks
+    const int grp = (warp - 4) >> 2;    // this group's item of every pair: 2 * pair + grp
     const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t tSg = tS + lane_off;
     const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
     const uint32_t tPg = tP + (uint32_t)(grp * 32) + lane_off;
-    const bool has1 = n_blocks > 1;
     uint32_t done = 0;  // key blocks this group has processed so far (all items): phase of s_full / o_full
     int it = 0;
     float m_run = -INFINITY, l_run = 0.f;
@@ -498,14 +503,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (it == ATTN_TRACE_ITEM) TRACE(j, 4);
     };
 
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
+      const int w = 2 * p + grp;
+      if (w >= n_items) continue;  // the grid's last pair may hold one item only
       const int qt = w % n_qt, h = (w / n_qt) % heads, g_idx = w / (n_qt * heads);
       const int row0 = g_idx * group_len, q0 = qt * BQ;
       const bool warp_has_rows = q0 + quarter * 32 < group_len;  // warp-uniform
       m_run = -INFINITY;
       l_run = 0.f;
-      for (int j = grp; j < n_blocks; j += 2, ++done) {
-        const bool first = j == grp;
+      for (int j = 0; j < n_blocks; ++j, ++done) {
+        const bool first = j == 0;
         ptx::mbar_wait(s_full(grp), done & 1u);
         ptx::tc_fence_after();
         if (warp_has_rows) {
@@ -524,58 +531,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_arrive_elect(p_full(grp));  // one arrival per warp: the group's P V issuer takes it from here
         __syncwarp();
       }
-      // ---- merge the two partial softmaxes: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1),  w_g = 2^(m_g - max m)
-      if (grp == 0 || has1) {
-        // every thread has followed all phases of its OWN group's o_full barrier, so this parity wait is exact; the other
-        // group's last product is covered by that group's threads before they reach the named barrier below
-        ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
-      }
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sML + (uint32_t)(grp * BQ + r) * 8u), "f"(m_run), "f"(l_run) : "memory");
-      merge_bar_sync();
+      // ---- the item's output rows: O[grp] / l once the last product has completed
+      if (it == ATTN_TRACE_ITEM) TRACE(31, 5);
+      ptx::mbar_wait(o_full(grp), (done - 1) & 1u);
       ptx::tc_fence_after();
+      if (it == ATTN_TRACE_ITEM) TRACE(31, 6);
       if (warp_has_rows) {
-        float m_o, l_o;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_o), "=f"(l_o) : "r"(sML + (uint32_t)((grp ^ 1) * BQ + r) * 8u) : "memory");
-        const float m0 = grp == 0 ? m_run : m_o, m1 = grp == 0 ? m_o : m_run;
-        const float l0 = grp == 0 ? l_run : l_o, l1 = grp == 0 ? l_o : l_run;
-        const float m = has1 ? fmaxf(m0, m1) : m0;
-        float w0 = ex2_approx(m0 - m), w1 = has1 ? ex2_approx(m1 - m) : 0.f;
-        const float inv = 1.f / (l0 * w0 + (has1 ? l1 * w1 : 0.f));
-        w0 *= inv;
-        w1 *= inv;
-        // this thread writes output dims [32 grp, 32 grp + 32) of its row
-        uint32_t a[32];
-        float o[32];
-        ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)(grp * 32), a);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(a[i]) * w0;
-        if (has1) {
-          ptx::tmem_ld_32x32b_x32(tO + 64u + lane_off + (uint32_t)(grp * 32), a);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(a[i]), w1, o[i]);
-        }
-        // both accumulators and the (m, l) exchange are in registers: the next item may overwrite them
-        ptx::tc_fence_before();
-        merge_bar_sync2();
+        const float inv = 1.f / l_run;
         const int q = q0 + r;
-        if (q < group_len) {
-          uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD + grp * 32);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 u;
-            u.x = pack_bf16(o[c * 8 + 0], o[c * 8 + 1]);
-            u.y = pack_bf16(o[c * 8 + 2], o[c * 8 + 3]);
-            u.z = pack_bf16(o[c * 8 + 4], o[c * 8 + 5]);
-            u.w = pack_bf16(o[c * 8 + 6], o[c * 8 + 7]);
-            dst[c] = u;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(tOg + (uint32_t)(half * 32), a);
+          ptx::tmem_ld_wait();
+          if (q < group_len) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 u;
+              u.x = pack_bf16(__uint_as_float(a[c * 8 + 0]) * inv, __uint_as_float(a[c * 8 + 1]) * inv);
+              u.y = pack_bf16(__uint_as_float(a[c * 8 + 2]) * inv, __uint_as_float(a[c * 8 + 3]) * inv);
+              u.z = pack_bf16(__uint_as_float(a[c * 8 + 4]) * inv, __uint_as_float(a[c * 8 + 5]) * inv);
+              u.w = pack_bf16(__uint_as_float(a[c * 8 + 6]) * inv, __uint_as_float(a[c * 8 + 7]) * inv);
+              dst[half * 4 + c] = u;
+            }
           }
         }
-      } else {
-        ptx::tc_fence_before();
-        merge_bar_sync2();
+        if (it == ATTN_TRACE_ITEM) TRACE(31, 10);
       }
+      // O[grp] is in registers / memory: the next item's first product (issued only after this warp's next p_full arrival,
+      // which follows this fence in program order) may overwrite it
+      ptx::tc_fence_before();
     }
   }
 
@@ -605,8 +591,9 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BQ, &tq)) return cudaErrorInvalidValue;
   if (!gemm_get_tensor_map(qkv, rows, 3 * heads * HD, ld_qkv, HD, BKV, &tkv)) return cudaErrorInvalidValue;
   const int n_items = ((group_len + BQ - 1) / BQ) * heads * n_groups;
-  int grid = 2 * gemm_sm_count();  // two CTAs per SM (TMEM: 2 x 256 columns), each walks items with stride `grid`
-  if (n_items < grid) grid = n_items;
+  const int n_pairs = (n_items + 1) / 2;
+  int grid = 2 * gemm_sm_count();  // two CTAs per SM (TMEM: 2 x 256 columns), each walks pairs of items with stride `grid`
+  if (n_pairs < grid) grid = n_pairs;
   const float sl2 = scale * 1.4426950408889634f;
 #ifdef ATTN_FORCE_POLY_PAIRS
   attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, (ATTN_FORCE_POLY_PAIRS > 0)><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);

@@ -43,22 +43,28 @@ static void run(const char* name, int n_groups, int glen, int heads, int iters) 
   const int nb = (glen + 63) / 64;
   long long t0 = 0;
   for (int w = 4; w < 12; ++w) {
-    const long long v = t[(w * 32 + (w >= 8)) * 12];
+    const long long v = t[(w * 32 + 0) * 12];
     if (v && (!t0 || v < t0)) t0 = v;
   }
-  printf("clk since the item's first block started | softmax warp: s_ready ld_done max_done exp_or_wait_done p_done\n");
-  for (int j = 0; j < nb && j < 32; ++j) {
-    const long long* r = &t[(1 * 32 + j) * 12];
-    printf("blk %2d S-issue: start %lld operands_ready %lld mma_issued %lld committed %lld\n", j, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0);
-    r = &t[((2 + (j & 1)) * 32 + j) * 12];
-    printf("blk %2d PV-issue: wait_start %lld p_full %lld mma_issued %lld committed %lld\n", j, r[5] - t0, r[6] - t0, r[9] - t0, r[7] - t0);
-    for (int w = 4; w < 12; ++w) {
-      if (((w - 4) >> 2) != (j & 1)) continue;
-      r = &t[(w * 32 + j) * 12];
-      printf("blk %2d warp %2d:", j, w);
-      for (int p = 0; p < 5; ++p) printf(" %7lld", r[p] ? r[p] - t0 : -1);
-      printf("\n");
+  printf("clk since the pair's first block started | softmax warp: s_ready ld_done max_done exp_or_wait_done p_done\n");
+  for (int j = 0; j < nb && j < 30; ++j) {
+    for (int g = 0; g < 2; ++g) {
+      const long long* r = &t[(1 * 32 + j) * 12];
+      printf("blk %2d g%d S-issue: start %lld operands_ready %lld mma_issued %lld committed %lld\n", j, g, r[0 + 6 * g] - t0, r[1 + 6 * g] - t0,
+             r[2 + 6 * g] - t0, r[3 + 6 * g] - t0);
+      r = &t[((2 + g) * 32 + j) * 12];
+      printf("blk %2d g%d PV-issue: wait_start %lld p_full %lld mma_issued %lld committed %lld\n", j, g, r[5] - t0, r[6] - t0, r[9] - t0, r[7] - t0);
+      for (int w = 4 + 4 * g; w < 8 + 4 * g; ++w) {
+        r = &t[(w * 32 + j) * 12];
+        printf("blk %2d g%d warp %2d:", j, g, w);
+        for (int p = 0; p < 5; ++p) printf(" %7lld", r[p] ? r[p] - t0 : -1);
+        printf("\n");
+      }
     }
+  }
+  for (int w = 4; w < 12; ++w) {
+    const long long* r = &t[(w * 32 + 31) * 12];
+    printf("epilogue warp %2d: enter %lld last_product_done %lld stored %lld\n", w, r[5] - t0, r[6] - t0, r[10] - t0);
   }
 #endif
   cudaFree(qkv); cudaFree(out);
