@@ -15,9 +15,10 @@
 // The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in practice
 // during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases P_j.  No
 // per-block read-back of O, no cross-warp max exchange, no named barrier anywhere.
-// 12 warps: TMA producer (K / V tiles of the two items alternate in the rings), S issuer (operands first, then the
-// hand-over of the score buffer, then 4 UTCHMMA), one P V issuer per group (blocking wait on the group's p_full), 2 x 4
-// softmax warps (setmaxnreg 32 / 104).  The last key block of a group issues only the 16-key steps that hold valid keys
+// 12 warps: TMA producer (K / V tiles of the two items alternate in the rings), one MMA issuer per group (S_j: operands first,
+// then the hand-over of the score buffer, then 4 UTCHMMA; after it the product of the group's previous block), a spare, 2 x 4
+// softmax warps (setmaxnreg 32 / 104).  Output rows leave through a small swizzled staging slice per warp so that every
+// global store instruction writes whole 64-byte runs.  The last key block of a group issues only the 16-key steps that hold valid keys
 // (197 = 3*64 + 5 -> N = 16); for >= 512 keys the exponentials run before the wait on the group's previous product and one
 // pair of every eight goes through a polynomial on the FMA pipe.
 //
@@ -41,15 +42,16 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;   // query rows per CTA = TMEM lanes
 constexpr int BKV = 64;   // keys per block
-constexpr int K_STAGES = 4, V_STAGES = 5;  // tiles of the two items in flight alternate in the rings (P no longer lives in shared memory)
+constexpr int K_STAGES = 3, V_STAGES = 4;  // tiles of the two items in flight alternate in the rings
+constexpr int STAGE_BYTES = 8 * 32 * 64;    // output staging: per softmax warp 32 rows x 32 dims bf16 (coalesced epilogue stores)
 constexpr int Q_BYTES = BQ * 128;         // 16 KB
 constexpr int KV_TILE_BYTES = BKV * 128;  // 8 KB
 constexpr int N_BARRIERS = 4 + 2 * K_STAGES + 2 * V_STAGES + 8;
-constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + 256 /*barriers + tmem slot*/;
+constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES + STAGE_BYTES + 256 /*barriers + tmem slot*/;
 static_assert(8 * N_BARRIERS + 4 <= 256, "barrier block");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 constexpr int NUM_SM_WARPS = 8;   // warps 4-7: softmax group 0, warps 8-11: group 1; TMEM lane quarter = warp & 3
-constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warp 1: S issuer + TMEM owner, warps 2 / 3: P V issuers
+constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warps 1 / 2: MMA issuers of group 0 / 1 (warp 1 owns TMEM), warp 3: spare
 constexpr int SERVICE_REGS = 32, SOFTMAX_REGS = 104;  // setmaxnreg split: the increase is served from the CTA's OWN pool (what its service
                                                       // warps released; more than that deadlocks), so 128 x 32 + 256 x 104 = 30720 = the launch allocation 384 x 80
 constexpr int TMEM_COLS = 256;    // S: [0,64), O[0]: [64,128), O[1]: [128,192), P[0]: [192,224), P[1]: [224,256)
@@ -162,7 +164,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   auto sQ = [&](int g) { return smem_base + g * Q_BYTES; };
   auto sK = [&](int s) { return smem_base + 2 * Q_BYTES + s * KV_TILE_BYTES; };
   auto sV = [&](int s) { return smem_base + 2 * Q_BYTES + (K_STAGES + s) * KV_TILE_BYTES; };
-  const uint32_t bar_base = smem_base + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
+  const uint32_t sStage = smem_base + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_BYTES;
+  const uint32_t bar_base = sStage + STAGE_BYTES;
   auto q_full = [&](int g) { return bar_base + 8u * g; };
   auto q_empty = [&](int g) { return bar_base + 8u * (2 + g); };
   auto k_full = [&](int s) { return bar_base + 8u * (4 + s); };
@@ -259,85 +262,84 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ S issuer (whole warp, elected lane issues)
+  } else if (warp < 3) {
+    // ------------------------------------------------------------ MMA issuer of softmax group g = warp - 1 (whole warp,
+    // elected lane issues): for its group's item, S_j = Q K_j^T into the shared score buffer and O[g] (+)= P_{j-1} V_{j-1},
+    // in that order.  One issuer per group: a single issuer for both groups spent ~850 cycles per block in its waits
+    // (each mbarrier wait costs ~100 cycles even when the phase has long completed), commits and issues -- with two groups
+    // to feed that was the pace of the whole kernel (traces in profiles/r02_attention_summary.md).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
-    uint32_t kc = 0;                  // K / V tiles consumed so far
-    uint32_t fills0 = 0, fills1 = 0;  // blocks handed to group 0 / group 1 so far
-    int prev_g = -1;                  // group that received the previous block: it holds the single S buffer until it has read it
-    int it = 0;
-    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
-      const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
-      for (int j = 0; j < n_blocks; ++j) {
-        for (int g = 0; g < n_it; ++g, ++kc) {
-          const int ks = kc % K_STAGES;
-          const int nk = min(BKV, group_len - j * BKV);
-          const int nk16 = (nk + 15) & ~15;
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 0 + 6 * g);
-          // operands first (they have usually landed long ago), THEN the hand-over of the score buffer: nothing but the
-          // issue itself stands between "the previous block has left S" and the next product
-          if (j == 0) ptx::mbar_wait(q_full(g), (uint32_t)(it & 1));
-          ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
-          ptx::mbar_wait(v_full(kc % V_STAGES), (kc / V_STAGES) & 1u);  // s_full then also means "this block's V has landed"
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 1 + 6 * g);
-          if (prev_g >= 0) ptx::mbar_wait(s_free(prev_g), ((prev_g ? fills1 : fills0) - 1) & 1u);
-          ptx::tc_fence_after();
-          const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ(g));
-          const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
-          const uint32_t id_s = idesc_qk(nk16);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 2 + 6 * g);
-          ptx::umma_commit_elect(s_full(g));
-          ptx::umma_commit_elect(k_empty(ks));  // K is dead once the product has been computed
-          if (j + 1 == n_blocks) ptx::umma_commit_elect(q_empty(g));  // ... and so is Q[g] after the item's last block
-          if (it == ATTN_TRACE_ITEM) TRACE(j, 3 + 6 * g);
-          if (g) ++fills1; else ++fills0;
-          prev_g = g;
-        }
-      }
-    }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------ P V issuer of softmax group g = warp - 2 (whole warp,
-    // elected lane issues): O[g] (+)= P_j V_j as soon as the four warps of the group have delivered P_j.  One issuer per
-    // group: each follows a single event stream with blocking waits.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
-    const int g = warp - 2;
+    const int g = warp - 1;
     const uint32_t tPg = tP + (uint32_t)(g * 32);
-    uint32_t done = 0;
+    const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ(g));
+    uint32_t mine = 0;  // blocks of this group issued so far (all items): S hand-over / p_full phases follow from it
+    uint32_t pv_done = 0;
     int it = 0;
+    auto issue_pv = [&](int j, uint32_t kc0, int n_it) {
+      const int vs = (int)((kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j)) % V_STAGES);
+      const int nk = min(BKV, group_len - j * BKV);
+      const int nk16 = (nk + 15) & ~15;
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
+      ptx::mbar_wait(p_full(g), pv_done & 1u);
+      ptx::tc_fence_after();
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
+      const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // resident: this warp waited for it before the block's S product
+      const uint32_t acc0 = j == 0 ? 0u : 1u;               // the item's first block starts a new O
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 8 TMEM columns (bf16 pairs), V advances 2 atoms
+        if (k * 16 < nk16)
+          umma_bf16_ts_elect(tO + (uint32_t)(g * 64), tPg + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
+      ptx::umma_commit_elect(o_full(g));
+      ptx::umma_commit_elect(v_empty(vs));
+      if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
+      ++pv_done;
+    };
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
       const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
       if (g >= n_it) continue;
-      // V ring position of this item's block j: every earlier pair was complete (only the last pair of the grid can be half)
+      // ring position of this item's block j: every earlier pair was complete (only the last pair of the grid can be half)
       const uint32_t kc0 = (uint32_t)it * 2u * (uint32_t)n_blocks;
-      for (int j = 0; j < n_blocks; ++j, ++done) {
-        const int vs = (int)((kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j)) % V_STAGES);
+      for (int j = 0; j < n_blocks; ++j, ++mine) {
+        const uint32_t kc = kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j);
+        const int ks = (int)(kc % K_STAGES);
         const int nk = min(BKV, group_len - j * BKV);
         const int nk16 = (nk + 15) & ~15;
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
-        ptx::mbar_wait(p_full(g), done & 1u);
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 0);
+        // operands first (they have usually landed long ago), THEN the hand-over of the score buffer
+        if (j == 0) ptx::mbar_wait(q_full(g), (uint32_t)(it & 1));
+        ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
+        ptx::mbar_wait(v_full((int)(kc % V_STAGES)), (kc / V_STAGES) & 1u);  // s_full then also means "this block's V has landed"
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 1);
+        // the block before this one in the CTA's sequence (the other group's, or -- in a half pair -- this group's own
+        // previous block) must have left S for its group's registers
+        if (n_it == 2 || j == 0) {
+          if (g == 1) ptx::mbar_wait(s_free(0), mine & 1u);                       // group 0's block with the same index
+          else if (mine > 0) ptx::mbar_wait(s_free(1), (mine - 1) & 1u);          // group 1's previous block
+        } else {
+          ptx::mbar_wait(s_free(0), (mine - 1) & 1u);
+        }
         ptx::tc_fence_after();
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
-        const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // resident: the S issuer waited for it before this block's S
-        const uint32_t acc0 = j == 0 ? 0u : 1u;               // the item's first block starts a new O
+        const uint64_t dk = ptx::umma_desc_sw128_kmajor(sK(ks));
+        const uint32_t id_s = idesc_qk(nk16);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 8 TMEM columns (bf16 pairs), V advances 2 atoms
-          if (k * 16 < nk16)
-            umma_bf16_ts_elect(tO + (uint32_t)(g * 64), tPg + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 9);
-        ptx::umma_commit_elect(o_full(g));
-        ptx::umma_commit_elect(v_empty(vs));
-        if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
+        ptx::umma_commit_elect(s_full(g));
+        ptx::umma_commit_elect(k_empty(ks));  // K is dead once the product has been computed
+        if (j + 1 == n_blocks) ptx::umma_commit_elect(q_empty(g));  // ... and so is Q[g] after the item's last block
+        if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
+        if (j > 0) issue_pv(j - 1, kc0, n_it);
       }
+      issue_pv(n_blocks - 1, kc0, n_it);
     }
+  } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));  // spare warp: only donates its registers
   } else {
     // ------------------------------------------------------------ softmax warpgroups: one thread per query row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
     const int quarter = warp & 3;
     const int grp = (warp - 4) >> 2;    // this group's item of every pair: 2 * pair + grp
-    const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const uint32_t tSg = tS + lane_off;
     const uint32_t tOg = tO + (uint32_t)(grp * 64) + lane_off;
@@ -537,25 +539,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tc_fence_after();
       if (it == ATTN_TRACE_ITEM) TRACE(31, 6);
       if (warp_has_rows) {
+        // O[grp] / l -> bf16 -> this warp's staging slice (32 rows x 32 dims, 16-byte chunks XOR-swizzled so that both the row-wise
+        // writes and the 8-rows-per-instruction reads are bank-conflict free) -> global memory with 4 lanes per 64-byte run
+        // of a row.  (One 16-byte store per lane straight from the row's registers touched 32 different 128-byte lines per
+        // instruction: 8 such instructions per thread kept the warps ~2500 cycles in the LSU replay queue per item.)
         const float inv = 1.f / l_run;
-        const int q = q0 + r;
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q) * ldo + h * HD);
+        const uint32_t stage = sStage + (uint32_t)((warp - 4) * 2048);
+        const int rows_left = group_len - (q0 + quarter * 32);  // valid rows of this warp's slice (may exceed 32)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t a[32];
           ptx::tmem_ld_32x32b_x32(tOg + (uint32_t)(half * 32), a);
           ptx::tmem_ld_wait();
-          if (q < group_len) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 u;
-              u.x = pack_bf16(__uint_as_float(a[c * 8 + 0]) * inv, __uint_as_float(a[c * 8 + 1]) * inv);
-              u.y = pack_bf16(__uint_as_float(a[c * 8 + 2]) * inv, __uint_as_float(a[c * 8 + 3]) * inv);
-              u.z = pack_bf16(__uint_as_float(a[c * 8 + 4]) * inv, __uint_as_float(a[c * 8 + 5]) * inv);
-              u.w = pack_bf16(__uint_as_float(a[c * 8 + 6]) * inv, __uint_as_float(a[c * 8 + 7]) * inv);
-              dst[half * 4 + c] = u;
-            }
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t u0 = pack_bf16(__uint_as_float(a[c * 8 + 0]) * inv, __uint_as_float(a[c * 8 + 1]) * inv);
+            const uint32_t u1 = pack_bf16(__uint_as_float(a[c * 8 + 2]) * inv, __uint_as_float(a[c * 8 + 3]) * inv);
+            const uint32_t u2 = pack_bf16(__uint_as_float(a[c * 8 + 4]) * inv, __uint_as_float(a[c * 8 + 5]) * inv);
+            const uint32_t u3 = pack_bf16(__uint_as_float(a[c * 8 + 6]) * inv, __uint_as_float(a[c * 8 + 7]) * inv);
+            const uint32_t addr = stage + (uint32_t)(lane * 64) + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2), c = lane & 3;
+            uint4 u;
+            const uint32_t addr = stage + (uint32_t)(row * 64) + (uint32_t)((c ^ ((row >> 1) & 3)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+            if (row < rows_left)
+              *reinterpret_cast<uint4*>(out + (size_t)(row0 + q0 + quarter * 32 + row) * ldo + h * HD + half * 32 + c * 8) = u;
+          }
+          __syncwarp();
         }
         if (it == ATTN_TRACE_ITEM) TRACE(31, 10);
       }

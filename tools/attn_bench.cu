@@ -49,11 +49,9 @@ static void run(const char* name, int n_groups, int glen, int heads, int iters) 
   printf("clk since the pair's first block started | softmax warp: s_ready ld_done max_done exp_or_wait_done p_done\n");
   for (int j = 0; j < nb && j < 30; ++j) {
     for (int g = 0; g < 2; ++g) {
-      const long long* r = &t[(1 * 32 + j) * 12];
-      printf("blk %2d g%d S-issue: start %lld operands_ready %lld mma_issued %lld committed %lld\n", j, g, r[0 + 6 * g] - t0, r[1 + 6 * g] - t0,
-             r[2 + 6 * g] - t0, r[3 + 6 * g] - t0);
-      r = &t[((2 + g) * 32 + j) * 12];
-      printf("blk %2d g%d PV-issue: wait_start %lld p_full %lld mma_issued %lld committed %lld\n", j, g, r[5] - t0, r[6] - t0, r[9] - t0, r[7] - t0);
+      const long long* r = &t[((1 + g) * 32 + j) * 12];
+      printf("blk %2d g%d S-issue: start %lld operands_ready %lld mma_issued %lld committed %lld | PV-issue: wait_start %lld p_full %lld committed %lld\n",
+             j, g, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[5] - t0, r[6] - t0, r[7] - t0);
       for (int w = 4 + 4 * g; w < 8 + 4 * g; ++w) {
         r = &t[(w * 32 + j) * 12];
         printf("blk %2d g%d warp %2d:", j, g, w);
