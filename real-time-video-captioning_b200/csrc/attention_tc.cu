@@ -15,8 +15,8 @@
 // The running max is LAZY: m_g only moves when a block's maximum exceeds it by more than 2^8; then (rarely, in practice
 // during the first blocks only) the warp rescales O_g in TMEM (tcgen05.ld / tcgen05.st) before it releases P_j.  No
 // per-block read-back of O, no cross-warp max exchange, no named barrier anywhere.
-// 12 warps: TMA producer (K / V tiles of the two items alternate in the rings), one MMA issuer per group (S_j: operands first,
-// then the hand-over of the score buffer, then 4 UTCHMMA; after it the product of the group's previous block), a spare, 2 x 4
+// 12 warps: two TMA producers (Q + K, and V: tiles of the two items alternate in the rings), one MMA issuer per group (S_j: operands first,
+// then the hand-over of the score buffer, then 4 UTCHMMA; after it the product of the group's previous block), 2 x 4
 // softmax warps (setmaxnreg 32 / 104).  Output rows leave through a small swizzled staging slice per warp so that every
 // global store instruction writes whole 64-byte runs.  The last key block of a group issues only the 16-key steps that hold valid keys
 // (197 = 3*64 + 5 -> N = 16); for >= 512 keys the exponentials run before the wait on the group's previous product and one
@@ -51,7 +51,7 @@ constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + (K_STAGES + V_STAGES) * KV_TILE_
 static_assert(8 * N_BARRIERS + 4 <= 256, "barrier block");
 static_assert(2 * (SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
 constexpr int NUM_SM_WARPS = 8;   // warps 4-7: softmax group 0, warps 8-11: group 1; TMEM lane quarter = warp & 3
-constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warps 1 / 2: MMA issuers of group 0 / 1 (warp 1 owns TMEM), warp 3: spare
+constexpr int NUM_THREADS = 128 + 32 * NUM_SM_WARPS;  // warp 0: TMA, warps 1 / 2: MMA issuers of group 0 / 1 (warp 1 owns TMEM), warp 3: TMA producer of V
 constexpr int SERVICE_REGS = 32, SOFTMAX_REGS = 104;  // setmaxnreg split: the increase is served from the CTA's OWN pool (what its service
                                                       // warps released; more than that deadlocks), so 128 x 32 + 256 x 104 = 30720 = the launch allocation 384 x 80
 constexpr int TMEM_COLS = 256;    // S: [0,64), O[0]: [64,128), O[1]: [128,192), P[0]: [192,224), P[1]: [224,256)
@@ -155,6 +155,10 @@ __device__ long long g_attn_trace[12 * 32 * 12];
 #define TRACE(blk, ph) do { } while (0)
 #endif
 
+// SHARE_KV: the two items of a pair that are query tiles of the same (group, head) read ONE copy of every K / V tile (half the
+// TMA traffic, twice the ring depth in key blocks).  Measured (tools/attn_bench.cu, same box): +4 % at 1182 keys, +5 % at 6168
+// keys, but -8 % / -12 % on the 197- / 257-key ViT shapes (a stage is then released by the slower of the two groups) ->
+// on for long groups only, together with EXP_FIRST.
 template <int ATTN_POLY_PAIRS, bool EXP_FIRST>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -192,6 +196,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int n_qt = (group_len + BQ - 1) / BQ;
   const int n_items = n_qt * heads * n_groups;
   const int n_pairs = (n_items + 1) / 2;
+  constexpr bool SHARE_KV = EXP_FIRST;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
@@ -205,11 +210,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
       for (int s = 0; s < K_STAGES; ++s) {
         ptx::mbar_init(k_full(s), 1);
-        ptx::mbar_init(k_empty(s), 1);
+        ptx::mbar_init(k_empty(s), 2);  // both groups' products when the pair shares its K / V tiles, one group twice otherwise
       }
       for (int s = 0; s < V_STAGES; ++s) {
         ptx::mbar_init(v_full(s), 1);
-        ptx::mbar_init(v_empty(s), 1);
+        ptx::mbar_init(v_empty(s), 2);
       }
       for (int g = 0; g < 2; ++g) {
         ptx::mbar_init(s_full(g), 1);
@@ -234,12 +239,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t tS = tmem_base + TM_S, tO = tmem_base + TM_O, tP = tmem_base + TM_P;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    // ------------------------------------------------------------ TMA producer of Q and K (whole warp, elected lane issues).
+    // V tiles have their own producer (warp 3): a V stage is only released by the P V product, ~2000 cycles after its load; in one
+    // in-order producer a full V ring also held back the K tiles the next score product was waiting for.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
-    uint32_t kc = 0;  // K / V tiles loaded so far (all pairs, both items interleaved): ring stage / phase follow from it
+    uint32_t kc = 0;  // K tiles loaded so far (all pairs): ring stage / phase follow from it
     int it = 0;
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
       const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
+      // the two items of a pair are usually two query tiles of the SAME (group, head): then they share every K / V tile
+      const int n_kv = (n_it == 2 && (!SHARE_KV || (2 * p) / n_qt != (2 * p + 1) / n_qt)) ? 2 : 1;
       int h2[2], row2[2];
       for (int g = 0; g < n_it; ++g) {
         const int w = 2 * p + g;
@@ -251,14 +260,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::tma_load_2d_elect(sQ(g), &tmap_q, q_full(g), h2[g] * HD, row2[g] + qt * BQ);
       }
       for (int j = 0; j < n_blocks; ++j) {
-        for (int g = 0; g < n_it; ++g, ++kc) {
-          const int ks = kc % K_STAGES, vs = kc % V_STAGES;
+        for (int g = 0; g < n_kv; ++g, ++kc) {
+          const int ks = kc % K_STAGES;
           ptx::mbar_wait(k_empty(ks), (uint32_t)(((kc / K_STAGES) & 1) ^ 1));
           ptx::mbar_arrive_expect_tx_elect(k_full(ks), KV_TILE_BYTES);
           ptx::tma_load_2d_elect(sK(ks), &tmap_kv, k_full(ks), width + h2[g] * HD, row2[g] + j * BKV);
-          ptx::mbar_wait(v_empty(vs), (uint32_t)(((kc / V_STAGES) & 1) ^ 1));
-          ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
-          ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h2[g] * HD, row2[g] + j * BKV);
         }
       }
     }
@@ -274,16 +280,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint64_t dq = ptx::umma_desc_sw128_kmajor(sQ(g));
     uint32_t mine = 0;  // blocks of this group issued so far (all items): S hand-over / p_full phases follow from it
     uint32_t pv_done = 0;
+    uint32_t kc0 = 0;     // ring position of the current pair's first K / V tile
+    bool single = false;  // the current pair holds one item only (the grid's last pair)
     int it = 0;
-    auto issue_pv = [&](int j, uint32_t kc0, int n_it) {
-      const int vs = (int)((kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j)) % V_STAGES);
+    auto issue_pv = [&](int j, uint32_t kc0, int n_kv) {
+      const uint32_t kcv = kc0 + (uint32_t)(n_kv == 2 ? 2 * j + g : j);
+      const int vs = (int)(kcv % V_STAGES);
       const int nk = min(BKV, group_len - j * BKV);
       const int nk16 = (nk + 15) & ~15;
       if (it == ATTN_TRACE_ITEM) TRACE(j, 5);
+      ptx::mbar_wait(v_full(vs), (kcv / V_STAGES) & 1u);  // landed long ago as a rule: checked while the group still computes P
       ptx::mbar_wait(p_full(g), pv_done & 1u);
       ptx::tc_fence_after();
       if (it == ATTN_TRACE_ITEM) TRACE(j, 6);
-      const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));  // resident: this warp waited for it before the block's S product
+      const uint64_t dv = umma_desc_sw128_mnmajor(sV(vs));
       const uint32_t acc0 = j == 0 ? 0u : 1u;               // the item's first block starts a new O
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k)  // 16 keys per step: P advances 8 TMEM columns (bf16 pairs), V advances 2 atoms
@@ -291,16 +301,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           umma_bf16_ts_elect(tO + (uint32_t)(g * 64), tPg + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_pv(), k != 0 ? 1u : acc0);
       ptx::umma_commit_elect(o_full(g));
       ptx::umma_commit_elect(v_empty(vs));
+      if (n_kv == 2 || single) ptx::umma_commit_elect(v_empty(vs));  // sole reader of this V tile: both arrivals
       if (it == ATTN_TRACE_ITEM) TRACE(j, 7);
       ++pv_done;
     };
     for (int p = blockIdx.x; p < n_pairs; p += gridDim.x, ++it) {
       const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
-      if (g >= n_it) continue;
-      // ring position of this item's block j: every earlier pair was complete (only the last pair of the grid can be half)
-      const uint32_t kc0 = (uint32_t)it * 2u * (uint32_t)n_blocks;
+      const int n_kv = (n_it == 2 && (!SHARE_KV || (2 * p) / n_qt != (2 * p + 1) / n_qt)) ? 2 : 1;  // tiles per key block: shared by the pair or one per item
+      single = n_it == 1;
+      if (g >= n_it) continue;  // (the last pair: nothing follows, kc0 needs no update)
       for (int j = 0; j < n_blocks; ++j, ++mine) {
-        const uint32_t kc = kc0 + (uint32_t)(n_it == 2 ? 2 * j + g : j);
+        const uint32_t kc = kc0 + (uint32_t)(n_kv == 2 ? 2 * j + g : j);
         const int ks = (int)(kc % K_STAGES);
         const int nk = min(BKV, group_len - j * BKV);
         const int nk16 = (nk + 15) & ~15;
@@ -308,7 +319,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // operands first (they have usually landed long ago), THEN the hand-over of the score buffer
         if (j == 0) ptx::mbar_wait(q_full(g), (uint32_t)(it & 1));
         ptx::mbar_wait(k_full(ks), (kc / K_STAGES) & 1u);
-        ptx::mbar_wait(v_full((int)(kc % V_STAGES)), (kc / V_STAGES) & 1u);  // s_full then also means "this block's V has landed"
         if (it == ATTN_TRACE_ITEM) TRACE(j, 1);
         // the block before this one in the CTA's sequence (the other group's, or -- in a half pair -- this group's own
         // previous block) must have left S for its group's registers
@@ -326,15 +336,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           ptx::umma_bf16_elect(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), id_s, k != 0);
         if (it == ATTN_TRACE_ITEM) TRACE(j, 2);
         ptx::umma_commit_elect(s_full(g));
-        ptx::umma_commit_elect(k_empty(ks));  // K is dead once the product has been computed
+        ptx::umma_commit_elect(k_empty(ks));  // K is dead once the product(s) reading it have been computed
+        if (n_kv == 2 || single) ptx::umma_commit_elect(k_empty(ks));  // sole reader of this K tile: both arrivals
         if (j + 1 == n_blocks) ptx::umma_commit_elect(q_empty(g));  // ... and so is Q[g] after the item's last block
         if (it == ATTN_TRACE_ITEM) TRACE(j, 3);
-        if (j > 0) issue_pv(j - 1, kc0, n_it);
+        if (j > 0) issue_pv(j - 1, kc0, n_kv);
       }
-      issue_pv(n_blocks - 1, kc0, n_it);
+      issue_pv(n_blocks - 1, kc0, n_kv);
+      kc0 += (uint32_t)(n_kv * n_blocks);
     }
   } else if (warp == 3) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));  // spare warp: only donates its registers
+    // ------------------------------------------------------------ TMA producer of V
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
+    uint32_t kc = 0;
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const int n_it = (2 * p + 1 < n_items) ? 2 : 1;
+      const int n_kv = (n_it == 2 && (!SHARE_KV || (2 * p) / n_qt != (2 * p + 1) / n_qt)) ? 2 : 1;
+      int h2[2], row2[2];
+      for (int g = 0; g < n_it; ++g) {
+        const int w = 2 * p + g;
+        h2[g] = (w / n_qt) % heads;
+        row2[g] = (w / (n_qt * heads)) * group_len;
+      }
+      for (int j = 0; j < n_blocks; ++j) {
+        for (int g = 0; g < n_kv; ++g, ++kc) {
+          const int vs = kc % V_STAGES;
+          ptx::mbar_wait(v_empty(vs), (uint32_t)(((kc / V_STAGES) & 1) ^ 1));
+          ptx::mbar_arrive_expect_tx_elect(v_full(vs), KV_TILE_BYTES);
+          ptx::tma_load_2d_elect(sV(vs), &tmap_kv, v_full(vs), 2 * width + h2[g] * HD, row2[g] + j * BKV);
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ softmax warpgroups: one thread per query row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SOFTMAX_REGS));
