@@ -283,6 +283,72 @@ def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=3)
     return out
 
 
+def distill_leg(g, gm, torch, dist, world, rank, local_rank, dev, steps=10, warmup=3):
+    """BASELINE.json configs[4]: one distillation training step per GPU -- the frozen GIT-large teacher (shipped config: ViT-L/14, 6
+    frames) gives teacher-forced logits for 8 clips x 20 caption tokens (forward_output_logits, model.py:896), the student
+    DECODER (config.py:76-84) runs forward + KL/CE loss + backward + Adam on the library, gradients are all-reduced over the
+    ranks (DDP average; the vocabulary-head bucket overlaps the layers' backward).  The student's TinyViT encoder is not part
+    of the library: `memory` is synthetic."""
+    sm = importlib.import_module("real-time-video-captioning_b200.student")
+    param = {"image_encoder_type": "CLIPViT_L_14", "visual_feature_size": 1024, "num_image_with_embedding": 6}
+    teacher = gm.GenerativeImageTextTeacher.from_random_init(param, device=dev)
+    torch.manual_seed(0)
+    student = sm.StudentCandidateV1(None, 576, 8, 1024, 0.3, 2, 30522, 101, 102).to(dev)
+    trainer = sm.DistillationTrainer(teacher, student, lr=1e-4)
+    B, L = 8, 20
+    gen = torch.Generator(device=dev).manual_seed(500 + rank)
+    x = torch.randn(B, 6, 3, RES, RES, device=dev, generator=gen)
+    y = torch.randint(1000, 30000, (B, L), device=dev, generator=gen)
+    y[:, 0] = 101
+    mem = torch.randn(B, 6, 576, device=dev, generator=gen)
+    batch = {"frames": x, "caption": y, "memory": mem}
+    stream = torch.cuda.current_stream(dev)
+    losses = []
+    for _ in range(warmup):
+        losses.append(trainer.training_step(batch))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record(stream)
+    for _ in range(steps):
+        losses.append(trainer.training_step(batch))
+    e[1].record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e[0].elapsed_time(e[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    # the student's share, timed on its own with fixed teacher logits; and the bare gradient all-reduce
+    t_logits = trainer.teacher_logits(x, y)
+    torch.cuda.synchronize(dev)
+    e[0].record(stream)
+    for _ in range(steps):
+        student.distillation_step(y, mem, t_logits)
+    e[1].record(stream)
+    torch.cuda.synchronize(dev)
+    student_ms = e[0].elapsed_time(e[1]) / steps
+    ar_ms = None
+    if world > 1:
+        gbuf = student._grads
+        dist.barrier()
+        e[0].record(stream)
+        for _ in range(steps):
+            dist.all_reduce(gbuf)
+        e[1].record(stream)
+        torch.cuda.synchronize(dev)
+        ar_ms = e[0].elapsed_time(e[1]) / steps
+    out = {"workload": "BASELINE.json configs[4]: distillation step, GIT-large (6-frame) teacher logits + student decoder fwd/bwd/Adam, DDP gradient all-reduce",
+           "clips_per_gpu_per_step": B, "caption_tokens": L, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+           "value": world * B / (ms * 1e-3), "unit": "clips/s (training)", "student_fwd_bwd_adam_allreduce_ms": student_ms,
+           "teacher_share": 1.0 - student_ms / ms, "gradient_floats": int(student._grads.numel()),
+           "allreduce_bytes_per_step": int(student._grads.numel()) * 4 if world > 1 else 0, "bare_allreduce_ms": ar_ms,
+           "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "dropout": "not applied (DESIGN.md)"}
+    del trainer, teacher, student
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -546,6 +612,7 @@ def main():
         legs["large_f24"] = dict(config_leg(g, gm, torch, dist, "large_f24", large24, 32, 24, greedy, 3, 2, world, rank, local_rank, dev,
                                             5123.70, 113.7, peaks), workload="BASELINE.json configs[3]: GIT-large (ViT-L/14) 24-frame clips, greedy max 15 + prefill-only sweep")
         legs["e2e_teacher_forward"] = teacher_forward_leg(g, gm, torch, dist, base_param, 256, world, rank, dev)
+        legs["distill_step"] = distill_leg(g, gm, torch, dist, world, rank, local_rank, dev)
 
     if rank != 0:
         if world > 1:
