@@ -434,29 +434,17 @@ def main():
         eng.set_early_exit(args.early_exit)
     if args.pipeline == 0:
         eng.reserve(B, FRAMES, args.beam, args.max_steps)
-    if args.graph:
-        eng.set_graph_max_clips(B)
-        eng.set_early_exit(0)  # a captured step cannot poll the host
-        torch.cuda.set_stream(torch.cuda.Stream(dev))  # graphs need a capturable (non-default) stream
-    config["cuda_graph_step"] = bool(args.graph)
+    if args.no_graphs:
+        eng.set_graph_segments(False)
+    config["cuda_graphs"] = "off (eager launches)" if args.no_graphs else "encode + visual pass per frame buffer, decode loop per 4-step segment (finished-clip poll between segments)"
 
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    n_sets = 2 if not args.graph else 1  # a graph replays one set of buffers
+    n_sets = 2  # alternate between resident frame batches
     frames = [torch.randn(B, FRAMES, 3, RES, RES, device=dev, generator=gen) for _ in range(n_sets)]
     stream = torch.cuda.current_stream(dev)
-    out_bufs = None
-    if args.graph:  # persistent output buffers: identical call signatures replay the captured graph
-        import ctypes as _c
-        out_bufs = (torch.empty(B, 1, args.max_steps, dtype=torch.int32, device=dev), torch.empty(B, 1, dtype=torch.float32, device=dev))
-        csp_g = sp.to_c()
 
     def caption_local(i):
-        if out_bufs is None:
-            return eng.caption(frames[i % n_sets], sp)[:2]
-        rc = eng.lib.gitb200_caption(eng.h, _c.c_void_p(frames[0].data_ptr()), B, FRAMES, _c.byref(csp_g), _c.c_void_p(out_bufs[0].data_ptr()),
-                                     _c.c_void_p(out_bufs[1].data_ptr()), None, _c.c_void_p(stream.cuda_stream))
-        assert rc == 0, eng.lib.gitb200_last_error(eng.h)
-        return out_bufs
+        return eng.caption(frames[i % n_sets], sp)[:2]
 
     def step(i):
         # C2: the caption tokens of all ranks are gathered (the path's only collective) -- asynchronously, one packed buffer
@@ -469,16 +457,13 @@ def main():
 
     eng.launch_count(reset=True)
     per_step_launches = 0
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 2 * n_sets)):  # every frame buffer's graphs are captured on its second use
         step(i).wait()
         if i == 0:
             per_step_launches = eng.launch_count()  # an eager step: what a graph replay re-issues without passing the counter
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    eng.launch_count(reset=True)
     graph0 = int(eng.lib.gitb200_graph_launches(eng.h))
-    if not args.graph:
-        eng.lib.gitb200_profile_gemm(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     handles = [step(i) for i in range(args.steps)]
@@ -487,11 +472,21 @@ def main():
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = eng.launch_count()
-    graph_step_replays = int(eng.lib.gitb200_graph_launches(eng.h)) - graph0
-    if args.graph and graph_step_replays > 0:  # a replay re-issues the captured launches without passing the library's counter
-        launches += graph_step_replays * per_step_launches
+    graph_replays_timed = int(eng.lib.gitb200_graph_launches(eng.h)) - graph0
+    # every kernel of the step is this library's: a step issues `per_step_launches` of them (counted on the first, eager warm-up
+    # step), whether they reach the GPU one by one or inside graph replays
+    launches = per_step_launches * args.steps
+    # ---- second, PROFILED pass of the same K steps for the roofline numbers: per-launch CUDA events around every GEMM and every
+    # decode-step attention launch on the launching stream (the events keep those steps out of the CUDA graphs)
     import ctypes
+    eng.lib.gitb200_profile_gemm(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for i in range(args.steps):
+        caption_local(i)
+    p1.record(stream)
+    sync_all()
+    ms_prof = p0.elapsed_time(p1)
     g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     eng.lib.gitb200_profile_gemm_read(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n))
     a_ms, a_by, a_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -514,7 +509,8 @@ def main():
     if args.quick:
         if rank == 0:
             emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                  "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "graph_step_replays": graph_step_replays,
+                  "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "graph_replays": graph_replays_timed,
+                  "ms_per_step_profiled_pass": ms_prof / args.steps,
                   "gemm_ms": g_ms.value, "gemm_tflops": g_fl.value / max(g_ms.value, 1e-9) / 1e9})
         if world > 1:
             dist.destroy_process_group()
@@ -634,7 +630,9 @@ def main():
                 "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
                 "traffic_note": "avg DRAM read+write bytes per launch of the 4 ViT-layer GEMMs at M=151296 (one 128-clip sub-batch of the 512-clip step; algorithmic average 1.049 GB; profiles/r01_gemm2_traffic.json)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
-                "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / ms if ms > 0 else None,
+                "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / ms_prof if ms_prof > 0 else None,
+                "timed_in": "a second pass of the same K steps with per-launch CUDA events on the launching stream (eager launches)",
+                "ms_per_step_profiled_pass": ms_prof / args.steps,
                 "algorithmic_gflop_per_clip": GFLOP_PER_CLIP,
                 "path_tflops_algorithmic": path_tflops,
                 # whole path against the tensor peak alone, and against BASELINE.md section 3's tensor + HBM model
@@ -656,7 +654,7 @@ def main():
                        "traffic_note": "dram read+write bytes per launch, ncu capture of the first decode step's 6 launches at 512 clips (profiles/r01_text_attention_traffic.json)",
                        "peak_source": f"{src} hbm_gbs (copy bandwidth)", "launches_timed": a_n.value,
                        "algorithmic_bytes_per_launch": (a_by.value / a_n.value) if a_n.value else None,
-                       "share_of_step": (a_ms.value / ms) if ms > 0 else None}
+                       "share_of_step": (a_ms.value / ms_prof) if ms_prof > 0 else None}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -666,7 +664,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches, "graph_replays_in_timed_region": graph_replays_timed,
             "e2e": e2e, "e2e_fp32_frames": e2e_f32, "gathered_tokens_match_local_shard": gathered_ok,
             "roofline": roofline, "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline, "latency_ms_p50_single_clip": p50,
             "latency_cuda_graph_replays": graph_replays, "latency_ms_p50_streaming_new_frame_to_caption": p50_stream,

@@ -116,6 +116,11 @@ int gitb200_last_decode_steps(const gitb200_ctx* ctx);
 /* gitb200_caption calls of up to `max_clips` clips are captured into CUDA graphs (default 8: the launch-bound latency
  * mode).  Larger values also graph throughput-sized batches once gitb200_reserve has pinned the workspaces. */
 int gitb200_set_graph_max_clips(gitb200_ctx* ctx, int max_clips);
+/* Batches above that size are graphed in pieces that do not depend on the caller's output pointers (default on): encode +
+ * visual pass per frame buffer (host paths: per staged chunk), the decode loop per segment of `every_steps` steps with the
+ * finished-clip poll between segments.  The ~1200 launches of a 512-clip step reach the GPU as a handful of graph launches.
+ * Calls on the legacy default stream run on the context's own stream, forked from / joined into the caller's.  0 = eager. */
+int gitb200_set_graph_segments(gitb200_ctx* ctx, int enable);
 
 /* Opt-in (default off): ViT ln_1 / ln_2 folded into the following QKV / fc1 GEMM: the GEMM reads the raw residual stream, its
  * weights carry gamma, its bias carries W*beta, and its epilogue applies rstd*(acc - mean*colsum) from row statistics

@@ -90,7 +90,7 @@ struct gitb200_ctx {
   std::vector<Buf<bf16>> kv;      // per decoder layer: [n_clips*Nv, 3H]
   std::vector<Buf<bf16>> txt_kv;  // per decoder layer: [max_len][rows][2H]
   Buf<bf16> tx, tq, ta, tb, tc, tf;
-  Buf<float> logits, partial, vf_in_f32, stats_a, stats_b;  // stats_*: [rows, 2] row sums for the folded LayerNorms
+  Buf<float> logits, partial, vf_in_f32, stats_a, stats_b;  // stats_*: [rows, 2 W / 256, 2] partial row sums for the folded LayerNorms
   Buf<int> ibuf;       // search ints
   Buf<double> dbuf;    // search doubles
   Buf<float> fbuf;     // search floats
@@ -103,15 +103,16 @@ struct gitb200_ctx {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_user = nullptr;
 
   // CUDA graphs for the launch-bound small-batch calls (latency mode): a call signature is captured on its second
-  // occurrence and replayed afterwards.  kind: 0 caption, 1 stream_push, 2 stream_caption.
+  // occurrence and replayed afterwards.  kind: 0 caption (small batch, whole call), 1 stream_push, 2 stream_caption, 3 stream_push_u8,
+  // 5 decode-step segment, 6 encode + visual pass of a device-resident batch, 7 / 8 encode of a host chunk (fp32 / raw uint8), 9 visual pass.
   struct GraphKey {
     int kind = -1;
     const void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
-    int i0 = 0, i1 = 0, i2 = 0;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
     gitb200_search_params sp{};
     bool operator==(const GraphKey& o) const {
-      return kind == o.kind && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && i0 == o.i0 && i1 == o.i1 && i2 == o.i2 &&
-             memcmp(&sp, &o.sp, sizeof(sp)) == 0;
+      return kind == o.kind && p0 == o.p0 && p1 == o.p1 && p2 == o.p2 && i0 == o.i0 && i1 == o.i1 && i2 == o.i2 && i3 == o.i3 &&
+             i4 == o.i4 && i5 == o.i5 && memcmp(&sp, &o.sp, sizeof(sp)) == 0;
     }
   };
   struct GraphEntry {
@@ -133,8 +134,8 @@ struct gitb200_ctx {
   // decode of one chunk overlaps the tensor bound encode of the next.
   gitb200_ctx* twin = nullptr;
   bool is_twin = false;
-  bool fold_ln = false;     // opt-in: ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); +1 % measured, and the
-                            // atomically accumulated row statistics make results run-to-run non-bit-exact -> default off
+  bool fold_ln = false;     // ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); the row statistics are partial sums per
+                            // 128-column half tile stored by the producing GEMM and added in slot order by the consumer: bit-reproducible
   int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
   // Large batches walk the ViT / the decoder's visual pass in sub-batches of about this many token rows (0: one sweep).
   // 151296 = 128 six-frame GIT-base clips.  Throughput-neutral from 128 clips up (A/B on one box, 512 clips per step:
@@ -157,7 +158,12 @@ struct gitb200_ctx {
   int early_exit_every = 4;
   int* h_done = nullptr;             // pinned
   int last_decode_steps = 0;         // decode steps the last gitb200_decode / _caption call enqueued
-  int graph_max_clips = 8;           // calls of up to this many clips are captured into CUDA graphs (latency mode)
+  int graph_max_clips = 8;           // calls of up to this many clips are captured into ONE CUDA graph (latency mode)
+  // Larger batches are graphed in pieces that do not depend on the caller's output pointers: encode (+ visual pass) per
+  // frame buffer, and the decode loop in segments of `early_exit_every` steps with the finished-clip poll between them --
+  // the ~1200 launches of a step reach the GPU as a handful of graph launches (+2-4 % at 512 clips, same-box A/B).
+  bool graph_segments = true;
+  cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr;
 
   // current state
   int cur_clips = 0, cur_nv = 0;     // visual features held in vf
@@ -339,13 +345,13 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   // ln_pre (in place semantics: x <- ln_pre(x)); the residual stream starts from the normalised tokens
   const bool fold = c->fold_ln && rows >= 1024;  // the folded-LayerNorm epilogue lives in the CTA-pair GEMM
   if (fold) {
-    ENSURE(c, c->stats_a, (size_t)rows * 2);
-    ENSURE(c, c->stats_b, (size_t)rows * 2);
+    ENSURE(c, c->stats_a, (size_t)rows * 2 * (2 * W / 256));
+    ENSURE(c, c->stats_b, (size_t)rows * 2 * (2 * W / 256));
   }
   {
     LayerNormArgs a;
     a.x = c->x.p; a.ldx = W; a.rows = rows; a.cols = W; a.gamma = c->ln_pre_g; a.beta = c->ln_pre_b; a.eps = k.vit_ln_eps;
-    a.out = c->lnb.p; a.ldo = W; a.stats_out = fold ? c->stats_a.p : nullptr;
+    a.out = c->lnb.p; a.ldo = W; a.stats_out = fold ? c->stats_a.p : nullptr; a.stats_slots = 2 * W / 256;
     CUDA_OK(c, layernorm_bf16(a, s));
   }
   std::swap(c->x.p, c->lnb.p);
@@ -370,7 +376,6 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
         TRY(gemm(c, g, s));
       }
       CUDA_OK(c, attention_groups_tc(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
-      CUDA_OK(c, cudaMemsetAsync(c->stats_b.p, 0, (size_t)rows * 2 * sizeof(float), s));
       {
         GemmArgs g = linear(c->attn.p, W, L.w_out, W, rows, W, L.b_out, c->x.p, W);
         g.residual = c->x.p; g.ldr = W; g.stats_out = c->stats_b.p;
@@ -381,7 +386,6 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
         g.act = ACT_QUICK_GELU; g.ln_stats = c->stats_b.p; g.ln_colsum = L.cs_fc1; g.ln_eps = k.vit_ln_eps;
         TRY(gemm(c, g, s));
       }
-      CUDA_OK(c, cudaMemsetAsync(c->stats_a.p, 0, (size_t)rows * 2 * sizeof(float), s));
       {
         GemmArgs g = linear(c->mlp.p, 4 * W, L.w_fc2, 4 * W, rows, W, L.b_fc2, c->x.p, W);
         g.residual = c->x.p; g.ldr = W; g.stats_out = c->stats_a.p;
@@ -664,6 +668,77 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
   return 0;
 }
 
+bool graph_stream_ok(cudaStream_t s) { return s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread; }
+
+// Runs `body` (a sequence of launches on stream s).  First occurrence of `key`: eager.  Second: captured into a graph,
+// instantiated and launched.  Later: replayed.  Any capture failure disables graphs for this context (eager for good).
+template <class Body>
+int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s, bool eligible, Body&& body) {
+  if (!eligible || !c->graphs_enabled || !c->tap_layers.empty() || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
+  {  // inside somebody else's capture (the whole-call graph of the latency mode): just contribute the launches
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return body();
+    }
+  }
+  // drop every graph captured before the last workspace reallocation / launch-sequence switch
+  for (size_t i = 0; i < c->graphs.size();) {
+    if (c->graphs[i].gen != c->ws_gen) {
+      if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
+      c->graphs.erase(c->graphs.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  gitb200_ctx::GraphEntry* ent = nullptr;
+  for (auto& g : c->graphs)
+    if (g.key == key) ent = &g;
+  if (ent && ent->exec) {
+    CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
+    c->graph_launches++;
+    return 1;  // replayed: the caller restores whatever host-side state `body` would have left
+  }
+  if (!ent) {
+    if (c->graphs.size() >= 64) {
+      for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      c->graphs.clear();
+    }
+    gitb200_ctx::GraphEntry e;
+    e.key = key;
+    const int r = body();  // every workspace gets sized by this eager run
+    e.gen = c->ws_gen;     // (read after the run: its own first-time allocations do not count against it)
+    c->graphs.push_back(e);
+    return r;
+  }
+  cudaGraph_t graph = nullptr;
+  const unsigned long long gen0 = c->ws_gen;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+    const int r = body();
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (c->ws_gen != gen0) {
+      // a workspace moved while capturing (cannot happen after the sizing run, but never keep such a graph): run eagerly
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ent->gen = c->ws_gen;
+      return body();
+    }
+    if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
+      cudaGraphDestroy(graph);
+      CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
+      c->graph_launches++;
+      return 0;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  cudaGetLastError();
+  ent->exec = nullptr;
+  c->graphs_enabled = false;
+  return body();
+}
+
+
 int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unused, int eos, const gitb200_search_params& sp,
                       SearchState* st) {
   (void)sos_unused;
@@ -704,8 +779,6 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
   if (!c->visual_pass_done) TRY(run_visual_pass(c, false, nullptr, 0, s));
   TRY(ensure_text(c, rows, rows, sp.max_steps));
   if (!logits_out) ENSURE(c, c->logits, (size_t)rows * c->vocab_pad);
-  CUDA_OK(c, search_init(st, k.sos, s));
-  int parity = 0;
   // model.py:640 `if all(done): break`: every `early_exit_every` steps the host reads the device's count of finished clips
   // (4 bytes, one stream synchronisation) and stops enqueueing decode steps once every clip is done.  Finished clips no
   // longer change, so the result is the same as running all steps; skipped while the stream is being captured into a graph.
@@ -717,20 +790,36 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
     if (poll_done && !c->h_done) CUDA_OK(c, cudaMallocHost(&c->h_done, sizeof(int)));
   }
   c->last_decode_steps = 0;
-  for (int t = 0; t + 1 < sp.max_steps; ++t) {  // model.py:518: while cur_len < max_length, cur_len = t + 1
-    TextPass tp;
-    tp.n_clips = B; tp.rows_per_clip = nb; tp.max_len = sp.max_steps;
-    tp.tokens = st.cur_tok; tp.positions = nullptr; tp.pos_const = t;
-    tp.n_text = nullptr; tp.n_text_const = t + 1;
-    tp.anc = sp.reorder_cache ? (parity ? st.anc_tmp : st.anc) : nullptr;
-    tp.slot_div = 1; tp.n_slots = rows; tp.slot_is_clip = 0;
-    tp.logits = logits_out ? logits_out + (size_t)t * rows * c->vocab_pad : c->logits.p;
-    tp.hidden_out = nullptr;
-    TRY(run_text_pass(c, tp, s));
-    CUDA_OK(c, search_step(st, tp.logits, t + 1, parity, s));
-    parity ^= 1;
-    c->last_decode_steps = t + 1;
-    if (poll_done && (t + 1) % c->early_exit_every == 0 && t + 2 < sp.max_steps) {
+  const int steps = sp.max_steps - 1;  // model.py:518: while cur_len < max_length, cur_len = t + 1
+  // The loop runs in segments of `early_exit_every` steps (all steps when polling is off).  A segment touches only
+  // context-owned buffers, so it is captured into a CUDA graph on its second occurrence and replayed from then on; the
+  // poll of the finished-clip count sits between segments.  Saved logits go to a caller buffer: eager.
+  const int seg = (poll_done && c->early_exit_every < steps) ? c->early_exit_every : steps;
+  const bool graphable = c->graph_segments && logits_out == nullptr && B > c->graph_max_clips;
+  for (int t0 = 0; t0 < steps; t0 += seg) {
+    const int n = steps - t0 < seg ? steps - t0 : seg;
+    gitb200_ctx::GraphKey key;
+    key.kind = 5; key.i0 = B; key.i1 = t0; key.i2 = n; key.i3 = c->cur_nv; key.sp = sp;
+    const int r = run_graphed(c, key, s, graphable, [&]() -> int {
+      if (t0 == 0) CUDA_OK(c, search_init(st, k.sos, s));
+      for (int t = t0; t < t0 + n; ++t) {
+        const int parity = t & 1;
+        TextPass tp;
+        tp.n_clips = B; tp.rows_per_clip = nb; tp.max_len = sp.max_steps;
+        tp.tokens = st.cur_tok; tp.positions = nullptr; tp.pos_const = t;
+        tp.n_text = nullptr; tp.n_text_const = t + 1;
+        tp.anc = sp.reorder_cache ? (parity ? st.anc_tmp : st.anc) : nullptr;
+        tp.slot_div = 1; tp.n_slots = rows; tp.slot_is_clip = 0;
+        tp.logits = logits_out ? logits_out + (size_t)t * rows * c->vocab_pad : c->logits.p;
+        tp.hidden_out = nullptr;
+        TRY(run_text_pass(c, tp, s));
+        CUDA_OK(c, search_step(st, tp.logits, t + 1, parity, s));
+      }
+      return 0;
+    });
+    if (r != 0 && r != 1) return r;
+    c->last_decode_steps = t0 + n;
+    if (poll_done && t0 + n < steps) {
       CUDA_OK(c, cudaMemcpyAsync(c->h_done, st.done_count, sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_OK(c, cudaStreamSynchronize(s));
       if (*c->h_done >= B) break;
@@ -819,67 +908,82 @@ int caption_pipelined(gitb200_ctx* c, const float* frames, int n_clips, int n_fr
   return 0;
 }
 
-bool graph_stream_ok(cudaStream_t s) { return s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread; }
+int effective_frames(const gitb200_ctx* c, int n_frames) {
+  const int n = c->cfg.num_image_with_embedding;
+  return (n > 0 && n_frames > n) ? n : n_frames;
+}
 
-// Runs `body` (a sequence of launches on stream s).  First occurrence of `key`: eager.  Second: captured into a graph,
-// instantiated and launched.  Later: replayed.  Any capture failure disables graphs for this context (eager for good).
-template <class Body>
-int run_graphed(gitb200_ctx* c, const gitb200_ctx::GraphKey& key, cudaStream_t s, bool eligible, Body&& body) {
-  if (!eligible || !c->graphs_enabled || !c->tap_layers.empty() || !graph_stream_ok(s) || gemm_profile_enabled()) return body();
-  // drop every graph captured before the last workspace reallocation / launch-sequence switch
-  for (size_t i = 0; i < c->graphs.size();) {
-    if (c->graphs[i].gen != c->ws_gen) {
-      if (c->graphs[i].exec) cudaGraphExecDestroy(c->graphs[i].exec);
-      c->graphs.erase(c->graphs.begin() + i);
-    } else {
-      ++i;
+int ensure_host_streams(gitb200_ctx* c) {
+  if (!c->copy_stream) {
+    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
   }
-  gitb200_ctx::GraphEntry* ent = nullptr;
-  for (auto& g : c->graphs)
-    if (g.key == key) ent = &g;
-  if (ent && ent->exec) {
-    CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
-    c->graph_launches++;
-    return 1;  // replayed: the caller restores whatever host-side state `body` would have left
+  // the legacy default stream would serialise with the copy stream; compute runs on a private one
+  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  if (!c->ev_user) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+  if (!c->ev_gfork) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_gfork, cudaEventDisableTiming));
+  if (!c->ev_gjoin) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_gjoin, cudaEventDisableTiming));
+  return 0;
+}
+
+// The decoder's pass over the visual tokens of the clips now held in vf (fills the visual K/V cache), graphed for large batches.
+int visual_pass_graphed(gitb200_ctx* c, cudaStream_t s) {
+  gitb200_ctx::GraphKey key;
+  key.kind = 9; key.i0 = c->cur_clips; key.i1 = c->cur_nv;
+  const int r = run_graphed(c, key, s, c->graph_segments && c->cur_clips > c->graph_max_clips,
+                            [&]() { return run_visual_pass(c, false, nullptr, 0, s); });
+  if (r == 1) {  // replayed: host-side state the eager run would have left
+    c->visual_pass_done = true;
+    c->visual_pass_full = 0;
+    return 0;
   }
-  if (!ent) {
-    if (c->graphs.size() >= 64) {
-      for (auto& g : c->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-      c->graphs.clear();
-    }
-    gitb200_ctx::GraphEntry e;
-    e.key = key;
-    const int r = body();  // every workspace gets sized by this eager run
-    e.gen = c->ws_gen;     // (read after the run: its own first-time allocations do not count against it)
-    c->graphs.push_back(e);
-    return r;
+  return r;
+}
+
+// Frames from the HOST (fp32 preprocessed, or raw uint8 BGR): chunks of `chunk_clips` clips are copied on the copy stream into
+// two staging buffers and encoded on `comp` as they arrive (the copy of chunk i+1 overlaps the ViT of chunk i; a small first
+// chunk keeps the un-overlapped head of the transfer short); then the decoder's visual pass over all clips.  For large
+// batches every chunk's encode and the visual pass are CUDA graphs (the staging buffers are context-owned: stable pointers).
+int encode_from_host(gitb200_ctx* c, const float* f32_host, const uint8_t* u8_host, int height, int width, int n_clips, int n_frames,
+                     int chunk_clips, cudaStream_t comp) {
+  const size_t clip_elems = u8_host ? (size_t)n_frames * height * width * 3 : (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
+  const size_t elem = u8_host ? 1 : sizeof(float);
+  for (int i = 0; i < 2; ++i) {
+    if (u8_host) ENSURE(c, c->stage_u8[i], (size_t)chunk_clips * clip_elems);
+    else ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
   }
-  cudaGraph_t graph = nullptr;
-  const unsigned long long gen0 = c->ws_gen;
-  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-    const int r = body();
-    const cudaError_t e = cudaStreamEndCapture(s, &graph);
-    if (c->ws_gen != gen0) {
-      // a workspace moved while capturing (cannot happen after the sizing run, but never keep such a graph): run eagerly
-      if (graph) cudaGraphDestroy(graph);
-      cudaGetLastError();
-      ent->gen = c->ws_gen;
-      return body();
+  const bool graphs = c->graph_segments && n_clips > c->graph_max_clips;
+  const int F = effective_frames(c, n_frames);
+  int done = 0, ch = 0;
+  while (done < n_clips) {
+    const int b = ch & 1;
+    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
+    if (nc > n_clips - done) nc = n_clips - done;
+    void* stage = u8_host ? (void*)c->stage_u8[b].p : (void*)c->stage[b].p;
+    const void* src = u8_host ? (const void*)(u8_host + (size_t)done * clip_elems) : (const void*)(f32_host + (size_t)done * clip_elems);
+    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
+    CUDA_OK(c, cudaMemcpyAsync(stage, src, (size_t)nc * clip_elems * elem, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
+    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
+    gitb200_ctx::GraphKey key;
+    key.kind = u8_host ? 8 : 7; key.p0 = stage; key.i0 = nc; key.i1 = done; key.i2 = n_clips; key.i3 = n_frames; key.i4 = height; key.i5 = width;
+    const RawFrames raw{c->stage_u8[b].p, height, width};
+    const int r = run_graphed(c, key, comp, graphs, [&]() {
+      return run_encode(c, u8_host ? nullptr : c->stage[b].p, nc, n_frames, comp, done, n_clips, nullptr, true, u8_host ? &raw : nullptr);
+    });
+    if (r == 1) {  // replayed: host-side state the eager run would have left
+      c->cur_clips = done + nc; c->cur_nv = F * c->T; c->visual_pass_done = false; c->step_rows_per_clip = 0;
+    } else if (r != 0) {
+      return r;
     }
-    if (r == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&ent->exec, graph, 0) == cudaSuccess) {
-      cudaGraphDestroy(graph);
-      CUDA_OK(c, cudaGraphLaunch(ent->exec, s));
-      c->graph_launches++;
-      return 0;
-    }
-    if (graph) cudaGraphDestroy(graph);
+    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
+    done += nc;
+    ++ch;
   }
-  cudaGetLastError();
-  ent->exec = nullptr;
-  c->graphs_enabled = false;
-  return body();
+  return visual_pass_graphed(c, comp);
 }
 
 }  // namespace
@@ -972,6 +1076,8 @@ void gitb200_destroy(gitb200_ctx* c) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c->h_done) cudaFreeHost(c->h_done);
   if (c->ev_user) cudaEventDestroy(c->ev_user);
+  if (c->ev_gfork) cudaEventDestroy(c->ev_gfork);
+  if (c->ev_gjoin) cudaEventDestroy(c->ev_gjoin);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
   for (int i = 0; i < 2; ++i) {
@@ -1244,6 +1350,38 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
       CUDA_OK(c, cudaSetDevice(c->device));
       return caption_pipelined(c, frames, n_clips, n_frames, *sp, tokens, logprobs, s, chunk);
     }
+    if (c->graph_segments && c->graphs_enabled && c->tap_layers.empty() && !gemm_profile_enabled() && n_clips > c->graph_max_clips) {
+      // Throughput-sized batch: encode + visual pass replay as one CUDA graph per frame buffer, the decode loop as one graph per
+      // segment of steps (run_decode); nothing in them depends on the caller's output pointers.  The legacy default stream
+      // cannot be captured: the work then runs on the context's compute stream, forked from / joined back into the caller's.
+      CUDA_OK(c, cudaSetDevice(c->device));
+      cudaStream_t gs = s;
+      const bool forked = !graph_stream_ok(s);
+      if (forked) {
+        TRY(ensure_host_streams(c));
+        gs = c->comp_stream;
+        CUDA_OK(c, cudaEventRecord(c->ev_gfork, s));
+        CUDA_OK(c, cudaStreamWaitEvent(gs, c->ev_gfork, 0));
+      }
+      gitb200_ctx::GraphKey key;
+      key.kind = 6; key.p0 = frames; key.i0 = n_clips; key.i1 = n_frames;
+      const int r = run_graphed(c, key, gs, true, [&]() -> int {
+        TRY(run_encode_sweeps(c, frames, n_clips, n_frames, gs));
+        return run_visual_pass(c, false, nullptr, 0, gs);
+      });
+      if (r == 1) {  // replayed: host-side state the eager run would have left
+        c->cur_clips = n_clips; c->cur_nv = effective_frames(c, n_frames) * c->T; c->visual_pass_done = true; c->visual_pass_full = 0;
+        c->step_rows_per_clip = 0;
+      } else if (r != 0) {
+        return r;
+      }
+      TRY(run_decode(c, *sp, tokens, logprobs, nullptr, gs));
+      if (forked) {
+        CUDA_OK(c, cudaEventRecord(c->ev_gjoin, gs));
+        CUDA_OK(c, cudaStreamWaitEvent(s, c->ev_gjoin, 0));
+      }
+      return GITB200_OK;
+    }
   }
   return caption_eager(c, frames, n_clips, n_frames, sp, tokens, logprobs, logits, stream);
 }
@@ -1348,6 +1486,12 @@ int gitb200_set_graph_max_clips(gitb200_ctx* c, int max_clips) {
   return GITB200_OK;
 }
 
+int gitb200_set_graph_segments(gitb200_ctx* c, int enable) {
+  if (!c) return GITB200_ERR_INVALID;
+  c->graph_segments = enable != 0;
+  return GITB200_OK;
+}
+
 int gitb200_set_pipeline(gitb200_ctx* c, int chunk_clips) {
   if (!c) return GITB200_ERR_INVALID;
   if (c->pipeline_chunk != chunk_clips) c->ws_gen++;
@@ -1364,21 +1508,13 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
   const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
   const int per_clip_tok = sp->num_keep_best * sp->max_steps;
-  if (!c->copy_stream) {
-    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-    }
-  }
-  // the legacy default stream would serialise with the copy stream; compute runs on a private one
-  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  TRY(ensure_host_streams(c));
   cudaStream_t comp = c->comp_stream;
-  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
   if (c->pipeline_chunk != 0) {
     // opt-in two-stream variant: chunk i is copied, then encoded + decoded on pipeline stream i & 1 (workspace set i & 1)
+    for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
     TRY(ensure_pipeline(c));
     int done = 0;
     for (int ch = 0; done < n_clips; ++ch) {
@@ -1408,27 +1544,10 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
       CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_join[i], 0));
     }
   } else {
-    // Encode chunk by chunk as the frames arrive (copy of chunk i+1 overlaps the ViT of chunk i; a small first chunk
-    // keeps the un-overlapped head of the transfer short), then run the decoder once over all clips: the decode steps
-    // have a fixed cost per launch that is amortised over the whole batch.
-    int done = 0, ch = 0;
-    while (done < n_clips) {
-      const int b = ch & 1;
-      int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
-      if (nc > n_clips - done) nc = n_clips - done;
-      if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
-      CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
-                                 cudaMemcpyHostToDevice, c->copy_stream));
-      CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
-      CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-      int r = run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips);
-      if (r) return r;
-      CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
-      done += nc;
-      ++ch;
-    }
-    int r = run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp);
-    if (r) return r;
+    // Encode chunk by chunk as the frames arrive, then run the decoder once over all clips: the decode steps have a fixed
+    // cost per launch that is amortised over the whole batch.
+    TRY(encode_from_host(c, frames_host, nullptr, 0, 0, n_clips, n_frames, chunk_clips, comp));
+    TRY(run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp));
   }
   CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));
@@ -1447,37 +1566,13 @@ int gitb200_caption_from_host(gitb200_ctx* c, const float* frames_host, int n_cl
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
-  const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
-  if (!c->copy_stream) {
-    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-    }
-  }
-  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
-  if (!c->ev_user) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
+  TRY(ensure_host_streams(c));
   cudaStream_t comp = c->comp_stream, user = (cudaStream_t)stream;
-  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage[i], (size_t)chunk_clips * clip_elems);
   // the caller's earlier work on its stream (e.g. the allocation of the output tensors) is ordered before ours
   CUDA_OK(c, cudaEventRecord(c->ev_user, user));
   CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_user, 0));
   CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_user, 0));
-  int done = 0, ch = 0;
-  while (done < n_clips) {
-    const int b = ch & 1;
-    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
-    if (nc > n_clips - done) nc = n_clips - done;
-    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // staging buffer free again
-    CUDA_OK(c, cudaMemcpyAsync(c->stage[b].p, frames_host + (size_t)done * clip_elems, (size_t)nc * clip_elems * sizeof(float),
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
-    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-    TRY(run_encode(c, c->stage[b].p, nc, n_frames, comp, done, n_clips));
-    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
-    done += nc;
-    ++ch;
-  }
+  TRY(encode_from_host(c, frames_host, nullptr, 0, 0, n_clips, n_frames, chunk_clips, comp));
   if (vf_dev) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_dev, c->cfg.vit_width, comp));
   TRY(run_decode(c, *sp, tokens_dev, logprobs_dev, logits_dev, comp));
   CUDA_OK(c, cudaEventRecord(c->ev_user, comp));
@@ -1496,36 +1591,12 @@ int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_cl
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
-  const size_t clip_bytes = (size_t)n_frames * height * width * 3;
   const int per_clip_tok = sp->num_keep_best * sp->max_steps;
-  if (!c->copy_stream) {
-    CUDA_OK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
-      CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-    }
-  }
-  if (!c->comp_stream) CUDA_OK(c, cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+  TRY(ensure_host_streams(c));
   cudaStream_t comp = c->comp_stream;
-  for (int i = 0; i < 2; ++i) ENSURE(c, c->stage_u8[i], (size_t)chunk_clips * clip_bytes);
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
-  int done = 0, ch = 0;
-  while (done < n_clips) {
-    const int b = ch & 1;
-    int nc = ch == 0 ? (chunk_clips + 1) / 2 : chunk_clips;
-    if (nc > n_clips - done) nc = n_clips - done;
-    if (ch >= 2) CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));  // byte staging buffer free again
-    CUDA_OK(c, cudaMemcpyAsync(c->stage_u8[b].p, frames_host + (size_t)done * clip_bytes, (size_t)nc * clip_bytes,
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_OK(c, cudaEventRecord(c->ev_copy[b], c->copy_stream));
-    CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_copy[b], 0));
-    const RawFrames raw{c->stage_u8[b].p, height, width};
-    TRY(run_encode(c, nullptr, nc, n_frames, comp, done, n_clips, nullptr, true, &raw));  // its first kernel consumes the bytes
-    CUDA_OK(c, cudaEventRecord(c->ev_done[b], comp));
-    done += nc;
-    ++ch;
-  }
+  TRY(encode_from_host(c, nullptr, frames_host, height, width, n_clips, n_frames, chunk_clips, comp));  // a chunk's first kernel consumes the bytes
   TRY(run_decode(c, *sp, c->out_tok.p, c->out_lp.p, nullptr, comp));
   CUDA_OK(c, cudaMemcpyAsync(tokens_host, c->out_tok.p, (size_t)n_clips * per_clip_tok * sizeof(int32_t), cudaMemcpyDeviceToHost, comp));
   CUDA_OK(c, cudaMemcpyAsync(logprobs_host, c->out_lp.p, (size_t)n_clips * sp->num_keep_best * sizeof(float), cudaMemcpyDeviceToHost, comp));

@@ -630,6 +630,10 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+#ifdef ATTN_FORCE_POLY_PAIRS
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+#endif
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -642,8 +646,11 @@ cudaError_t attention_groups_tc(const bf16* qkv, int ld_qkv, bf16* out, int ldo,
   int grid = 2 * gemm_sm_count();  // two CTAs per SM (TMEM: 2 x 256 columns), each walks pairs of items with stride `grid`
   if (n_pairs < grid) grid = n_pairs;
   const float sl2 = scale * 1.4426950408889634f;
-#ifdef ATTN_FORCE_POLY_PAIRS
-  attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, (ATTN_FORCE_POLY_PAIRS > 0)><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
+#ifdef ATTN_FORCE_POLY_PAIRS  // tuning builds (tools/attn_bench.cu): the same exp2 split for every shape, the usual order of the phases
+  if (group_len >= LONG_GROUP)
+    attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
+  else
+    attention_tc_kernel<ATTN_FORCE_POLY_PAIRS, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);
 #else
   if (group_len >= LONG_GROUP)
     attention_tc_kernel<1, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, tkv, out, ldo, group_len, heads, n_groups, sl2);

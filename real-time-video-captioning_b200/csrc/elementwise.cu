@@ -91,10 +91,9 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(LayerNormArgs a) {
   if (a.stats_out) {
     st1 = warp_sum(st1);
     st2 = warp_sum(st2);
-    if (lane == 0) {
-      a.stats_out[2 * (size_t)warp] = st1;
-      a.stats_out[2 * (size_t)warp + 1] = st2;
-    }
+    // slot 0 of the row's `stats_slots` partial-sum slots holds the whole row, the others are zero (the consuming GEMM adds all)
+    for (int sl = lane; sl < a.stats_slots; sl += 32)
+      reinterpret_cast<float2*>(a.stats_out)[(size_t)warp * a.stats_slots + sl] = sl == 0 ? make_float2(st1, st2) : make_float2(0.f, 0.f);
   }
   }
 }

@@ -44,10 +44,12 @@ struct Epi2 {
   const float* bias;
   int act;
   int has_res;
-  const float* ln_stats;   // folded LayerNorm on the A rows: (sum, sum of squares) per row, or nullptr
+  const float* ln_stats;   // folded LayerNorm on the A rows: [M][ln_slots] partial (sum, sum of squares) per row, or nullptr
   const float* ln_colsum;  // [N]
   float ln_inv_k, ln_eps;
-  float* stats_out;        // (sum, sum of squares) of the output rows, accumulated with atomics, or nullptr
+  float* stats_out;        // [M][2 * N / BN] partial (sum, sum of squares) of the output rows, one slot per 128-column half tile, or nullptr
+  int ln_slots;            // partial-sum slots per row of ln_stats (= 2 * K / BN: the producer's column halves)
+  int out_slots;           // = 2 * N / BN
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -254,7 +256,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const int my_row = row0 + lane;
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (FOLD && ep.ln_stats != nullptr && my_row < M) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + my_row);
+        // the row's statistics: partial sums of the producer's column halves, added in slot order (deterministic)
+        float2 st = make_float2(0.f, 0.f);
+        for (int sl = 0; sl < ep.ln_slots; ++sl) {
+          const float2 pp = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + (size_t)my_row * ep.ln_slots + sl);
+          st.x += pp.x;
+          st.y += pp.y;
+        }
         ln_mean = st.x * ep.ln_inv_k;
         ln_rstd = rsqrtf(fmaxf(st.y * ep.ln_inv_k - ln_mean * ln_mean, 0.f) + ep.ln_eps);
       }
@@ -341,10 +349,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           G2TRACE(e_it, c == c_begin ? 4 : 7);
         }
       }
-      if (FOLD && ep.stats_out != nullptr && my_row < M) {
-        atomicAdd(ep.stats_out + 2 * (size_t)my_row, so1);
-        atomicAdd(ep.stats_out + 2 * (size_t)my_row + 1, so2);
-      }
+      if (FOLD && ep.stats_out != nullptr && my_row < M)  // this warp's 128 columns of the row: its own slot, a plain store
+        reinterpret_cast<float2*>(ep.stats_out)[(size_t)my_row * ep.out_slots + (n0 / BN) * 2 + (ew >> 2)] = make_float2(so1, so2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
@@ -383,7 +389,7 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
   int clusters = gemm_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out};
+  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out, 2 * a.K / BN, 2 * a.N / BN};
   if (a.ln_stats != nullptr || a.stats_out != nullptr)
     gemm2_kernel<true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
   else

@@ -33,12 +33,13 @@ struct GemmArgs {
   int gin = 0, gout = 0, goff = 0;
   // LayerNorm folded into this GEMM (pre-LN blocks): A holds the UN-normalised rows x, W already carries gamma
   // (W' = W * diag(gamma)), bias already carries W * beta, and the epilogue applies
-  //     rstd_r * (acc - mean_r * ln_colsum[n]) + bias[n]      with (sum, sum of squares) of row r in ln_stats[2r..2r+1].
-  const float* ln_stats = nullptr;   // [M, 2] fp32
+  //     rstd_r * (acc - mean_r * ln_colsum[n]) + bias[n]      with (sum, sum of squares) of row r = the sum over the row's
+  //     2 * K / 256 partial slots in ln_stats (one per 128-column half tile of the GEMM that produced A; added in slot order).
+  const float* ln_stats = nullptr;   // [M, 2 * K / 256, 2] fp32
   const float* ln_colsum = nullptr;  // [N] fp32: sum_k W'[n, k]
   float ln_eps = 1e-5f;
-  // Optional: accumulate (sum, sum of squares) of every OUTPUT row (bf16-rounded values) into stats_out[2r..2r+1]
-  // with atomics -- the statistics the next folded LayerNorm needs.  Must be zeroed by the caller.
+  // Optional: (sum, sum of squares) of every OUTPUT row (bf16-rounded values), one partial pair per 128-column half tile, stored
+  // (not accumulated: deterministic, nothing to zero) into stats_out[r][2 * N / 256][2] -- what the next folded LayerNorm needs.
   float* stats_out = nullptr;
   // ---- weight-streaming skinny kernel only (M <= 8 decode rows; gemm_bf16 rejects them on the tensor-core kernels) ----
   // LayerNorm of the A rows ON LOAD (M <= 4, K == 768): A holds the UN-normalised rows; every warp normalises them exactly
@@ -78,7 +79,8 @@ struct LayerNormArgs {
   int ldo = 0;
   float* out_f32 = nullptr;  // optional fp32 copy
   int ldo32 = 0;
-  float* stats_out = nullptr;  // optional [rows, 2]: (sum, sum of squares) of the bf16-rounded output row (plain store)
+  float* stats_out = nullptr;  // optional [rows, stats_slots, 2]: (sum, sum of squares) of the bf16-rounded output row in slot 0, zeros elsewhere
+  int stats_slots = 1;
 };
 cudaError_t layernorm_bf16(const LayerNormArgs& a, cudaStream_t stream);
 

@@ -333,6 +333,10 @@ class Engine:
     def set_graph_max_clips(self, max_clips: int) -> None:
         check(self.lib.gitb200_set_graph_max_clips(self.h, max_clips), self.h, "gitb200_set_graph_max_clips")
 
+    def set_graph_segments(self, enable: bool) -> None:
+        """Large batches replay CUDA graphs of encode / visual pass / decode-step segments (default on); False = eager launches."""
+        check(self.lib.gitb200_set_graph_segments(self.h, 1 if enable else 0), self.h, "gitb200_set_graph_segments")
+
     def set_pipeline(self, chunk_clips: int) -> None:
         """Clips per chunk of the two-stream encode/decode pipeline (0 = off, -1 = automatic)."""
         check(self.lib.gitb200_set_pipeline(self.h, chunk_clips), self.h, "gitb200_set_pipeline")

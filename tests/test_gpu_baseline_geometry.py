@@ -478,3 +478,49 @@ def test_stale_state_is_rejected_loudly(g):
     eng.encode(frames[:1].contiguous(), want_features=False)      # features replaced: the step state is void
     with pytest.raises(g.GitB200Error):
         eng.decode_step(torch.full((2,), 101), 1)
+
+
+def test_large_batch_graph_segments_equal_eager(g):
+    """Throughput-sized batches replay CUDA graphs of encode + visual pass and of the decode loop's step segments (gitb200_
+    set_graph_segments, default on).  Device-resident frames on the default stream (forked onto the context's stream) and on
+    a side stream, the fp32 and raw-uint8 host paths, a batch-size change in between (workspaces grow: stale graphs must be
+    dropped), beam search, and the early exit between segments: all must equal the eager launches bit for bit."""
+    cfg = go.GitConfig(num_image_with_embedding=2, tie_output=False)
+    sd = go.init_state_dict(cfg, seed=71, temporal_std=0.02, perturb=True)
+    sd["textual.output.bias"] = sd["textual.output.bias"].clone()
+    sd["textual.output.bias"][cfg.eos_index] += 4.0  # captions end early: the finished-clip poll between segments matters
+    eng = g.Engine(g.make_config({"num_image_with_embedding": 2}, cfg.sos_index, cfg.eos_index), 0)
+    eng.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(4)
+    a = torch.randn(12, 2, 3, 224, 224, generator=gen).cuda()
+    b = torch.randn(20, 2, 3, 224, 224, generator=gen).cuda()
+    raw = torch.randint(0, 256, (12, 2, 120, 160, 3), dtype=torch.uint8, generator=gen)
+    results = {}
+    for mode in ("eager", "graphs"):
+        eng.set_graph_segments(mode == "graphs")
+        before = eng.lib.gitb200_graph_launches(eng.h)
+        out = []
+        for nb, ms in ((1, 12), (4, 9)):
+            sp = g.SearchConfig(beam_size=nb, max_steps=ms)
+            for _ in range(3):                                   # eager, capture, replay
+                out.append(eng.caption(a, sp)[:2])
+                steps_a = eng.last_decode_steps()
+            out.append(eng.caption(b, sp)[:2])                   # larger batch: workspaces move
+            for _ in range(2):
+                out.append(eng.caption(a, sp)[:2])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    out.append(eng.caption(a, sp)[:2])
+            side.synchronize()
+            for _ in range(3):
+                out.append(eng.caption_host(a.cpu().pin_memory(), sp, chunk_clips=5))
+                out.append(eng.caption_host_u8(raw.pin_memory(), sp, chunk_clips=5))
+            assert steps_a < ms - 1                              # the loop left early in both modes
+        torch.cuda.synchronize()
+        results[mode] = [(t.cpu().clone(), l.cpu().clone()) for t, l in out]
+        replays = eng.lib.gitb200_graph_launches(eng.h) - before
+        assert (replays > 20) if mode == "graphs" else (replays == 0), (mode, replays)
+    for (te, le), (tg, lg) in zip(results["eager"], results["graphs"]):
+        assert torch.equal(te, tg) and torch.equal(le, lg)

@@ -52,6 +52,8 @@ def main():
     if args.sweep_rows >= 0:
         eng.set_sweep_rows(args.sweep_rows)
     eng.reserve(B, 6, 1, 15)
+    if not args.graph:
+        eng.set_graph_segments(False)  # the eager timeline: one launch per kernel
     if args.graph:
         eng.set_graph_max_clips(B)
         eng.set_early_exit(0)
