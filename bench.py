@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step (512: +3.5 % over 256, the decode-step weights amortise over more rows)")
+    ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step (512: +3.5 %% over 256, the decode-step weights amortise over more rows)")
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--max-steps", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     ap.add_argument("--no-config-legs", action="store_true", help="skip the short legs of the other BASELINE.json configurations and the teacher-forward leg")
     ap.add_argument("--early-exit", type=int, default=-1, help="poll the device's finished-clip count every N decode steps (-1: library default 4; 0: never)")
-    ap.add_argument("--graph", action="store_true", help="A/B: capture the whole batch step into a CUDA graph and replay it (one frame set, no early-exit polling)")
+    ap.add_argument("--no-graphs", action="store_true", help="A/B: eager launches instead of the CUDA graphs of encode / visual pass / decode segments")
     args = ap.parse_args()
     claim_stdout()
 

@@ -102,3 +102,37 @@ def test_history_cache_equals_full_forward():
         outs = [st(toks[:, :t + 1]) for t in range(toks.shape[1])]
     for t, o in enumerate(outs):
         assert torch.allclose(o, full[:, t], atol=1e-4), (t, (o - full[:, t]).abs().max())
+
+
+def test_oracle_greedy_search_matches_hf_generate_on_a_single_image():
+    """An independent END-TO-END check of encode + decoding + greedy search: HuggingFace's ``GitForCausalLM.generate`` (its own
+    generation loop) against the oracle's ``infer`` (the reference's ``GeneratorWithBeamSearchV2.search`` restated line by line,
+    beam_size 1, over the upstream hidden-state history cache) on the single-image branch (model.py:387-388; HF's generation
+    cannot take videos: SURVEY Appendix C).  Untied random head, so the tokens are not the trivial copy.  ``use_cache=False``:
+    in transformers 5.5 HF's CACHED GIT generation disagrees with HF's own full forward from the second step on
+    ([101, 18861, 24035, ...] cached vs [101, 18861, 29428, ...] for both its un-cached loop and its teacher-forced forward on
+    this input); the un-cached loop re-runs the full forward the other test pins the oracle against, inside HF's loop.
+    The reference's loop scores ``max_steps - 1`` steps, keeps the first ``max_steps - 2`` words and appends EOS (model.py:585-596,
+    :653-677): those words must be HF's greedy continuation."""
+    from transformers import GitConfig as HFGitConfig, GitForCausalLM
+    from oracle import search_oracle as so
+
+    torch.manual_seed(0)
+    cfg = go.GitConfig(num_image_with_embedding=0, embedding_ln_eps=1e-12, tie_output=False)
+    sd = go.init_state_dict(cfg, seed=9, temporal_std=0.0, perturb=True)
+    hf_cfg = HFGitConfig(num_image_with_embedding=None, layer_norm_eps=1e-12, tie_word_embeddings=False,
+                         bos_token_id=101, eos_token_id=102, pad_token_id=0)
+    hf = GitForCausalLM(hf_cfg).eval()
+    missing, unexpected = hf.load_state_dict(to_hf_state_dict(sd, cfg), strict=False)
+    assert not [m for m in missing if "position_ids" not in m] and not unexpected
+    image = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    max_steps = 9
+    with torch.no_grad():
+        vf = go.vit_forward(sd, cfg, image)                                   # [1, 197, 768]: no temporal embedding
+        ref = so.infer(sd, cfg, vf, beam_size=1, max_steps=max_steps, save_logits=False)["predictions"][0]
+        out = hf.generate(pixel_values=image, input_ids=torch.tensor([[101]]), max_length=max_steps - 1, do_sample=False, num_beams=1,
+                          use_cache=False)[0]
+    words = ref[1:max_steps - 1]
+    assert ref[0].item() == 101 and ref[max_steps - 1].item() == 102
+    assert 102 not in words.tolist()                                          # random head: nobody emits EOS in 7 steps
+    assert out[0].item() == 101 and torch.equal(out[1:], words), (out, ref)
