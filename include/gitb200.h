@@ -129,6 +129,11 @@ int gitb200_set_graph_segments(gitb200_ctx* ctx, int enable);
  * LayerNorm launches disappear (4.5 % of the step) but the heavier GEMM epilogues give most of it back (+1 % net), and
  * the atomically accumulated statistics make results run-to-run non-bit-exact, hence off by default. */
 int gitb200_set_fold_layernorm(gitb200_ctx* ctx, int enable);
+/* Default on: for sweeps of >= 1024 rows the LayerNorm that FOLLOWS a residual GEMM -- ViT ln_2 after the out-projection, the
+ * next block's ln_1 after fc2, the decoder's visual_projection LayerNorm and its two post-LNs per layer over the visual rows --
+ * is produced by that GEMM as a second output: the CTA pair owns whole 256-row blocks, accumulates the rows' statistics over its
+ * N / 256 tiles in a fixed order and writes the normalised rows itself.  Bit-reproducible; 0 restores the separate kernels. */
+int gitb200_set_fuse_layernorm(gitb200_ctx* ctx, int enable);
 
 /* Large batches walk the ViT and the decoder's pass over the visual tokens in sub-batches of about `rows` token rows
  * (default 151296 = 128 six-frame ViT-B/16 clips; 0 = the whole batch in one sweep), so that the row-sized scratch
@@ -271,6 +276,10 @@ int gitb200_student_greedy_decode(gitb200_student* s, const float* memory_dev, i
 int gitb200_op_gemm(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev,
                     const void* residual_dev, int act, void* out_bf16_dev, float* out_f32_dev, int tile_n,
                     void* stream);
+/* C = A W^T + bias + residual (bf16) AND LayerNorm(C) * gamma + beta as a second bf16 output, both from the CTA-pair tcgen05 GEMM
+ * (M >= 1024, N a multiple of 256 up to 1024): the operator behind gitb200_set_fuse_layernorm. */
+int gitb200_op_gemm_ln(const void* a_dev, const void* w_dev, int M, int N, int K, const float* bias_dev, const void* residual_dev,
+                       const float* gamma_dev, const float* beta_dev, float eps, void* out_bf16_dev, void* ln_out_bf16_dev, void* stream);
 int gitb200_op_layernorm(const void* x_dev, int rows, int cols, const float* gamma_dev, const float* beta_dev,
                          float eps, void* out_bf16_dev, void* stream);
 /* qkv: bf16 [n_groups*group_len, 3*heads*64] -> out bf16 [n_groups*group_len, heads*64] */

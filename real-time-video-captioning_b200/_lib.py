@@ -81,6 +81,8 @@ SIGNATURES = {
     "gitb200_last_decode_steps": (c_int, [c_void_p]),
     "gitb200_set_graph_max_clips": (c_int, [c_void_p, c_int]),
     "gitb200_set_graph_segments": (c_int, [c_void_p, c_int]),
+    "gitb200_set_fuse_layernorm": (c_int, [c_void_p, c_int]),
+    "gitb200_op_gemm_ln": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "gitb200_set_sweep_rows": (c_int, [c_void_p, c_int]),
     "gitb200_caption_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p]),
     "gitb200_caption_host_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(SearchParams), c_void_p,

@@ -136,6 +136,9 @@ struct gitb200_ctx {
   bool is_twin = false;
   bool fold_ln = false;     // ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); the row statistics are partial sums per
                             // 128-column half tile stored by the producing GEMM and added in slot order by the consumer: bit-reproducible
+  // The LayerNorm that follows a residual GEMM (ViT ln_2 / next block's ln_1, the decoder's three post-LNs over the visual rows)
+  // is written by that GEMM as a second output (gemm2 LNOUT, rows >= 1024): no separate LayerNorm kernel, bit-reproducible.
+  bool fuse_ln = true;
   int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
   // Large batches walk the ViT / the decoder's visual pass in sub-batches of about this many token rows (0: one sweep).
   // 151296 = 128 six-frame GIT-base clips.  Throughput-neutral from 128 clips up (A/B on one box, 512 clips per step:
@@ -344,6 +347,7 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
   CUDA_OK(c, write_cls_rows(c->cls, c->pos_bf16, n_clips * F, T, W, c->x.p, s));
   // ln_pre (in place semantics: x <- ln_pre(x)); the residual stream starts from the normalised tokens
   const bool fold = c->fold_ln && rows >= 1024;  // the folded-LayerNorm epilogue lives in the CTA-pair GEMM
+  const bool fuse = c->fuse_ln && !fold && rows >= 1024 && W <= 1024;  // LayerNorm as the residual GEMM's second output (CTA-pair GEMM)
   if (fold) {
     ENSURE(c, c->stats_a, (size_t)rows * 2 * (2 * W / 256));
     ENSURE(c, c->stats_b, (size_t)rows * 2 * (2 * W / 256));
@@ -394,15 +398,19 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
       TRY(emit_tap(l));
       continue;
     }
-    TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
+    // ln_1: a kernel of its own for the first block; afterwards the previous block's fc2 GEMM has written it (fused)
+    if (!(fuse && l > 0)) TRY(ln(c, c->x.p, rows, W, L.ln1_g, L.ln1_b, k.vit_ln_eps, c->lnb.p, s));
     TRY(gemm(c, linear(c->lnb.p, W, L.w_qkv, W, rows, 3 * W, L.b_qkv, c->qkv.p, 3 * W), s));
     CUDA_OK(c, attention_groups_tc(c->qkv.p, 3 * W, c->attn.p, W, n_clips * F, T, k.vit_heads, scale, s));
     {
       GemmArgs g = linear(c->attn.p, W, L.w_out, W, rows, W, L.b_out, c->x.p, W);
       g.residual = c->x.p; g.ldr = W;  // x += out_proj(attn): each element is read then written by one thread
+      if (fuse) {  // ... and ln_2(x) leaves the same GEMM as its second output
+        g.lnout = c->lnb.p; g.lnout_ld = W; g.lnout_gamma = L.ln2_g; g.lnout_beta = L.ln2_b; g.lnout_eps = k.vit_ln_eps;
+      }
       TRY(gemm(c, g, s));
     }
-    TRY(ln(c, c->x.p, rows, W, L.ln2_g, L.ln2_b, k.vit_ln_eps, c->lnb.p, s));
+    if (!fuse) TRY(ln(c, c->x.p, rows, W, L.ln2_g, L.ln2_b, k.vit_ln_eps, c->lnb.p, s));
     {
       GemmArgs g = linear(c->lnb.p, W, L.w_fc1, W, rows, 4 * W, L.b_fc1, c->mlp.p, 4 * W);
       g.act = ACT_QUICK_GELU;
@@ -411,6 +419,10 @@ int run_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, c
     {
       GemmArgs g = linear(c->mlp.p, 4 * W, L.w_fc2, 4 * W, rows, W, L.b_fc2, c->x.p, W);
       g.residual = c->x.p; g.ldr = W;
+      if (fuse && l + 1 < k.vit_layers) {  // the next block's ln_1
+        const VitLayer& Ln = c->vit[l + 1];
+        g.lnout = c->lnb.p; g.lnout_ld = W; g.lnout_gamma = Ln.ln1_g; g.lnout_beta = Ln.ln1_b; g.lnout_eps = k.vit_ln_eps;
+      }
       TRY(gemm(c, g, s));
     }
     TRY(emit_tap(l));
@@ -463,8 +475,15 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
   };
 
   // visual_projection = Linear + LayerNorm
-  TRY(gemm(c, linear(c->vf.p + (size_t)b0 * Nv * k.vit_width, k.vit_width, c->w_proj, k.vit_width, M, H, c->b_proj, c->hvb.p, H), s));
-  TRY(ln(c, c->hvb.p, M, H, c->lnp_g, c->lnp_b, k.proj_ln_eps, c->hv.p, s));
+  const bool fuse = c->fuse_ln && M >= 1024;  // the LayerNorms leave the GEMMs that feed them as a second output (CTA-pair GEMM)
+  {
+    GemmArgs g = linear(c->vf.p + (size_t)b0 * Nv * k.vit_width, k.vit_width, c->w_proj, k.vit_width, M, H, c->b_proj, c->hvb.p, H);
+    if (fuse) {
+      g.lnout = c->hv.p; g.lnout_ld = H; g.lnout_gamma = c->lnp_g; g.lnout_beta = c->lnp_b; g.lnout_eps = k.proj_ln_eps;
+    }
+    TRY(gemm(c, g, s));
+  }
+  if (!fuse) TRY(ln(c, c->hvb.p, M, H, c->lnp_g, c->lnp_b, k.proj_ln_eps, c->hv.p, s));
   TRY(emit_hidden(0));
   for (int l = 0; l < k.dec_layers; ++l) {
     const DecLayer& L = c->dec[l];
@@ -481,9 +500,12 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
     {
       GemmArgs g = linear(c->vattn.p, H, L.w_out, H, M, H, L.b_out, c->hvb.p, H);
       g.residual = c->hv.p; g.ldr = H;
+      if (fuse) {
+        g.lnout = c->hvc.p; g.lnout_ld = H; g.lnout_gamma = L.lna_g; g.lnout_beta = L.lna_b; g.lnout_eps = k.bert_ln_eps;
+      }
       TRY(gemm(c, g, s));
     }
-    TRY(ln(c, c->hvb.p, M, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->hvc.p, s));
+    if (!fuse) TRY(ln(c, c->hvb.p, M, H, L.lna_g, L.lna_b, k.bert_ln_eps, c->hvc.p, s));
     {
       GemmArgs g = linear(c->hvc.p, H, L.w_fc1, H, M, k.ffn, L.b_fc1, c->vmlp.p, k.ffn);
       g.act = ACT_GELU_ERF;
@@ -492,9 +514,12 @@ int run_visual_pass(gitb200_ctx* c, bool full_last, float* hidden_out, int L_tex
     {
       GemmArgs g = linear(c->vmlp.p, k.ffn, L.w_fc2, k.ffn, M, H, L.b_fc2, c->hvb.p, H);
       g.residual = c->hvc.p; g.ldr = H;
+      if (fuse) {
+        g.lnout = c->hv.p; g.lnout_ld = H; g.lnout_gamma = L.lno_g; g.lnout_beta = L.lno_b; g.lnout_eps = k.bert_ln_eps;
+      }
       TRY(gemm(c, g, s));
     }
-    TRY(ln(c, c->hvb.p, M, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->hv.p, s));
+    if (!fuse) TRY(ln(c, c->hvb.p, M, H, L.lno_g, L.lno_b, k.bert_ln_eps, c->hv.p, s));
     TRY(emit_hidden(l + 1));
   }
  }
@@ -844,7 +869,7 @@ void free_workspaces(gitb200_ctx* c) {
 gitb200_ctx* make_twin(gitb200_ctx* c) {
   gitb200_ctx* t = new gitb200_ctx();
   t->cfg = c->cfg; t->device = c->device; t->finalized = true; t->is_twin = true; t->graphs_enabled = false; t->pipeline_chunk = 0;
-  t->fold_ln = c->fold_ln; t->sweep_rows = c->sweep_rows;
+  t->fold_ln = c->fold_ln; t->fuse_ln = c->fuse_ln; t->sweep_rows = c->sweep_rows;
   t->T = c->T; t->kpad = c->kpad; t->vocab_pad = c->vocab_pad; t->n_temporal = c->n_temporal;
   t->w_patch = c->w_patch; t->pos_bf16 = c->pos_bf16; t->cls = c->cls; t->ln_pre_g = c->ln_pre_g; t->ln_pre_b = c->ln_pre_b;
   t->ln_post_g = c->ln_post_g; t->ln_post_b = c->ln_post_b; t->temporal = c->temporal; t->vit = c->vit;
@@ -1486,6 +1511,14 @@ int gitb200_set_graph_max_clips(gitb200_ctx* c, int max_clips) {
   return GITB200_OK;
 }
 
+int gitb200_set_fuse_layernorm(gitb200_ctx* c, int enable) {
+  if (!c) return GITB200_ERR_INVALID;
+  if (c->fuse_ln != (enable != 0)) c->ws_gen++;  // captured graphs replay the other launch sequence
+  c->fuse_ln = enable != 0;
+  if (c->twin) c->twin->fuse_ln = c->fuse_ln;
+  return GITB200_OK;
+}
+
 int gitb200_set_graph_segments(gitb200_ctx* c, int enable) {
   if (!c) return GITB200_ERR_INVALID;
   c->graph_segments = enable != 0;
@@ -1684,6 +1717,17 @@ int gitb200_op_gemm(const void* a, const void* w, int M, int N, int K, const flo
   g.residual = (const bf16*)residual; g.ldr = N; g.act = act; g.out = (bf16*)out_bf16; g.ldo = N; g.out_f32 = out_f32; g.ldo32 = N;
   cudaError_t e = gemm_bf16(g, (cudaStream_t)stream, tile_n);
   if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "gemm: %s [%s]", cudaGetErrorString(e), gemm_last_error());
+  return GITB200_OK;
+}
+
+int gitb200_op_gemm_ln(const void* a, const void* w, int M, int N, int K, const float* bias, const void* residual, const float* gamma,
+                       const float* beta, float eps, void* out_bf16, void* ln_out_bf16, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)a; g.lda = K; g.W = (const bf16*)w; g.ldw = K; g.M = M; g.N = N; g.K = K; g.bias = bias;
+  g.residual = (const bf16*)residual; g.ldr = N; g.out = (bf16*)out_bf16; g.ldo = N;
+  g.lnout = (bf16*)ln_out_bf16; g.lnout_ld = N; g.lnout_gamma = gamma; g.lnout_beta = beta; g.lnout_eps = eps;
+  cudaError_t e = gemm_bf16(g, (cudaStream_t)stream, 0);
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "gemm_ln: %s [%s]", cudaGetErrorString(e), gemm_last_error());
   return GITB200_OK;
 }
 

@@ -29,7 +29,8 @@ constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int BN = 256;          // columns per pair tile
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int STAGES = 6;  // (the LNOUT instantiation uses LN_STAGES)
+constexpr int PLAIN_STAGES = STAGES;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of W
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -39,6 +40,9 @@ constexpr int EPI_COLS = 64;                       // columns per staged block (
 constexpr int STAGING_BYTES = 32 * EPI_COLS * 2;   // 4 KB per epilogue warp
 constexpr int TMEM_COLS = 2 * BN;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + 1024 + 512;
+constexpr int LN_STAGES = 5;  // LNOUT instantiation: one operand stage fewer pays for a second staging buffer per epilogue warp
+constexpr int SMEM_BYTES_LN = LN_STAGES * STAGE_BYTES + 2 * NUM_EPI_WARPS * STAGING_BYTES + 1024 + 512;
+static_assert(SMEM_BYTES_LN <= 227 * 1024, "shared memory");
 
 struct Epi2 {
   const float* bias;
@@ -50,6 +54,10 @@ struct Epi2 {
   float* stats_out;        // [M][2 * N / BN] partial (sum, sum of squares) of the output rows, one slot per 128-column half tile, or nullptr
   int ln_slots;            // partial-sum slots per row of ln_stats (= 2 * K / BN: the producer's column halves)
   int out_slots;           // = 2 * N / BN
+  // LNOUT: LayerNorm of the OUTPUT rows written as a second tensor (tmap_ln) by the CTA pair that owns the whole row block
+  const float* lnout_gamma;
+  const float* lnout_beta;
+  float lnout_eps;
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -119,21 +127,28 @@ __device__ long long g_gemm2_trace[10 * 16 * 8];
 // flags the compiler if-converted it into predicated FFMA / FMUL / PRMT that every element of every GEMM still issued
 // (ncu: 10.6 issued instructions per output element for a plain bias epilogue), and the 8 epilogue warps -- not the
 // tensor pipe -- set the tile period of the K = 768 GEMMs.
-template <bool FOLD>
+// LNOUT: the pair walks whole ROW BLOCKS (the N / 256 tiles of 256 rows one after the other), so that its epilogue threads
+// see complete output rows: they accumulate the rows' (sum, sum of squares) over the tiles, then re-read the just-written
+// output blocks (L2 hits, TMA loads double-buffered per warp), normalise them and TMA-store them to a second tensor -- the
+// LayerNorm that follows a residual GEMM costs one extra write from the GEMM instead of a read + write by its own kernel.
+template <bool FOLD, bool LNOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, int M, int N, int K,
-             Epi2 ep) {
+             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+             const __grid_constant__ CUtensorMap tmap_ln, int M, int N, int K, Epi2 ep) {
+  constexpr int STAGES = LNOUT ? LN_STAGES : PLAIN_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = ptx::warp_uniform((ptx::smem_u32(smem_raw) + 1023u) & ~1023u);
   const uint32_t staging_base = smem_base + STAGES * STAGE_BYTES;  // 1024-aligned (32 KB multiples)
-  const uint32_t bar_base = staging_base + NUM_EPI_WARPS * STAGING_BYTES;
+  const uint32_t staging2_base = staging_base + NUM_EPI_WARPS * STAGING_BYTES;  // LNOUT only
+  const uint32_t bar_base = staging_base + (LNOUT ? 2 : 1) * NUM_EPI_WARPS * STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + w); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + NUM_EPI_WARPS);
+  auto ln_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 4 + NUM_EPI_WARPS + w); };  // LNOUT: second staging buffer's loads
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + 2 * NUM_EPI_WARPS);
   auto smem_a = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
 
@@ -148,6 +163,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int n_tiles = N / BN;
   const int num_tiles = m_pairs * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  // i-th tile of this pair: round-robin over all tiles, or (LNOUT) the n_tiles tiles of row block cluster_id + k * num_clusters in turn
+  auto tile_at = [&](int i, int& tile) -> bool {
+    if (LNOUT) {
+      const int rb = cluster_id + (i / n_tiles) * num_clusters;
+      tile = rb * n_tiles + i % n_tiles;
+      return rb < m_pairs;
+    }
+    tile = cluster_id + i * num_clusters;
+    return tile < num_tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -165,7 +190,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         ptx::mbar_init(tfull_bar(a), 1);
         ptx::mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // every epilogue warp of BOTH CTAs arrives on the leader's
       }
-      for (int w = 0; w < NUM_EPI_WARPS; ++w) ptx::mbar_init(res_bar(w), 1);
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) {
+        ptx::mbar_init(res_bar(w), 1);
+        if (LNOUT) ptx::mbar_init(ln_bar(w), 1);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -184,7 +212,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tile;
+      for (int ti = 0; tile_at(ti, tile); ++ti) {
         const int m0 = (tile / n_tiles) * 2 * BM + (int)rank * BM;
         const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -208,7 +237,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
       uint32_t it = 0;       // k blocks issued so far: stage = it % STAGES, phase = (it / STAGES) & 1
       uint32_t tile_it = 0;  // tiles issued so far: accumulator = tile_it & 1, phase = (tile_it >> 1) & 1
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tile_it) {
+      int tile;
+      for (int ti = 0; tile_at(ti, tile); ++ti, ++tile_it) {
         const uint32_t acc = tile_it & 1u;
         G2TRACE(tile_it, 0);
         ptx::mbar_wait(tempty_bar(acc), ((tile_it >> 1) & 1u) ^ 1u);
@@ -239,11 +269,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint32_t stg = staging_base + ew * STAGING_BYTES;
     const uint32_t rbar = res_bar(ew);
     const uint32_t my_row_off = (uint32_t)lane * 128u;
-    uint32_t res_phase = 0;
+    uint32_t res_phase = 0, ln_phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     int e_it = -1;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    float ln_s1 = 0.f, ln_s2 = 0.f;  // LNOUT: this thread's row, its 128-column halves of the row block's tiles so far
+    int tile;
+    for (int ti = 0; tile_at(ti, tile); ++ti) {
       ++e_it;
       const int m0 = (tile / n_tiles) * 2 * BM + (int)rank * BM;
       const int n0 = (tile % n_tiles) * BN;
@@ -333,6 +365,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             }
             const uint32_t p0 = pack_bf16(f[0], f[1]), p1 = pack_bf16(f[2], f[3]), p2 = pack_bf16(f[4], f[5]), p3 = pack_bf16(f[6], f[7]);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            if (LNOUT) {  // statistics of the row as stored (bf16-rounded), accumulated over the row block's tiles
+              const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1), r2 = unpack_bf16(p2), r3 = unpack_bf16(p3);
+              ln_s1 += (r0.x + r0.y) + (r1.x + r1.y) + (r2.x + r2.y) + (r3.x + r3.y);
+              ln_s2 = fmaf(r0.x, r0.x, ln_s2); ln_s2 = fmaf(r0.y, r0.y, ln_s2); ln_s2 = fmaf(r1.x, r1.x, ln_s2); ln_s2 = fmaf(r1.y, r1.y, ln_s2);
+              ln_s2 = fmaf(r2.x, r2.x, ln_s2); ln_s2 = fmaf(r2.y, r2.y, ln_s2); ln_s2 = fmaf(r3.x, r3.x, ln_s2); ln_s2 = fmaf(r3.y, r3.y, ln_s2);
+            }
             if (FOLD && ep.stats_out != nullptr) {  // statistics of the values as stored (bf16-rounded)
               const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1), r2 = unpack_bf16(p2), r3 = unpack_bf16(p3);
               so1 += (r0.x + r0.y) + (r1.x + r1.y) + (r2.x + r2.y) + (r3.x + r3.y);
@@ -356,6 +394,78 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      if (LNOUT && (tile % n_tiles) == n_tiles - 1) {
+        // ---- the row block is complete: LayerNorm of its rows into the second output tensor
+        const uint32_t stg2 = staging2_base + ew * STAGING_BYTES;
+        const uint32_t lbar = ln_bar(ew);
+        // (1) the other column half of every row lives in warp ew ^ 4: exchange (sum, sum of squares) through the second staging
+        //     buffer (free here), halves added in a fixed order
+        if (lane == 0) ptx::tma_store_wait<0>();  // this warp's output blocks are in L2 / HBM (and nothing reads the staging buffers)
+        __syncwarp();
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stg2 + (uint32_t)lane * 8u), "f"(ln_s1), "f"(ln_s2) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+        float o1, o2;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o1), "=f"(o2) : "r"(staging2_base + (ew ^ 4) * STAGING_BYTES + (uint32_t)lane * 8u) : "memory");
+        const float t1 = (ew < 4) ? ln_s1 + o1 : o1 + ln_s1, t2 = (ew < 4) ? ln_s2 + o2 : o2 + ln_s2;
+        const float inv_n = 1.0f / (float)N;
+        const float mean = t1 * inv_n;
+        const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.lnout_eps);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");  // everybody has read its partner's pair: the buffer is free
+        ln_s1 = 0.f;
+        ln_s2 = 0.f;
+        // (2) this warp's 2 * n_tiles blocks (32 rows x 64 columns) come back by TMA, two in flight
+        const int n_blk = 2 * n_tiles;
+        auto blk_col = [&](int q) { return (q >> 1) * BN + c_begin + (q & 1) * EPI_COLS; };
+        uint32_t ph_a = res_phase, ph_b = 0;  // parity of the next completion of res_bar / ln_bar (ln_bar: tracked across row blocks below)
+        ph_b = ln_phase;
+        if (row0 < M) {
+          ptx::mbar_arrive_expect_tx_elect(rbar, STAGING_BYTES);
+          ptx::tma_load_2d_elect(stg, &tmap_out, rbar, blk_col(0), row0);
+#pragma unroll 1
+          for (int q = 0; q < n_blk; ++q) {
+            const uint32_t buf = (q & 1) ? stg2 : stg;
+            if (q + 1 < n_blk) {  // next block into the other buffer, once the store that last read it has let go of it
+              if (lane == 0) ptx::tma_store_wait_read<0>();
+              __syncwarp();
+              const uint32_t nb = (q & 1) ? stg : stg2, nbar = (q & 1) ? rbar : lbar;
+              ptx::mbar_arrive_expect_tx_elect(nbar, STAGING_BYTES);
+              ptx::tma_load_2d_elect(nb, &tmap_out, nbar, blk_col(q + 1), row0);
+            }
+            if (q & 1) {
+              ptx::mbar_wait(lbar, ph_b);
+              ph_b ^= 1u;
+            } else {
+              ptx::mbar_wait(rbar, ph_a);
+              ph_a ^= 1u;
+            }
+            const int col = blk_col(q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t saddr = buf + my_row_off + (uint32_t)((j ^ (lane & 7)) << 4);
+              uint4 u;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(ep.lnout_gamma + col + j * 8));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(ep.lnout_gamma + col + j * 8 + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.lnout_beta + col + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.lnout_beta + col + j * 8 + 4));
+              const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+              const uint32_t p0 = pack_bf16(fmaf((a0.x - mean) * rstd, g0.x, b0.x), fmaf((a0.y - mean) * rstd, g0.y, b0.y));
+              const uint32_t p1 = pack_bf16(fmaf((a1.x - mean) * rstd, g0.z, b0.z), fmaf((a1.y - mean) * rstd, g0.w, b0.w));
+              const uint32_t p2 = pack_bf16(fmaf((a2.x - mean) * rstd, g1.x, b1.x), fmaf((a2.y - mean) * rstd, g1.y, b1.y));
+              const uint32_t p3 = pack_bf16(fmaf((a3.x - mean) * rstd, g1.z, b1.z), fmaf((a3.y - mean) * rstd, g1.w, b1.w));
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_ln, buf, col, row0);
+              ptx::tma_store_commit();
+            }
+          }
+        }
+        res_phase = ph_a;
+        ln_phase = ph_b;
+      }
     }
     if (lane == 0) ptx::tma_store_wait<0>();  // all output bytes written before the CTA may exit
   }
@@ -375,8 +485,9 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (a.N % BN != 0 || a.out == nullptr || a.out_f32 != nullptr || a.gin > 0 || a.res_periodic) return cudaErrorNotSupported;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_LN);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -389,11 +500,21 @@ cudaError_t gemm2_bf16(const GemmArgs& a, cudaStream_t stream) {
   const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
   int clusters = gemm_sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out, 2 * a.K / BN, 2 * a.N / BN};
-  if (a.ln_stats != nullptr || a.stats_out != nullptr)
-    gemm2_kernel<true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
+  Epi2 ep{a.bias, a.act, a.residual != nullptr ? 1 : 0, a.ln_stats, a.ln_colsum, 1.0f / (float)a.K, a.ln_eps, a.stats_out, 2 * a.K / BN, 2 * a.N / BN,
+          a.lnout_gamma, a.lnout_beta, a.lnout_eps};
+  CUtensorMap tl = to;
+  if (a.lnout != nullptr) {
+    // LayerNorm of the output rows as a second output: the pair must own whole rows (row-block tile order), N <= 1024
+    if (a.ln_stats != nullptr || a.stats_out != nullptr || a.N > 1024 || a.lnout_gamma == nullptr || a.lnout_beta == nullptr || a.lnout_ld % 8 != 0)
+      return cudaErrorInvalidValue;
+    if (!gemm_get_tensor_map(a.lnout, a.M, a.N, a.lnout_ld, EPI_COLS, 32, &tl)) return cudaErrorInvalidValue;
+    const int row_blocks = (a.M + 2 * BM - 1) / (2 * BM);
+    if (row_blocks < clusters) clusters = row_blocks;
+    gemm2_kernel<false, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES_LN, stream>>>(ta, tb, to, tr, tl, a.M, a.N, a.K, ep);
+  } else if (a.ln_stats != nullptr || a.stats_out != nullptr)
+    gemm2_kernel<true, false><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, tl, a.M, a.N, a.K, ep);
   else
-    gemm2_kernel<false><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, a.M, a.N, a.K, ep);
+    gemm2_kernel<false, false><<<2 * clusters, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, tr, tl, a.M, a.N, a.K, ep);
   note_launch();
   return cudaGetLastError();
 }

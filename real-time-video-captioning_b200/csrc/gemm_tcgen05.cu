@@ -452,7 +452,7 @@ cudaError_t gemm_bf16(const GemmArgs& a, cudaStream_t stream, int force_bn) {
     cudaEventRecord(g_prof.ev[2 * slot], stream);
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (a.ln_stats != nullptr || a.stats_out != nullptr) {  // only the CTA-pair kernel implements the folded LayerNorm
+  if (a.ln_stats != nullptr || a.stats_out != nullptr || a.lnout != nullptr) {  // only the CTA-pair kernel implements the folded / fused LayerNorm
     e = gemm2_bf16(a, stream);
     if (e == cudaErrorNotSupported) {
       g_err = "gemm_bf16: folded LayerNorm / row statistics need the CTA-pair kernel (N % 256 == 0, bf16 output, no remap)";

@@ -41,6 +41,14 @@ struct GemmArgs {
   // Optional: (sum, sum of squares) of every OUTPUT row (bf16-rounded values), one partial pair per 128-column half tile, stored
   // (not accumulated: deterministic, nothing to zero) into stats_out[r][2 * N / 256][2] -- what the next folded LayerNorm needs.
   float* stats_out = nullptr;
+  // LayerNorm of the OUTPUT rows as a second output (CTA-pair kernel only, N <= 1024, bf16 `out` required):
+  //     lnout[r, :] = LN(out[r, :]) * lnout_gamma + lnout_beta      (statistics of the bf16-rounded output row, fp32)
+  // -- the LayerNorm that follows a residual GEMM, written by the GEMM itself (see gemm2_tcgen05.cu, LNOUT).
+  bf16* lnout = nullptr;
+  int lnout_ld = 0;
+  const float* lnout_gamma = nullptr;
+  const float* lnout_beta = nullptr;
+  float lnout_eps = 1e-5f;
   // ---- weight-streaming skinny kernel only (M <= 8 decode rows; gemm_bf16 rejects them on the tensor-core kernels) ----
   // LayerNorm of the A rows ON LOAD (M <= 4, K == 768): A holds the UN-normalised rows; every warp normalises them exactly
   // like layernorm_kernel (fp32 statistics, result rounded to bf16) before its dot products, and CTA 0 also stores the

@@ -333,6 +333,10 @@ class Engine:
     def set_graph_max_clips(self, max_clips: int) -> None:
         check(self.lib.gitb200_set_graph_max_clips(self.h, max_clips), self.h, "gitb200_set_graph_max_clips")
 
+    def set_fuse_layernorm(self, enable: bool) -> None:
+        """LayerNorms that follow a residual GEMM written by that GEMM as a second output (default on, sweeps of >= 1024 rows)."""
+        check(self.lib.gitb200_set_fuse_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fuse_layernorm")
+
     def set_graph_segments(self, enable: bool) -> None:
         """Large batches replay CUDA graphs of encode / visual pass / decode-step segments (default on); False = eager launches."""
         check(self.lib.gitb200_set_graph_segments(self.h, 1 if enable else 0), self.h, "gitb200_set_graph_segments")
@@ -360,6 +364,22 @@ def op_gemm(a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, act: int
     check(lib.gitb200_op_gemm(_ptr(a), _ptr(w), M, N, K, _ptr(bias), _ptr(residual), act, _ptr(out), _ptr(o32), tile_n, s),
           None, "gitb200_op_gemm")
     return (out, o32) if out_f32 else out
+
+
+def op_gemm_ln(a: torch.Tensor, w: torch.Tensor, bias, residual, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    """(A W^T + bias + residual, LayerNorm of that) from one launch of the CTA-pair GEMM (M >= 1024, N % 256 == 0, N <= 1024)."""
+    lib = _lib.load()
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    ln = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    if residual is not None:
+        residual = residual.contiguous()
+    s = ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)
+    check(lib.gitb200_op_gemm_ln(_ptr(a), _ptr(w), M, N, K, _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), eps, _ptr(out), _ptr(ln), s),
+          None, "gitb200_op_gemm_ln")
+    return out, ln
 
 
 def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):

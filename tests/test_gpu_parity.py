@@ -92,6 +92,60 @@ def test_op_gemm(g, M, N, K, act, tile):
     assert (err16 <= 0.02 + 0.01 * ref.abs()).all(), err16.max()
 
 
+@pytest.mark.parametrize("M,N,K,eps,res", [(1182 * 2, 768, 768, 1e-5, True), (4097, 768, 3072, 1e-12, True), (1542, 1024, 1024, 1e-5, True),
+                                            (2048, 768, 768, 1e-5, False), (1024 * 40 + 3, 768, 768, 1e-12, True)])
+def test_op_gemm_with_layernorm_as_second_output(g, M, N, K, eps, res):
+    """gitb200_set_fuse_layernorm's operator: the residual GEMM also writes LayerNorm(its output rows).  First output as in
+    test_op_gemm; second output against F.layer_norm of the kernel's OWN bf16 first output (what a separate LayerNorm kernel
+    would read) within one bf16 rounding; run-to-run bit-identical; more row blocks than CTA pairs in the last shape."""
+    from importlib import import_module
+    eng = import_module("real-time-video-captioning_b200.engine")
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=gen) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=gen)
+    r = (torch.randn(M, N, device="cuda", generator=gen) * 2 + 0.5).bfloat16() if res else None
+    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=gen)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=gen)
+    out, ln = eng.op_gemm_ln(a, w, bias, r, gamma, beta, eps)
+    ref = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    assert ((out.float() - ref).abs() <= 0.02 + 0.01 * ref.abs()).all()
+    ref_ln = F.layer_norm(out.float(), (N,), gamma, beta, eps)
+    err = (ln.float() - ref_ln).abs()
+    record("op_gemm_ln", M=M, N=N, K=K, max_err=err.max().item())
+    assert (err <= 0.02 + 0.01 * ref_ln.abs()).all(), err.max()
+    out2, ln2 = eng.op_gemm_ln(a, w, bias, r, gamma, beta, eps)
+    assert torch.equal(out, out2) and torch.equal(ln, ln2)
+    plain = eng.op_gemm(a, w, bias, r, 0)
+    assert torch.equal(out, plain)   # the first output does not depend on the tile order or on the second output
+
+
+def test_fused_layernorm_equals_separate_kernels_within_rounding(g, setup):
+    """Engine level: features / logits with the LayerNorms fused into the residual GEMMs (default) against the separate
+    LayerNorm kernels and against the oracle -- both inside the stated tolerances, the fused path bit-reproducible."""
+    cfg, sd, eng = setup[True]
+    frames = torch.randn(4, N_FRAMES, 3, 224, 224, generator=torch.Generator().manual_seed(33))  # 1576 rows: the CTA-pair GEMM
+    with torch.no_grad():
+        ref = torch.cat([go.encode_clip(sd, cfg, f) for f in frames])
+    tokens = torch.full((4, 3), 1012, dtype=torch.int32, device="cuda")
+    try:
+        eng.set_fuse_layernorm(True)
+        vf_f = eng.encode(frames.cuda()).clone()
+        vf_f2 = eng.encode(frames.cuda()).clone()
+        lo_f = eng.forward_logits(frames.cuda(), tokens)[0].clone()
+        eng.set_fuse_layernorm(False)
+        vf_s = eng.encode(frames.cuda()).clone()
+        lo_s = eng.forward_logits(frames.cuda(), tokens)[0].clone()
+    finally:
+        eng.set_fuse_layernorm(True)
+    assert torch.equal(vf_f, vf_f2)
+    e_f, e_s = rel_fro(vf_f.cpu(), ref), rel_fro(vf_s.cpu(), ref)
+    record("fuse_ln", rel_fro_fused=e_f, rel_fro_separate=e_s, fused_vs_separate=rel_fro(vf_f, vf_s),
+           logits_fused_vs_separate=(lo_f - lo_s).abs().max().item() / lo_s.std().item())
+    assert e_f < 2e-2 and e_s < 2e-2 and rel_fro(vf_f, vf_s) < 1e-2
+    assert (lo_f - lo_s).abs().max().item() < 0.1 * lo_s.std().item()
+
+
 @pytest.mark.parametrize("rows,cols,eps", [(1, 768, 1e-5), (1183, 768, 1e-12), (514, 1024, 1e-5)])
 def test_op_layernorm(g, rows, cols, eps):
     from importlib import import_module
