@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e / latency / cpu legs): for ncu captures")
     ap.add_argument("--no-config-legs", action="store_true", help="skip the short legs of the other BASELINE.json configurations and the teacher-forward leg")
     ap.add_argument("--early-exit", type=int, default=-1, help="poll the device's finished-clip count every N decode steps (-1: library default 4; 0: never)")
-    ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: separate LayerNorm kernels instead of the residual GEMMs' second output")
+    ap.add_argument("--fuse-ln", action="store_true", help="opt-in: LayerNorms written by the residual GEMMs as a second output (DESIGN.md dead ends)")
     ap.add_argument("--no-graphs", action="store_true", help="A/B: eager launches instead of the CUDA graphs of encode / visual pass / decode segments")
     args = ap.parse_args()
     claim_stdout()
@@ -435,8 +435,8 @@ def main():
         eng.set_early_exit(args.early_exit)
     if args.pipeline == 0:
         eng.reserve(B, FRAMES, args.beam, args.max_steps)
-    if args.no_fuse_ln:
-        eng.set_fuse_layernorm(False)
+    if args.fuse_ln:
+        eng.set_fuse_layernorm(True)
     if args.no_graphs:
         eng.set_graph_segments(False)
     config["cuda_graphs"] = "off (eager launches)" if args.no_graphs else "encode + visual pass per frame buffer, decode loop per 4-step segment (finished-clip poll between segments)"

@@ -129,10 +129,11 @@ int gitb200_set_graph_segments(gitb200_ctx* ctx, int enable);
  * LayerNorm launches disappear (4.5 % of the step) but the heavier GEMM epilogues give most of it back (+1 % net), and
  * the atomically accumulated statistics make results run-to-run non-bit-exact, hence off by default. */
 int gitb200_set_fold_layernorm(gitb200_ctx* ctx, int enable);
-/* Default on: for sweeps of >= 1024 rows the LayerNorm that FOLLOWS a residual GEMM -- ViT ln_2 after the out-projection, the
+/* Opt-in (default off: measured 1 % slower than the separate LayerNorm kernels at the bench geometry, profiles/r02_layernorm_fusion.md):
+ * for sweeps of >= 1024 rows the LayerNorm that FOLLOWS a residual GEMM -- ViT ln_2 after the out-projection, the
  * next block's ln_1 after fc2, the decoder's visual_projection LayerNorm and its two post-LNs per layer over the visual rows --
  * is produced by that GEMM as a second output: the CTA pair owns whole 256-row blocks, accumulates the rows' statistics over its
- * N / 256 tiles in a fixed order and writes the normalised rows itself.  Bit-reproducible; 0 restores the separate kernels. */
+ * N / 256 tiles in a fixed order and writes the normalised rows itself.  Bit-reproducible. */
 int gitb200_set_fuse_layernorm(gitb200_ctx* ctx, int enable);
 
 /* Large batches walk the ViT and the decoder's pass over the visual tokens in sub-batches of about `rows` token rows

@@ -136,9 +136,10 @@ struct gitb200_ctx {
   bool is_twin = false;
   bool fold_ln = false;     // ViT ln_1 / ln_2 folded into the QKV / fc1 GEMMs (rows >= 1024); the row statistics are partial sums per
                             // 128-column half tile stored by the producing GEMM and added in slot order by the consumer: bit-reproducible
-  // The LayerNorm that follows a residual GEMM (ViT ln_2 / next block's ln_1, the decoder's three post-LNs over the visual rows)
-  // is written by that GEMM as a second output (gemm2 LNOUT, rows >= 1024): no separate LayerNorm kernel, bit-reproducible.
-  bool fuse_ln = true;
+  // Opt-in: the LayerNorm that follows a residual GEMM (ViT ln_2 / next block's ln_1, the decoder's three post-LNs over the visual
+  // rows) written by that GEMM as a second output (gemm2 LNOUT, rows >= 1024): no separate LayerNorm kernel, bit-reproducible --
+  // and measured 1 % SLOWER than the separate kernels (profiles/r02_layernorm_fusion.md): default off.
+  bool fuse_ln = false;
   int pipeline_chunk = 0;   // 0 off (default: measured slower), -1 auto, > 0 clips per chunk
   // Large batches walk the ViT / the decoder's visual pass in sub-batches of about this many token rows (0: one sweep).
   // 151296 = 128 six-frame GIT-base clips.  Throughput-neutral from 128 clips up (A/B on one box, 512 clips per step:

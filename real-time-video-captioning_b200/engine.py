@@ -334,7 +334,7 @@ class Engine:
         check(self.lib.gitb200_set_graph_max_clips(self.h, max_clips), self.h, "gitb200_set_graph_max_clips")
 
     def set_fuse_layernorm(self, enable: bool) -> None:
-        """LayerNorms that follow a residual GEMM written by that GEMM as a second output (default on, sweeps of >= 1024 rows)."""
+        """Opt-in (default off, measured slower): LayerNorms that follow a residual GEMM written by that GEMM as a second output (sweeps of >= 1024 rows)."""
         check(self.lib.gitb200_set_fuse_layernorm(self.h, 1 if enable else 0), self.h, "gitb200_set_fuse_layernorm")
 
     def set_graph_segments(self, enable: bool) -> None:
