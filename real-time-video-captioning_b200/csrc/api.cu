@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -100,6 +101,12 @@ struct gitb200_ctx {
   Buf<int> out_tok;
   Buf<float> out_lp;
   cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
+  // The caller's stream that last received work of this context (every entry point with a `stream` argument is asynchronous).
+  // The host-frame entry points run on the context's private NON-BLOCKING streams, which nothing orders behind that stream --
+  // not even the legacy default stream does -- so they wait for it explicitly (order_after_caller_work): without that a
+  // gitb200_caption(...) immediately followed by gitb200_caption_host*(...) ran both on the same workspaces at once.
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_user = nullptr;
 
   // CUDA graphs for the launch-bound small-batch calls (latency mode): a call signature is captured on its second
@@ -201,6 +208,14 @@ int fail(gitb200_ctx* c, int code, const char* fmt, ...) {
                   gemm_last_error(), __FILE__, __LINE__);                                                  \
   } while (0)
 
+// Debug aid (GITB200_POISON=1 in the environment): every fresh device allocation is filled with 0xFF bytes (NaN as bf16 and
+// as fp32, -1 as int), so a kernel that consumes memory nobody wrote shows up as NaN / a fault instead of depending on
+// whatever the allocator hands out (a fresh process gets zero pages, a long-running one gets its own freed buffers).
+bool poison_allocs() {
+  static const bool on = [] { const char* e = getenv("GITB200_POISON"); return e != nullptr && e[0] != '\0' && e[0] != '0'; }();
+  return on;
+}
+
 template <typename T>
 int ensure(gitb200_ctx* c, Buf<T>& b, size_t n) {
   if (b.cap >= n) return 0;
@@ -211,6 +226,7 @@ int ensure(gitb200_ctx* c, Buf<T>& b, size_t n) {
   b.p = nullptr;
   b.cap = 0;
   CUDA_OK(c, cudaMalloc(&b.p, n * sizeof(T)));
+  if (poison_allocs()) CUDA_OK(c, cudaMemset(b.p, 0xFF, n * sizeof(T)));
   b.cap = n;
   return 0;
 }
@@ -223,6 +239,7 @@ int ensure(gitb200_ctx* c, Buf<T>& b, size_t n) {
 template <typename T>
 int walloc(gitb200_ctx* c, T** p, size_t n) {
   CUDA_OK(c, cudaMalloc(p, n * sizeof(T)));
+  if (poison_allocs()) CUDA_OK(c, cudaMemset(*p, 0xFF, n * sizeof(T)));
   c->weight_allocs.push_back(*p);
   return 0;
 }
@@ -628,7 +645,8 @@ int run_text_pass(gitb200_ctx* c, const TextPass& t, cudaStream_t s) {
   // run inside the skinny GEMMs that consume them (normalise-on-load, CTA 0 stores the normalised rows for the residuals)
   // and the K/V scatter inside the QKV projection: 6 launches per layer instead of 9 (a decode step is launch-latency
   // bound: ~5 us per dependent kernel against a 24 us weight-streaming floor).
-  const bool fused = rows <= 4 && t.hidden_out == nullptr && H == 768;
+  static const bool no_fused = [] { const char* e = getenv("GITB200_NO_FUSED_STEP"); return e != nullptr && e[0] == '1'; }();  // debug switch
+  const bool fused = rows <= 4 && t.hidden_out == nullptr && H == 768 && !no_fused;
   for (int l = 0; l < k.dec_layers; ++l) {
     const DecLayer& L = c->dec[l];
     {
@@ -952,6 +970,29 @@ int ensure_host_streams(gitb200_ctx* c) {
   if (!c->ev_user) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
   if (!c->ev_gfork) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_gfork, cudaEventDisableTiming));
   if (!c->ev_gjoin) CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_gjoin, cudaEventDisableTiming));
+  return 0;
+}
+
+cudaStream_t caller_stream(gitb200_ctx* c, void* stream) {
+  if (c) {
+    c->last_stream = (cudaStream_t)stream;
+    c->last_stream_valid = true;
+  }
+  return (cudaStream_t)stream;
+}
+
+// The context's private streams wait for whatever this context last enqueued on a caller's stream (see gitb200_ctx::last_stream).
+int order_after_caller_work(gitb200_ctx* c) {
+  if (!c->last_stream_valid) return 0;
+  TRY(ensure_host_streams(c));
+  if (cudaEventRecord(c->ev_user, c->last_stream) != cudaSuccess) {
+    cudaGetLastError();  // the caller's stream no longer exists: everything it was given has to be complete, the blunt way
+    CUDA_OK(c, cudaDeviceSynchronize());
+  } else {
+    CUDA_OK(c, cudaStreamWaitEvent(c->comp_stream, c->ev_user, 0));
+    CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_user, 0));
+  }
+  c->last_stream_valid = false;
   return 0;
 }
 
@@ -1293,7 +1334,7 @@ int gitb200_encode(gitb200_ctx* c, const float* frames, int n_clips, int n_frame
   if (!c || !frames || n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad encode argument");
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   TRY(run_encode_sweeps(c, frames, n_clips, n_frames, s));
   if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_clips * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
   return GITB200_OK;
@@ -1303,7 +1344,7 @@ int gitb200_encode_images(gitb200_ctx* c, const float* images, int n_images, flo
   if (!c || !images || n_images < 1) return fail(c, GITB200_ERR_INVALID, "bad encode_images argument");
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   TRY(run_encode_sweeps(c, images, n_images, 1, s, /*temporal=*/false));
   if (vf_out) CUDA_OK(c, cast_bf16_to_f32(c->vf.p, n_images * c->cur_nv, c->cfg.vit_width, c->cfg.vit_width, vf_out, c->cfg.vit_width, s));
   return GITB200_OK;
@@ -1327,7 +1368,7 @@ int gitb200_set_visual_features(gitb200_ctx* c, const float* vf, int n_clips, in
   CUDA_OK(c, cudaSetDevice(c->device));
   const int W = c->cfg.vit_width;
   ENSURE(c, c->vf, (size_t)n_clips * nv * W);
-  CUDA_OK(c, cast_f32_to_bf16(vf, n_clips * nv, W, W, c->vf.p, W, n_clips * nv, W, (cudaStream_t)stream));
+  CUDA_OK(c, cast_f32_to_bf16(vf, n_clips * nv, W, W, c->vf.p, W, n_clips * nv, W, caller_stream(c, stream)));
   c->cur_clips = n_clips;
   c->cur_nv = nv;
   c->visual_pass_done = false;
@@ -1340,7 +1381,7 @@ int gitb200_decode(gitb200_ctx* c, const gitb200_search_params* sp, int32_t* tok
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   if (c->cur_clips <= 0) return fail(c, GITB200_ERR_STATE, "no visual features: call gitb200_encode or gitb200_set_visual_features first");
   CUDA_OK(c, cudaSetDevice(c->device));
-  return run_decode(c, *sp, tokens, logprobs, logits, (cudaStream_t)stream);
+  return run_decode(c, *sp, tokens, logprobs, logits, caller_stream(c, stream));
 }
 
 static int caption_eager(gitb200_ctx* c, const float* frames, int n_clips, int n_frames, const gitb200_search_params* sp,
@@ -1355,7 +1396,7 @@ int gitb200_caption(gitb200_ctx* c, const float* frames, int n_clips, int n_fram
   if (!c || !sp) return fail(c, GITB200_ERR_INVALID, "bad caption argument");
   // Latency mode: a small batch is launch-bound (~850 kernels per caption), so the second call with the same
   // buffers / shapes on a capturable stream is recorded into a CUDA graph and later calls replay it.
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   if (n_clips > 0 && n_clips <= c->graph_max_clips && frames && tokens && logprobs && c->finalized) {
     gitb200_ctx::GraphKey key;
     key.kind = 0; key.p0 = frames; key.p1 = tokens; key.p2 = logprobs; key.i0 = n_clips; key.i1 = n_frames;
@@ -1431,7 +1472,7 @@ int gitb200_stream_push(gitb200_ctx* c, const float* frame, void* stream) {
     gitb200_ctx::GraphKey key;
     key.kind = 1; key.p0 = frame; key.i0 = c->ring_head;
     bf16* dst = c->ring.p + (size_t)c->ring_head * per_frame;
-    const int r = run_graphed(c, key, (cudaStream_t)stream, true, [&]() { return run_encode(c, frame, 1, 1, (cudaStream_t)stream, 0, 0, dst); });
+    const int r = run_graphed(c, key, caller_stream(c, stream), true, [&]() { return run_encode(c, frame, 1, 1, caller_stream(c, stream), 0, 0, dst); });
     if (r != 0 && r != 1) return r;
   }
   c->ring_head = (c->ring_head + 1) % cap;
@@ -1454,8 +1495,8 @@ int gitb200_stream_push_u8(gitb200_ctx* c, const uint8_t* frame, int height, int
     key.kind = 3; key.p0 = frame; key.i0 = c->ring_head; key.i1 = height; key.i2 = width;
     bf16* dst = c->ring.p + (size_t)c->ring_head * per_frame;
     const RawFrames raw{frame, height, width};
-    const int r = run_graphed(c, key, (cudaStream_t)stream, true,
-                              [&]() { return run_encode(c, nullptr, 1, 1, (cudaStream_t)stream, 0, 0, dst, true, &raw); });
+    const int r = run_graphed(c, key, caller_stream(c, stream), true,
+                              [&]() { return run_encode(c, nullptr, 1, 1, caller_stream(c, stream), 0, 0, dst, true, &raw); });
     if (r != 0 && r != 1) return r;
   }
   c->ring_head = (c->ring_head + 1) % cap;
@@ -1469,7 +1510,7 @@ int gitb200_stream_caption(gitb200_ctx* c, const gitb200_search_params* sp, int3
   if (!c || !sp || !tokens || !logprobs) return fail(c, GITB200_ERR_INVALID, "bad stream_caption argument");
   if (c->ring_count < 1) return fail(c, GITB200_ERR_STATE, "no frames in the streaming window: call gitb200_stream_push first");
   CUDA_OK(c, cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   const int cap = c->cfg.num_image_with_embedding, n = c->ring_count, T = c->T, W = c->cfg.vit_width;
   ENSURE(c, c->vf, (size_t)n * T * W);
   const int first = (c->ring_head - n + cap) % cap;  // oldest frame -> temporal position 0
@@ -1543,6 +1584,7 @@ int gitb200_caption_host(gitb200_ctx* c, const float* frames_host, int n_clips, 
   const size_t clip_elems = (size_t)n_frames * 3 * c->cfg.resolution * c->cfg.resolution;
   const int per_clip_tok = sp->num_keep_best * sp->max_steps;
   TRY(ensure_host_streams(c));
+  TRY(order_after_caller_work(c));
   cudaStream_t comp = c->comp_stream;
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
@@ -1601,7 +1643,8 @@ int gitb200_caption_from_host(gitb200_ctx* c, const float* frames_host, int n_cl
   CUDA_OK(c, cudaSetDevice(c->device));
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
   TRY(ensure_host_streams(c));
-  cudaStream_t comp = c->comp_stream, user = (cudaStream_t)stream;
+  TRY(order_after_caller_work(c));  // (work given to ANOTHER stream before this call)
+  cudaStream_t comp = c->comp_stream, user = caller_stream(c, stream);
   // the caller's earlier work on its stream (e.g. the allocation of the output tensors) is ordered before ours
   CUDA_OK(c, cudaEventRecord(c->ev_user, user));
   CUDA_OK(c, cudaStreamWaitEvent(comp, c->ev_user, 0));
@@ -1627,6 +1670,7 @@ int gitb200_caption_host_u8(gitb200_ctx* c, const uint8_t* frames_host, int n_cl
   if (chunk_clips < 1) chunk_clips = n_clips < 32 ? n_clips : 32;
   const int per_clip_tok = sp->num_keep_best * sp->max_steps;
   TRY(ensure_host_streams(c));
+  TRY(order_after_caller_work(c));
   cudaStream_t comp = c->comp_stream;
   ENSURE(c, c->out_tok, (size_t)n_clips * per_clip_tok);
   ENSURE(c, c->out_lp, (size_t)n_clips * sp->num_keep_best);
@@ -1644,7 +1688,7 @@ int gitb200_forward_logits(gitb200_ctx* c, const float* frames, int n_clips, int
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   if (L > c->cfg.max_positions) return fail(c, GITB200_ERR_INVALID, "caption length %d exceeds %d positions", L, c->cfg.max_positions);
   CUDA_OK(c, cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   if (frames) {
     if (n_clips < 1 || n_frames < 1) return fail(c, GITB200_ERR_INVALID, "bad forward_logits argument");
     TRY(run_encode_sweeps(c, frames, n_clips, n_frames, s));
@@ -1671,7 +1715,7 @@ int gitb200_decode_begin(gitb200_ctx* c, int rows_per_clip, void* stream) {
   if (!c || rows_per_clip < 1) return fail(c, GITB200_ERR_INVALID, "bad decode_begin argument");
   if (!c->finalized) return fail(c, GITB200_ERR_STATE, "call gitb200_finalize_weights first");
   CUDA_OK(c, cudaSetDevice(c->device));
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = caller_stream(c, stream);
   if (!c->visual_pass_done) TRY(run_visual_pass(c, false, nullptr, 0, s));
   const int rows = c->cur_clips * rows_per_clip, ml = c->cfg.max_positions < 64 ? c->cfg.max_positions : 64;
   TRY(ensure_text(c, rows, rows, ml));
@@ -1694,7 +1738,7 @@ int gitb200_decode_step(gitb200_ctx* c, const int32_t* tokens, int pos, float* l
   tp.tokens = tokens; tp.positions = nullptr; tp.pos_const = pos; tp.n_text = nullptr; tp.n_text_const = pos + 1;
   tp.anc = c->step_anc_used ? c->ibuf.p + (size_t)c->anc_parity * rows * ml : nullptr;
   tp.slot_div = 1; tp.n_slots = rows; tp.slot_is_clip = 0; tp.logits = logits; tp.hidden_out = nullptr;
-  return run_text_pass(c, tp, (cudaStream_t)stream);
+  return run_text_pass(c, tp, caller_stream(c, stream));
 }
 
 int gitb200_decode_reorder(gitb200_ctx* c, const int32_t* beam_idx, int pos, void* stream) {
@@ -1704,7 +1748,7 @@ int gitb200_decode_reorder(gitb200_ctx* c, const int32_t* beam_idx, int pos, voi
   const int rows = c->cur_clips * c->step_rows_per_clip, ml = c->cfg.max_positions < 64 ? c->cfg.max_positions : 64;
   int* a0 = c->ibuf.p + (size_t)c->anc_parity * rows * ml;
   int* a1 = c->ibuf.p + (size_t)(c->anc_parity ^ 1) * rows * ml;
-  CUDA_OK(c, anc_reorder(c->step_anc_used ? a0 : nullptr, a1, beam_idx, rows, ml, pos, (cudaStream_t)stream));
+  CUDA_OK(c, anc_reorder(c->step_anc_used ? a0 : nullptr, a1, beam_idx, rows, ml, pos, caller_stream(c, stream)));
   c->anc_parity ^= 1;
   c->step_anc_used = true;
   return GITB200_OK;
