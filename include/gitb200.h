@@ -113,6 +113,11 @@ int gitb200_caption(gitb200_ctx* ctx, const float* frames_dev, int n_clips, int 
  * (= len(saved_logits) of the reference; rows of logits_dev beyond it are not written). */
 int gitb200_set_early_exit(gitb200_ctx* ctx, int every_steps);
 int gitb200_last_decode_steps(const gitb200_ctx* ctx);
+/* Latency mode of the search loop (default on): the search of ONE clip (gitb200_caption / _decode / _stream_caption with one
+ * clip, beam_size <= 4, no saved logits) runs as one persistent cooperative kernel -- every decode step's embedding, decoder
+ * layers, vocabulary head and search step (model.py:518-640) are phases of a grid that stays resident, separated by
+ * grid-wide barriers instead of ~42 kernel launches per step.  Bit-identical to the launch sequence (0 selects it). */
+int gitb200_set_persistent_decode(gitb200_ctx* ctx, int enable);
 /* gitb200_caption calls of up to `max_clips` clips are captured into CUDA graphs (default 8: the launch-bound latency
  * mode).  Larger values also graph throughput-sized batches once gitb200_reserve has pinned the workspaces. */
 int gitb200_set_graph_max_clips(gitb200_ctx* ctx, int max_clips);

@@ -167,6 +167,8 @@ struct gitb200_ctx {
 
   // decode loop early exit (model.py:640): poll the device's done count every N steps (0 = never: fully asynchronous)
   int early_exit_every = 4;
+  bool persistent_decode = true;     // single-clip searches run as ONE persistent cooperative kernel (decode_mega.cu)
+  Buf<unsigned int> mega_bar;        // its grid-barrier counter
   int* h_done = nullptr;             // pinned
   int last_decode_steps = 0;         // decode steps the last gitb200_decode / _caption call enqueued
   int graph_max_clips = 8;           // calls of up to this many clips are captured into ONE CUDA graph (latency mode)
@@ -823,6 +825,46 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
   if (!c->visual_pass_done) TRY(run_visual_pass(c, false, nullptr, 0, s));
   TRY(ensure_text(c, rows, rows, sp.max_steps));
   if (!logits_out) ENSURE(c, c->logits, (size_t)rows * c->vocab_pad);
+  // Latency mode: ONE clip (rows = its beams <= 4).  The whole step loop -- embedding, decoder layers, vocabulary head and
+  // search step of every step -- runs as one persistent cooperative kernel whose phases are separated by grid barriers
+  // instead of kernel boundaries (decode_mega.cu; bit-identical to the launch sequence below, which remains the path for
+  // everything else and for devices that cannot keep the grid resident).  It leaves its loop itself once the clip is done.
+  if (c->persistent_decode && B == 1 && rows <= 4 && logits_out == nullptr && k.hidden == 768 && k.dec_layers <= MEGA_MAX_LAYERS &&
+      !gemm_profile_enabled()) {
+    MegaArgs m;
+    memset(&m, 0, sizeof(m));
+    m.n_layers = k.dec_layers; m.rows = rows; m.hidden = k.hidden; m.heads = k.dec_heads; m.ffn = k.ffn; m.Nv = c->cur_nv;
+    decode_mega_attention_geometry(rows, k.dec_heads, c->cur_nv, sp.max_steps, &m.splits, &m.kcap);
+    m.vocab_pad = c->vocab_pad; m.steps = sp.max_steps - 1;
+    m.words = c->words_f32; m.pos_table = c->pos_f32; m.lne_g = c->lne_g; m.lne_b = c->lne_b;
+    m.embed_eps = k.embed_ln_eps; m.ln_eps = k.bert_ln_eps;
+    m.scale_log2 = (1.0f / sqrtf((float)(k.hidden / k.dec_heads))) * 1.4426950408889634f;
+    m.w_vocab = c->w_vocab; m.b_vocab = c->b_vocab;
+    m.logits = c->logits.p; m.logits_step_stride = 0;
+    m.st = st;
+    if (decode_mega_supported(m)) {
+      if (m.splits > 1) ENSURE(c, c->partial, text_attention_workspace_floats(rows, k.dec_heads, m.splits));
+      ENSURE(c, c->mega_bar, 32);
+      for (int l = 0; l < k.dec_layers; ++l) {
+        const DecLayer& L = c->dec[l];
+        MegaLayer& ml = m.layer[l];
+        ml.w_qkv = L.w_qkv; ml.w_out = L.w_out; ml.w_fc1 = L.w_fc1; ml.w_fc2 = L.w_fc2;
+        ml.b_qkv = L.b_qkv; ml.b_out = L.b_out; ml.b_fc1 = L.b_fc1; ml.b_fc2 = L.b_fc2;
+        ml.lna_g = L.lna_g; ml.lna_b = L.lna_b; ml.lno_g = L.lno_g; ml.lno_b = L.lno_b;
+        ml.vis_kv = c->kv[l].p; ml.txt_kv = c->txt_kv[l].p;
+      }
+      m.tq = c->tq.p; m.ta = c->ta.p; m.tb = c->tb.p; m.tf = c->tf.p; m.partial = c->partial.p; m.barrier = c->mega_bar.p;
+      CUDA_OK(c, search_init(st, k.sos, s));
+      const cudaError_t e = decode_mega(m, s);
+      if (e == cudaSuccess) {
+        c->last_decode_steps = sp.max_steps - 1;
+        CUDA_OK(c, search_finalize(st, tokens_out, logprobs_out, s));
+        return 0;
+      }
+      if (e != cudaErrorNotSupported) CUDA_OK(c, e);
+      cudaGetLastError();
+    }
+  }
   // model.py:640 `if all(done): break`: every `early_exit_every` steps the host reads the device's count of finished clips
   // (4 bytes, one stream synchronisation) and stops enqueueing decode steps once every clip is done.  Finished clips no
   // longer change, so the result is the same as running all steps; skipped while the stream is being captured into a graph.
@@ -1542,6 +1584,13 @@ int gitb200_set_fold_layernorm(gitb200_ctx* c, int enable) {
 int gitb200_set_early_exit(gitb200_ctx* c, int every_steps) {
   if (!c || every_steps < 0) return fail(c, GITB200_ERR_INVALID, "gitb200_set_early_exit: every_steps must be >= 0");
   c->early_exit_every = every_steps;
+  return GITB200_OK;
+}
+
+int gitb200_set_persistent_decode(gitb200_ctx* c, int enable) {
+  if (!c) return GITB200_ERR_INVALID;
+  if (c->persistent_decode != (enable != 0)) c->ws_gen++;  // captured small-batch graphs hold the other launch sequence
+  c->persistent_decode = enable != 0;
   return GITB200_OK;
 }
 

@@ -175,6 +175,32 @@ cudaError_t search_init(const SearchState& s, int sos, cudaStream_t stream);
 // decoded [n_clips, n_keep, max_len] (eos padded), logprobs [n_clips, n_keep]
 cudaError_t search_finalize(const SearchState& s, int* decoded, float* logprobs, cudaStream_t stream);
 
+// ---- persistent single-clip decode kernel (decode_mega.cu): the whole search of ONE clip (rows = beams <= 4) in one launch
+constexpr int MEGA_MAX_LAYERS = 8;
+struct MegaLayer {
+  const bf16 *w_qkv, *w_out, *w_fc1, *w_fc2;  // [3H, H], [H, H], [ffn, H], [H, ffn]
+  const float *b_qkv, *b_out, *b_fc1, *b_fc2, *lna_g, *lna_b, *lno_g, *lno_b;
+  const bf16* vis_kv;  // the clip's visual q|k|v rows of this layer: [Nv, 3H]
+  bf16* txt_kv;        // this layer's text K|V plane: [max_len][rows][2H]
+};
+struct MegaArgs {
+  MegaLayer layer[MEGA_MAX_LAYERS];
+  int n_layers, rows, hidden, heads, ffn, Nv, splits, kcap, vocab_pad, steps;
+  const float *words, *pos_table, *lne_g, *lne_b;  // fp32 embedding tables, embedding LayerNorm
+  float embed_eps, ln_eps, scale_log2;
+  const bf16* w_vocab;   // [vocab_pad, H]
+  const float* b_vocab;  // [vocab_pad]
+  float* logits;         // [steps or 1][rows, vocab_pad]
+  long long logits_step_stride;  // floats between the logits of consecutive steps (0: one buffer reused)
+  bf16 *tq, *ta, *tb, *tf;  // scratch rows: [rows, 3H], [rows, H], [rows, H], [rows, ffn]
+  float* partial;           // key-split partials of the attention
+  unsigned int* barrier;    // grid barrier counter (reset by the launcher)
+  SearchState st;
+};
+bool decode_mega_supported(const MegaArgs& a);
+void decode_mega_attention_geometry(int rows, int heads, int Nv, int max_text, int* splits, int* kcap);
+cudaError_t decode_mega(const MegaArgs& a, cudaStream_t stream);
+
 // pos[r] = r % L, n_text[r] = r % L + 1 (teacher-forced text rows)
 cudaError_t fill_positions(int* pos, int* n_text, int rows, int L, cudaStream_t stream);
 // Step-wise decoding cache re-index: out[r][s] = in ? in[beam_idx[r]][s] : beam_idx[r] for s < pos; out[r][pos] = beam_idx[r].

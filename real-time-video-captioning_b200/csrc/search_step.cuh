@@ -13,10 +13,12 @@ constexpr int MAX_NB = 8;
 
 __device__ __forceinline__ bool better(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
 
-// One search step of clip `clip`, executed by the SS_THREADS threads of one CTA (search_step_kernel: one CTA per clip; the
-// persistent single-clip decode kernel calls it from its CTA 0).
+// One search step of clip `clip`, executed by SS_THREADS threads (tid = 0 .. SS_THREADS-1) that meet in sync()
+// (search_step_kernel: one CTA per clip, __syncthreads; the persistent single-clip decode kernel calls it from the first
+// SS_THREADS threads of its CTA 0 with a named barrier).  COHERENT: the logits were written by other CTAs of the same launch.
+template <bool COHERENT, class Sync>
 __device__ __forceinline__ void search_step_device(const SearchState& st, const float* __restrict__ logits, int cur_len, int parity,
-                                                   int clip) {
+                                                   int clip, int tid, Sync sync) {
   __shared__ float red_f[SS_THREADS / 32];
   __shared__ int red_i[SS_THREADS / 32];
   __shared__ float row_lse_max[MAX_NB], row_lse[MAX_NB];
@@ -27,7 +29,8 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
   __shared__ float bc_f;
   __shared__ int bc_i;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
+  auto ldx = [](const float* q) { return COHERENT ? __ldcg(q) : *q; };
   const int nb = st.nb, V = st.V, C = st.cand;
   const int* tok_in = parity ? st.tokens_tmp : st.tokens;
   int* tok_out = parity ? st.tokens : st.tokens_tmp;
@@ -38,30 +41,30 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
   for (int b = 0; b < nb; ++b) {
     const float* x = logits + (size_t)(clip * nb + b) * st.ldl;
     float m = -INFINITY;
-    for (int i = tid; i < V; i += SS_THREADS) m = fmaxf(m, x[i]);
+    for (int i = tid; i < V; i += SS_THREADS) m = fmaxf(m, ldx(x + i));
     m = warp_max(m);
     if (lane == 0) red_f[warp] = m;
-    __syncthreads();
+    sync();
     if (tid == 0) {
       float mm = red_f[0];
       for (int w = 1; w < SS_THREADS / 32; ++w) mm = fmaxf(mm, red_f[w]);
       bc_f = mm;
     }
-    __syncthreads();
+    sync();
     m = bc_f;
     float s = 0.f;
-    for (int i = tid; i < V; i += SS_THREADS) s += expf(x[i] - m);
+    for (int i = tid; i < V; i += SS_THREADS) s += expf(ldx(x + i) - m);
     s = warp_sum(s);
-    __syncthreads();
+    sync();
     if (lane == 0) red_f[warp] = s;
-    __syncthreads();
+    sync();
     if (tid == 0) {
       float ss = 0.f;
       for (int w = 0; w < SS_THREADS / 32; ++w) ss += red_f[w];
       row_lse_max[b] = m;
       row_lse[b] = logf(ss);
     }
-    __syncthreads();
+    sync();
   }
 
   // ---- 2. top-C of (log_softmax + beam_score) over nb * V candidates               (model.py:561-565)
@@ -76,7 +79,7 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
     const float* x = logits + (size_t)(clip * nb + b) * st.ldl;
     const float m = row_lse_max[b], l = row_lse[b], bs = st.beam_scores[clip * nb + b];
     for (int i = tid; i < V; i += SS_THREADS) {
-      const float sc = ((x[i] - m) - l) + bs;
+      const float sc = ((ldx(x + i) - m) - l) + bs;
       const int id = b * V + i;
       if (better(sc, id, ls[C - 1], li[C - 1])) {
         // insertion into the sorted local list (C is tiny)
@@ -108,7 +111,7 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
       red_f[warp] = bs_;
       red_i[warp] = bi_;
     }
-    __syncthreads();
+    sync();
     if (tid == 0) {
       float s = red_f[0];
       int i = red_i[0];
@@ -121,9 +124,9 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
       cand_idx[c] = i;
       bc_i = i;
     }
-    __syncthreads();
+    sync();
     if (head < C && li[head] == bc_i) ++head;  // candidate ids are unique, exactly one thread pops
-    __syncthreads();
+    sync();
   }
 
   // ---- 3. candidate walk (thread 0), exactly the reference's control flow           (model.py:573-611)
@@ -194,7 +197,7 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
     if (is_done && !st.done[clip]) atomicAdd(st.done_count, 1);  // the host polls this to leave the step loop early
     st.done[clip] = is_done;
   }
-  __syncthreads();
+  sync();
 
   // ---- 4. re-order token rows (model.py:615-621) and, optionally, the text-KV ancestor table
   for (int b = 0; b < nb; ++b) {

@@ -327,6 +327,10 @@ class Engine:
         0 = never (fully asynchronous decode)."""
         check(self.lib.gitb200_set_early_exit(self.h, every_steps), self.h, "gitb200_set_early_exit")
 
+    def set_persistent_decode(self, enable: bool) -> None:
+        """Single-clip searches as one persistent cooperative kernel (default on; bit-identical to the launch sequence)."""
+        check(self.lib.gitb200_set_persistent_decode(self.h, 1 if enable else 0), self.h, "gitb200_set_persistent_decode")
+
     def last_decode_steps(self) -> int:
         return int(self.lib.gitb200_last_decode_steps(self.h))
 
