@@ -118,6 +118,11 @@ int gitb200_last_decode_steps(const gitb200_ctx* ctx);
  * layers, vocabulary head and search step (model.py:518-640) are phases of a grid that stays resident, separated by
  * grid-wide barriers instead of ~42 kernel launches per step.  Bit-identical to the launch sequence (0 selects it). */
 int gitb200_set_persistent_decode(gitb200_ctx* ctx, int enable);
+/* Profiling aid: while enabled, CTA 0 of the persistent decode kernel adds the SM cycles it spends in each phase to 32
+ * counters (0-6: QKV, attention, out-proj, fc1, fc2, vocabulary head, search -- its own work; 16-22: the wait in the grid
+ * barrier that ends the phase; 15: launches).  Copies the counters to out32 (may be NULL), then enables / disables (both
+ * reset them).  Synchronises the device. */
+int gitb200_debug_persistent_decode_trace(gitb200_ctx* ctx, unsigned long long* out32, int enable);
 /* gitb200_caption calls of up to `max_clips` clips are captured into CUDA graphs (default 8: the launch-bound latency
  * mode).  Larger values also graph throughput-sized batches once gitb200_reserve has pinned the workspaces. */
 int gitb200_set_graph_max_clips(gitb200_ctx* ctx, int max_clips);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "gitb200_caption_from_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(SearchParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gitb200_set_early_exit": (c_int, [c_void_p, c_int]),
     "gitb200_set_persistent_decode": (c_int, [c_void_p, c_int]),
+    "gitb200_debug_persistent_decode_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "gitb200_last_decode_steps": (c_int, [c_void_p]),
     "gitb200_set_graph_max_clips": (c_int, [c_void_p, c_int]),
     "gitb200_set_graph_segments": (c_int, [c_void_p, c_int]),

@@ -169,6 +169,8 @@ struct gitb200_ctx {
   int early_exit_every = 4;
   bool persistent_decode = true;     // single-clip searches run as ONE persistent cooperative kernel (decode_mega.cu)
   Buf<unsigned int> mega_bar;        // its grid-barrier counter
+  Buf<unsigned long long> mega_trace;  // optional per-phase cycle counters (gitb200_debug_persistent_decode_trace)
+  bool mega_trace_on = false;
   int* h_done = nullptr;             // pinned
   int last_decode_steps = 0;         // decode steps the last gitb200_decode / _caption call enqueued
   int graph_max_clips = 8;           // calls of up to this many clips are captured into ONE CUDA graph (latency mode)
@@ -844,7 +846,7 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
     m.st = st;
     if (decode_mega_supported(m)) {
       if (m.splits > 1) ENSURE(c, c->partial, text_attention_workspace_floats(rows, k.dec_heads, m.splits));
-      ENSURE(c, c->mega_bar, 32);
+      ENSURE(c, c->mega_bar, 32 + 2 * 128);  // [0]: barrier counter; [32, 160): candidate scores; [160, 288): candidate ids
       for (int l = 0; l < k.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
         MegaLayer& ml = m.layer[l];
@@ -853,7 +855,9 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
         ml.lna_g = L.lna_g; ml.lna_b = L.lna_b; ml.lno_g = L.lno_g; ml.lno_b = L.lno_b;
         ml.vis_kv = c->kv[l].p; ml.txt_kv = c->txt_kv[l].p;
       }
+      m.trace = c->mega_trace_on ? c->mega_trace.p : nullptr;
       m.tq = c->tq.p; m.ta = c->ta.p; m.tb = c->tb.p; m.tf = c->tf.p; m.partial = c->partial.p; m.barrier = c->mega_bar.p;
+      m.cand_score = reinterpret_cast<float*>(c->mega_bar.p + 32); m.cand_idx = reinterpret_cast<int*>(c->mega_bar.p + 160);
       CUDA_OK(c, search_init(st, k.sos, s));
       const cudaError_t e = decode_mega(m, s);
       if (e == cudaSuccess) {
@@ -1591,6 +1595,23 @@ int gitb200_set_persistent_decode(gitb200_ctx* c, int enable) {
   if (!c) return GITB200_ERR_INVALID;
   if (c->persistent_decode != (enable != 0)) c->ws_gen++;  // captured small-batch graphs hold the other launch sequence
   c->persistent_decode = enable != 0;
+  return GITB200_OK;
+}
+
+int gitb200_debug_persistent_decode_trace(gitb200_ctx* c, unsigned long long* out32, int enable) {
+  if (!c) return GITB200_ERR_INVALID;
+  CUDA_OK(c, cudaSetDevice(c->device));
+  CUDA_OK(c, cudaDeviceSynchronize());
+  if (c->mega_trace.p == nullptr) {
+    ENSURE(c, c->mega_trace, 32);
+    CUDA_OK(c, cudaMemset(c->mega_trace.p, 0, 32 * sizeof(unsigned long long)));
+  }
+  if (out32) CUDA_OK(c, cudaMemcpy(out32, c->mega_trace.p, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if ((enable != 0) != c->mega_trace_on) {
+    c->ws_gen++;  // captured graphs hold the kernel's arguments
+    CUDA_OK(c, cudaMemset(c->mega_trace.p, 0, 32 * sizeof(unsigned long long)));
+  }
+  c->mega_trace_on = enable != 0;
   return GITB200_OK;
 }
 

@@ -45,7 +45,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
   if (threadIdx.x == 0) {
     target += n_ctas;
-    __threadfence();
+    // release (cumulative over what the bar.sync above ordered before this thread) ... acquire: no separate fences needed
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v;
     const long long t0 = clock64();
@@ -57,7 +57,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
         __trap();
       }
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -145,15 +144,19 @@ __device__ __forceinline__ void embed_row_to_smem(const float* __restrict__ w, c
 
 // ---- NC output columns of a K = 768 contraction by one warp: acc[m][c] = sum_k x[m][k] * W[n_c][k], lane owns
 // k = lane * 8 + it * 256 (it = 0, 1, 2 in this order; 8 sequential FMAs per slice) -- gemv_skinny's non-split-K order.
-// All 3 * NC weight loads are issued before the first FMA.  wrow[c] == nullptr: column absent (result ignored).
-template <int MT, int NC>
-__device__ __forceinline__ void dot768(const bf16* const (&wrow)[NC], const uint4* xs /* [MT][HV] shared */, int lane, float (&acc)[MT][NC]) {
-  uint4 wv[NC][3];
+// load768 issues all 3 * NC weight loads; they are static data, so a phase's first columns are fetched BEFORE the grid
+// barrier that precedes the phase and the HBM latency hides behind the barrier and the phase's prologue.
+// wrow[c] == nullptr: column absent (result ignored).
+template <int NC>
+__device__ __forceinline__ void load768(const bf16* const (&wrow)[NC], int lane, uint4 (&wv)[NC][3]) {
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int it = 0; it < 3; ++it)
       wv[c][it] = wrow[c] != nullptr ? __ldg(reinterpret_cast<const uint4*>(wrow[c]) + it * 32 + lane) : make_uint4(0, 0, 0, 0);
+}
+template <int MT, int NC>
+__device__ __forceinline__ void fma768(const uint4 (&wv)[NC][3], const uint4* xs /* [MT][HV] shared */, int lane, float (&acc)[MT][NC]) {
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -191,6 +194,103 @@ __device__ __forceinline__ float pick(const float (&acc)[MT][NC], int m, int c) 
   return v;
 }
 
+// ---- phase B: the launch path's decode-step attention CTA as "virtual CTAs" of 128 threads 
+template <int NB>
+__device__ __forceinline__ void attention_phase(const MegaArgs& a, const MegaLayer& L, float* attn_smem, int attn_floats, int t, int parity,
+                                             int M, int chunks, int n_vcta) {
+  const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+  TextAttnArgs ta;
+  ta.q = a.tq; ta.ldq = 3 * H; ta.n_clips = 1; ta.rows_per_clip = M; ta.heads = a.heads;
+  ta.vis_kv = L.vis_kv; ta.ld_vis = 3 * H; ta.k_off = H; ta.v_off = 2 * H; ta.Nv = a.Nv;
+  ta.txt_kv = L.txt_kv; ta.txt_slots = M; ta.text_slot_is_clip = 0;
+  ta.anc = a.st.reorder_cache ? (parity ? a.st.anc_tmp : a.st.anc) : nullptr;
+  ta.anc_ld = a.st.max_len; ta.n_text = nullptr; ta.n_text_const = t + 1; ta.max_text = a.st.max_len;
+  ta.out = a.ta; ta.ldo = H; ta.partial = a.partial; ta.splits = a.splits;
+  const int vslot = tid >> 7, vtid = tid & 127;
+  float* scratch = attn_smem + (size_t)vslot * attn_floats;
+  for (int v = b + G * vslot; v < n_vcta; v += G * VCTAS) {
+    const int h = v % a.heads, rest = v / a.heads;
+    text_attn_dev::text_attention_body<NB, true>(ta, a.scale_log2, a.kcap, scratch, 0, rest % chunks, h, rest / chunks, vtid,
+                                                 [vslot] { named_barrier(1 + vslot, text_attn_dev::TA_THREADS); });
+    named_barrier(1 + vslot, text_attn_dev::TA_THREADS);  // scratch reuse by the next virtual CTA of this slot
+  }
+}
+
+// ---- phase C prologue: key-split partials of every (row, head) -> the attention output rows in shared memory
+__device__ __forceinline__ void combine_phase(const MegaArgs& a, uint4* as, int M) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int task = wid; task < M * a.heads; task += MEGA_WARPS) {
+    const int m = task / a.heads, h = task % a.heads;
+    const uint32_t u = text_attn_dev::combine_partials<true>(a.partial + (size_t)task * a.splits * (text_attn_dev::HD + 2), a.splits, lane);
+    reinterpret_cast<uint32_t*>(as + m * HV)[h * 32 + lane] = u;
+  }
+}
+
+// ---- search step, part 1: beam row `row` from the staged logits (all threads of the CTA)
+__device__ __forceinline__ void search_row_phase(const MegaArgs& a, const float* stage, float thread_max, int row, search_dev::SearchSmem& sh,
+                                                 float* wred) {
+  const int tid = threadIdx.x, C = a.st.cand;
+  search_dev::search_row_staged(a.st, stage, thread_max, row, 0, tid, MEGA_THREADS, [] { __syncthreads(); },
+                                [] { named_barrier(6, search_dev::SS_THREADS); }, sh, wred);
+  if (tid < C) {
+    a.cand_score[row * C + tid] = sh.cand_score[tid];
+    a.cand_idx[row * C + tid] = sh.cand_idx[tid];
+  }
+}
+
+// ---- search step, part 2 (CTA 0): merge of the rows' candidate lists, candidate walk, re-ordering
+__device__ __forceinline__ void search_walk_phase(const MegaArgs& a, int M, int t, int parity, search_dev::SearchSmem& sh) {
+  const int tid = threadIdx.x, C = a.st.cand;
+  __shared__ float all_s[4 * search_dev::MAX_CAND];
+  __shared__ int all_i[4 * search_dev::MAX_CAND];
+  if (tid < M * C) {
+    all_s[tid] = __ldcg(a.cand_score + tid);
+    all_i[tid] = __ldcg(a.cand_idx + tid);
+  }
+  named_barrier(6, search_dev::SS_THREADS);
+  if (tid == 0) {
+    int head[search_dev::MAX_NB];
+    for (int r = 0; r < M; ++r) head[r] = 0;
+    for (int c = 0; c < C; ++c) {  // M sorted lists of C candidates -> the best C of all, in `better` order
+      int br = -1;
+      float bs = 0.f;
+      int bi = 0;
+      for (int r = 0; r < M; ++r) {
+        if (head[r] >= C) continue;
+        const float s2 = all_s[r * C + head[r]];
+        const int i2 = all_i[r * C + head[r]];
+        if (br < 0 || search_dev::better(s2, i2, bs, bi)) {
+          br = r;
+          bs = s2;
+          bi = i2;
+        }
+      }
+      sh.cand_score[c] = bs;
+      sh.cand_idx[c] = bi;
+      ++head[br];
+    }
+  }
+  named_barrier(6, search_dev::SS_THREADS);
+  search_dev::search_walk_reorder(a.st, t + 1, parity, 0, tid, [] { named_barrier(6, search_dev::SS_THREADS); }, sh);
+}
+
+__device__ __forceinline__ void preload_qkv(const MegaArgs& a, int l, int gw, int lane, uint4 (&wA)[1][3]) {
+  // UNCONDITIONAL (out-of-range warps re-read the last column): a conditional definition would keep the registers alive
+  // around the whole layer loop in the compiler's view
+  const bf16* const wr[1] = {a.layer[l].w_qkv + (size_t)min(gw, 3 * H - 1) * H};
+  load768<1>(wr, lane, wA);
+}
+// fc2 weights of one CTA column block: 3 columns of this warp's column group x its (at most) two 256-wide K slices
+__device__ __forceinline__ void load_fc2(const bf16* __restrict__ w_fc2, int ffn, int c0, int vw, int lane, uint4 (&w)[3][2]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int k0 = (vw + 8 * r) * 256 + lane * 8;
+      w[c][r] = (c0 + c < H && k0 < ffn) ? __ldg(reinterpret_cast<const uint4*>(w_fc2 + (size_t)(c0 + c) * ffn + k0)) : make_uint4(0, 0, 0, 0);
+    }
+}
+
 struct Smem {
   uint4* xs;     // [4][HV] layer input (normalised), the attention sub-layer's residual
   uint4* cs;     // [4][HV] LN_a output: fc1 input, fc2 residual
@@ -211,6 +311,30 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
   constexpr int NB = MT >= 4 ? 4 : (MT >= 2 ? 2 : 1);
   const int chunks = (M + NB - 1) / NB;
   const int n_vcta = a.heads * chunks * a.splits;
+  __shared__ search_dev::SearchSmem sh;
+  __shared__ float wred[MEGA_WARPS];
+  // optional phase trace (gitb200_debug_persistent_decode_trace): SM cycles CTA 0 spends working in / waiting after each phase
+  const bool tracing = a.trace != nullptr && b == 0 && tid == 0;
+  long long t_prev = tracing ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (tracing) {
+      const long long now = clock64();
+      a.trace[slot] += (unsigned long long)(now - t_prev);
+      t_prev = now;
+    }
+  };
+  auto barrier = [&](int slot) {
+    __syncthreads();
+    mark(slot);          // work of this phase (CTA 0's share)
+    grid_barrier(a.barrier, bar_target, G);
+    mark(slot + 16);     // waiting for the other CTAs + the barrier itself
+  };
+
+  // weights of a phase's first columns, fetched before the barrier in front of the phase
+  uint4 wA[1][3], wC[1][3], wD[2][3], wE[3][2], wV[4][3];
+  const int cols_per_cta = 6, n_cta_cols = (H + cols_per_cta - 1) / cols_per_cta;  // fc2: columns per CTA
+  const int vw = wid & 7, cg = wid >> 3;                                             // fc2: K-slice warp, column group
+  preload_qkv(a, 0, gw, lane, wA);
 
   for (int t = 0; t < a.steps; ++t) {
     const int parity = t & 1;
@@ -233,9 +357,12 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
         __syncthreads();
       }
       for (int n = gw; n < 3 * H; n += n_gw) {
-        const bf16* const wr[1] = {L.w_qkv + (size_t)n * H};
+        if (n != gw) {
+          const bf16* const wr[1] = {L.w_qkv + (size_t)n * H};
+          load768<1>(wr, lane, wA);
+        }
         float acc[MT][1];
-        dot768<MT, 1>(wr, sm.xs, lane, acc);
+        fma768<MT, 1>(wA, sm.xs, lane, acc);
         if (lane < M) {
           const float v = pick<MT, 1>(acc, lane, 0) + L.b_qkv[n];
           const bf16 o = __float2bfloat16(v);
@@ -243,36 +370,20 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           if (n >= H) L.txt_kv[((size_t)t * M + lane) * 2 * H + (n - H)] = o;
         }
       }
-      grid_barrier(a.barrier, bar_target, G);
+      barrier(0);
 
       // ---------------------------------------------------------------- B: attention (virtual 128-thread CTAs)
+      attention_phase<NB>(a, L, sm.attn, attn_floats, t, parity, M, chunks, n_vcta);
       {
-        TextAttnArgs ta;
-        ta.q = a.tq; ta.ldq = 3 * H; ta.n_clips = 1; ta.rows_per_clip = M; ta.heads = a.heads;
-        ta.vis_kv = L.vis_kv; ta.ld_vis = 3 * H; ta.k_off = H; ta.v_off = 2 * H; ta.Nv = a.Nv;
-        ta.txt_kv = L.txt_kv; ta.txt_slots = M; ta.text_slot_is_clip = 0;
-        ta.anc = a.st.reorder_cache ? (parity ? a.st.anc_tmp : a.st.anc) : nullptr;
-        ta.anc_ld = a.st.max_len; ta.n_text = nullptr; ta.n_text_const = t + 1; ta.max_text = a.st.max_len;
-        ta.out = a.ta; ta.ldo = H; ta.partial = a.partial; ta.splits = a.splits;
-        const int vslot = tid >> 7, vtid = tid & 127;
-        float* scratch = sm.attn + (size_t)vslot * attn_floats;
-        for (int v = b + G * vslot; v < n_vcta; v += G * VCTAS) {
-          const int h = v % a.heads, rest = v / a.heads;
-          text_attn_dev::text_attention_body<NB, true>(ta, a.scale_log2, a.kcap, scratch, 0, rest % chunks, h, rest / chunks, vtid,
-                                                       [vslot] { named_barrier(1 + vslot, text_attn_dev::TA_THREADS); });
-          named_barrier(1 + vslot, text_attn_dev::TA_THREADS);  // scratch reuse by the next virtual CTA of this slot
-        }
+        const bf16* const wr[1] = {L.w_out + (size_t)min(gw, H - 1) * H};
+        load768<1>(wr, lane, wC);
       }
-      grid_barrier(a.barrier, bar_target, G);
+      barrier(1);
 
       // ---------------------------------------------------------------- C: combine + output projection + residual x
       if (b * MEGA_WARPS < H) {
         if (a.splits > 1) {
-          for (int task = wid; task < M * a.heads; task += MEGA_WARPS) {
-            const int m = task / a.heads, h = task % a.heads;
-            const uint32_t u = text_attn_dev::combine_partials<true>(a.partial + (size_t)task * a.splits * (text_attn_dev::HD + 2), a.splits, lane);
-            reinterpret_cast<uint32_t*>(sm.as + m * HV)[h * 32 + lane] = u;
-          }
+          combine_phase(a, sm.as, M);
         } else {
           for (int i = tid; i < M * HV; i += MEGA_THREADS) sm.as[i] = __ldcg(reinterpret_cast<const uint4*>(a.ta) + i);
         }
@@ -280,9 +391,12 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           for (int i = tid; i < (MT - M) * HV; i += MEGA_THREADS) sm.as[M * HV + i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         for (int n = gw; n < H; n += n_gw) {
-          const bf16* const wr[1] = {L.w_out + (size_t)n * H};
+          if (n != gw) {
+            const bf16* const wr[1] = {L.w_out + (size_t)n * H};
+            load768<1>(wr, lane, wC);
+          }
           float acc[MT][1];
-          dot768<MT, 1>(wr, sm.as, lane, acc);
+          fma768<MT, 1>(wC, sm.as, lane, acc);
           if (lane < M) {
             float v = pick<MT, 1>(acc, lane, 0) + L.b_out[n];
             v += __bfloat162float(reinterpret_cast<const bf16*>(sm.xs + lane * HV)[n]);
@@ -290,7 +404,11 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           }
         }
       }
-      grid_barrier(a.barrier, bar_target, G);
+      {
+        const bf16* const wr[2] = {L.w_fc1 + (size_t)min(gw, ffn - 1) * H, L.w_fc1 + (size_t)min(gw + n_gw, ffn - 1) * H};
+        load768<2>(wr, lane, wD);
+      }
+      barrier(2);
 
       // ---------------------------------------------------------------- D: c = LN_a(tb); fc1 + GELU
       if (wid < M) ln_row_to_smem(a.tb + (size_t)wid * H, L.lna_g, L.lna_b, a.ln_eps, sm.cs + wid * HV, lane);
@@ -299,53 +417,55 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       __syncthreads();
       for (int n = gw; n < ffn; n += 2 * n_gw) {
         const int n2 = n + n_gw;
-        const bf16* const wr[2] = {L.w_fc1 + (size_t)n * H, n2 < ffn ? L.w_fc1 + (size_t)n2 * H : nullptr};
+        if (n != gw) {
+          const bf16* const wr[2] = {L.w_fc1 + (size_t)n * H, n2 < ffn ? L.w_fc1 + (size_t)n2 * H : nullptr};
+          load768<2>(wr, lane, wD);
+        }
         float acc[MT][2];
-        dot768<MT, 2>(wr, sm.cs, lane, acc);
+        fma768<MT, 2>(wD, sm.cs, lane, acc);
         if (lane < 2 * M) {
           const int m = lane >> 1, c = lane & 1, nn = c ? n2 : n;
           if (nn < ffn) a.tf[(size_t)m * ffn + nn] = __float2bfloat16(gelu_erf(pick<MT, 2>(acc, m, c) + L.b_fc1[nn]));
         }
       }
-      grid_barrier(a.barrier, bar_target, G);
+      load_fc2(L.w_fc2, ffn, min(b, n_cta_cols - 1) * cols_per_cta + cg * 3, vw, lane, wE);
+      barrier(3);
 
       // ---------------------------------------------------------------- E: fc2 (split K, fixed-order reduction) + residual c
       {
         // columns of this CTA: 3 per 8-warp half, the same warp -> K-slice assignment as gemv_skinny's split-K kernel
         // (virtual warp w takes the 256-wide slices w, w + 8, ...; partials added in the order w = 0 .. 7)
-        const int cols_per_cta = 6, n_cta_cols = (H + cols_per_cta - 1) / cols_per_cta;
         for (int cb = b; cb < n_cta_cols; cb += G) {
           for (int i = tid; i < M * (ffn / 8); i += MEGA_THREADS) sm.tfs[i] = __ldcg(reinterpret_cast<const uint4*>(a.tf) + i);
+          if (cb != b) load_fc2(L.w_fc2, ffn, cb * cols_per_cta + cg * 3, vw, lane, wE);
           __syncthreads();
-          const int vw = wid & 7, cg = wid >> 3;
-          const int c0 = cb * cols_per_cta + cg * 3;
           float acc[MT][3];
 #pragma unroll
           for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int c = 0; c < 3; ++c) acc[m][c] = 0.f;
-          for (int k0 = vw * 256 + lane * 8; k0 < ffn; k0 += 8 * 256) {
-            uint4 wv[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              wv[c] = (c0 + c < H) ? __ldg(reinterpret_cast<const uint4*>(L.w_fc2 + (size_t)(c0 + c) * ffn + k0)) : make_uint4(0, 0, 0, 0);
-            float xf[MT][8];
+          for (int r = 0; r < 2; ++r) {  // slices vw, vw + 8 (ffn <= 4096: at most two per virtual warp)
+            const int k0 = (vw + 8 * r) * 256 + lane * 8;
+            if (k0 < ffn) {
+              float xf[MT][8];
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              if (m < M) unpack8(sm.tfs[m * (ffn / 8) + (k0 >> 3)], xf[m]);
-              else {
+              for (int m = 0; m < MT; ++m) {
+                if (m < M) unpack8(sm.tfs[m * (ffn / 8) + (k0 >> 3)], xf[m]);
+                else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xf[m][i] = 0.f;
+                  for (int i = 0; i < 8; ++i) xf[m][i] = 0.f;
+                }
               }
-            }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float wf[8];
-              unpack8(wv[c], wf);
+              for (int c = 0; c < 3; ++c) {
+                float wf[8];
+                unpack8(wE[c][r], wf);
 #pragma unroll
-              for (int m = 0; m < MT; ++m)
+                for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[m][c] = fmaf(xf[m][i], wf[i], acc[m][c]);
+                  for (int i = 0; i < 8; ++i) acc[m][c] = fmaf(xf[m][i], wf[i], acc[m][c]);
+              }
             }
           }
 #pragma unroll
@@ -370,7 +490,17 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           __syncthreads();
         }
       }
-      grid_barrier(a.barrier, bar_target, G);
+      if (l + 1 < a.n_layers) {
+        preload_qkv(a, l + 1, gw, lane, wA);
+        barrier(4);
+      }
+    }
+    {  // (the last layer's closing barrier, with the vocabulary head's first weights in flight)
+      const int n = min(gw * 4, a.vocab_pad - 4);
+      const bf16* const wrc[4] = {a.w_vocab + (size_t)n * H, a.w_vocab + (size_t)(n + 1) * H, a.w_vocab + (size_t)(n + 2) * H,
+                                  a.w_vocab + (size_t)(n + 3) * H};
+      load768<4>(wrc, lane, wV);
+      barrier(4);
     }
 
     // ------------------------------------------------------------------ vocabulary head: x = LN_o(tb); logits
@@ -379,32 +509,67 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       if (wid < M) ln_row_to_smem(a.tb + (size_t)wid * H, Ll.lno_g, Ll.lno_b, a.ln_eps, sm.xs + wid * HV, lane);
       __syncthreads();
       float* logits = a.logits + (size_t)t * a.logits_step_stride;
-      const int cpw = (a.vocab_pad + n_gw - 1) / n_gw;         // columns per warp (contiguous block)
-      const int n_begin = gw * cpw, n_end = min(a.vocab_pad, n_begin + cpw);
-      for (int n = n_begin; n < n_end; n += 4) {
-        const bf16* wr[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) wr[c] = n + c < n_end ? a.w_vocab + (size_t)(n + c) * H : nullptr;
-        const bf16* const wrc[4] = {wr[0], wr[1], wr[2], wr[3]};
+      // groups of 4 consecutive columns dealt round-robin to all warps of the grid (7680 groups over 2368 warps: 3-4 each)
+      const int n_end = a.vocab_pad;
+      for (int n = gw * 4; n < n_end; n += n_gw * 4) {
+        if (n != gw * 4) {
+          const bf16* const wrc[4] = {a.w_vocab + (size_t)n * H, a.w_vocab + (size_t)(n + 1) * H, a.w_vocab + (size_t)(n + 2) * H,
+                                      a.w_vocab + (size_t)(n + 3) * H};
+          load768<4>(wrc, lane, wV);
+        }
         float acc[MT][4];
-        dot768<MT, 4>(wrc, sm.xs, lane, acc);
+        fma768<MT, 4>(wV, sm.xs, lane, acc);
         if (lane < 4 * M) {
           const int m = lane >> 2, c = lane & 3;
-          if (n + c < n_end) logits[(size_t)m * a.vocab_pad + n + c] = pick<MT, 4>(acc, m, c) + a.b_vocab[n + c];
+          logits[(size_t)m * a.vocab_pad + n + c] = pick<MT, 4>(acc, m, c) + a.b_vocab[n + c];
         }
       }
-      grid_barrier(a.barrier, bar_target, G);
+      barrier(5);
 
-      // ---------------------------------------------------------------- search step (CTA 0, first 256 threads)
-      if (b == 0 && tid < search_dev::SS_THREADS)
-        search_dev::search_step_device<true>(a.st, logits, t + 1, parity, 0, tid, [] { named_barrier(6, search_dev::SS_THREADS); });
-      grid_barrier(a.barrier, bar_target, G);
+      // ---------------------------------------------------------------- search step, part 1: one CTA per beam row.
+      // The launch path's per-clip search CTA walks the rows' 30522 logits three times from L2 with 256 threads (latency
+      // bound: 67 us greedy / 270 us beam 4 per step when run as one CTA here).  Instead CTA r stages row r in shared memory
+      // (one round of 16-byte loads by all 512 threads), computes its log-softmax statistics and its exact top-C there -- the
+      // SAME arithmetic in the same order -- and publishes C candidates; the clip's top-C is the top-C of the rows' top-Cs.
+      if (b < M) {
+        float* stage = reinterpret_cast<float*>(sm.xs);  // the whole dynamic shared memory: nothing in it is live here
+        const float4* xr = reinterpret_cast<const float4*>(logits + (size_t)b * a.vocab_pad);
+        const int n4 = (a.st.V + 3) / 4;
+        float tmax = -INFINITY;  // maximum of the logits this thread stages (row maximum + selection threshold, search_row_staged)
+        for (int i0 = tid; i0 < n4; i0 += 8 * MEGA_THREADS) {  // 8 independent 16-byte loads per thread in flight
+          float4 v8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (i0 + j * MEGA_THREADS < n4) v8[j] = __ldcg(xr + i0 + j * MEGA_THREADS);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int i4 = i0 + j * MEGA_THREADS;
+            if (i4 < n4) {
+              reinterpret_cast<float4*>(stage)[i4] = v8[j];
+              const int i = 4 * i4;  // elements beyond V (the padded tail of the last vector) do not count
+              if (i < a.st.V) tmax = fmaxf(tmax, v8[j].x);
+              if (i + 1 < a.st.V) tmax = fmaxf(tmax, v8[j].y);
+              if (i + 2 < a.st.V) tmax = fmaxf(tmax, v8[j].z);
+              if (i + 3 < a.st.V) tmax = fmaxf(tmax, v8[j].w);
+            }
+          }
+        }
+        __syncthreads();
+        search_row_phase(a, stage, tmax, b, sh, wred);
+      }
+      barrier(6);
+      // ---------------------------------------------------------------- part 2 (CTA 0): merge, candidate walk, re-order
+      if (b == 0 && tid < search_dev::SS_THREADS) search_walk_phase(a, M, t, parity, sh);
+      preload_qkv(a, 0, gw, lane, wA);  // the next step's first weights
+      barrier(7);
     }
     // model.py:640 `if all(done): break`: the clip's search is finished, later steps would not change anything
     if (__ldcg(a.st.done) != 0) break;
   }
+  if (tracing) a.trace[15] += 1;
 }
 
+template <int MT>  // rows padded to 1 / 2 / 4: one kernel each (own register allocation)
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a, int attn_floats) {
   extern __shared__ uint4 smem_mega[];
   Smem sm;
@@ -414,15 +579,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   sm.tfs = sm.as + 4 * HV;
   sm.red2 = reinterpret_cast<float*>(sm.tfs + 4 * (a.ffn / 8));
   sm.attn = sm.red2 + 2 * 8 * 4 * 3;
-  if (a.rows <= 1) mega_body<1>(a, sm, attn_floats);
-  else if (a.rows <= 2) mega_body<2>(a, sm, attn_floats);
-  else mega_body<4>(a, sm, attn_floats);
+  mega_body<MT>(a, sm, attn_floats);
 }
 
 size_t mega_smem_bytes(const MegaArgs& a, int* attn_floats) {
   const int nb = a.rows > 2 ? 4 : (a.rows == 2 ? 2 : 1);  // = NB of mega_body<MT> (3 rows share one 4-row virtual CTA: per-row arithmetic does not depend on it)
   *attn_floats = nb * a.kcap + text_attn_dev::TA_GROUPS * nb * text_attn_dev::HD;
-  return (size_t)(3 * 4 * HV + 4 * (a.ffn / 8)) * sizeof(uint4) + (size_t)(2 * 8 * 4 * 3 + VCTAS * *attn_floats) * sizeof(float);
+  const size_t layers = (size_t)(3 * 4 * HV + 4 * (a.ffn / 8)) * sizeof(uint4) + (size_t)(2 * 8 * 4 * 3 + VCTAS * *attn_floats) * sizeof(float);
+  const size_t search = (size_t)((a.st.V + 3) / 4) * sizeof(float4);  // one staged logits row
+  return layers > search ? layers : search;
 }
 
 }  // namespace
@@ -461,13 +626,16 @@ cudaError_t decode_mega(const MegaArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_mega_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if (!coop || n_sm < 8) return cudaErrorNotSupported;
+  void (*kernel)(const MegaArgs, int) = a.rows <= 1 ? decode_mega_kernel<1> : (a.rows <= 2 ? decode_mega_kernel<2> : decode_mega_kernel<4>);
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, MEGA_THREADS, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MEGA_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorNotSupported;
   e = cudaMemsetAsync(a.barrier, 0, sizeof(unsigned int), stream);
@@ -482,7 +650,7 @@ cudaError_t decode_mega(const MegaArgs& a, cudaStream_t stream) {
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, decode_mega_kernel, a, attn_floats);
+  e = cudaLaunchKernelEx(&cfg, kernel, a, attn_floats);
   if (e != cudaSuccess) return e;
   note_launch();
   return cudaGetLastError();

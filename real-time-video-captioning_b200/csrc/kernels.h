@@ -195,6 +195,9 @@ struct MegaArgs {
   bf16 *tq, *ta, *tb, *tf;  // scratch rows: [rows, 3H], [rows, H], [rows, H], [rows, ffn]
   float* partial;           // key-split partials of the attention
   unsigned int* barrier;    // grid barrier counter (reset by the launcher)
+  unsigned long long* trace;  // optional [32]: SM cycles of CTA 0 per phase (0-7: work, 16-23: barrier wait; 15: launches)
+  float* cand_score;        // [rows * st.cand] every beam row's own top candidates (search step, part 1 -> part 2)
+  int* cand_idx;
   SearchState st;
 };
 bool decode_mega_supported(const MegaArgs& a);

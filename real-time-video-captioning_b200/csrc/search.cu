@@ -21,7 +21,8 @@ using search_dev::MAX_NB;
 using search_dev::SS_THREADS;
 
 __global__ void __launch_bounds__(SS_THREADS) search_step_kernel(SearchState st, const float* __restrict__ logits, int cur_len, int parity) {
-  search_dev::search_step_device<false>(st, logits, cur_len, parity, blockIdx.x, threadIdx.x, [] { __syncthreads(); });
+  __shared__ search_dev::SearchSmem sh;
+  search_dev::search_step_device<false>(st, logits, cur_len, parity, blockIdx.x, threadIdx.x, [] { __syncthreads(); }, sh);
 }
 
 __global__ void search_init_kernel(SearchState st, int sos) {

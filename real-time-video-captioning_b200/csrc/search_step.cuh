@@ -13,91 +13,121 @@ constexpr int MAX_NB = 8;
 
 __device__ __forceinline__ bool better(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
 
-// One search step of clip `clip`, executed by SS_THREADS threads (tid = 0 .. SS_THREADS-1) that meet in sync()
-// (search_step_kernel: one CTA per clip, __syncthreads; the persistent single-clip decode kernel calls it from the first
-// SS_THREADS threads of its CTA 0 with a named barrier).  COHERENT: the logits were written by other CTAs of the same launch.
-template <bool COHERENT, class Sync>
-__device__ __forceinline__ void search_step_device(const SearchState& st, const float* __restrict__ logits, int cur_len, int parity,
-                                                   int clip, int tid, Sync sync) {
-  __shared__ float red_f[SS_THREADS / 32];
-  __shared__ int red_i[SS_THREADS / 32];
-  __shared__ float row_lse_max[MAX_NB], row_lse[MAX_NB];
-  __shared__ float cand_score[MAX_CAND];
-  __shared__ int cand_idx[MAX_CAND];
-  __shared__ int nxt_parent[MAX_NB], nxt_word[MAX_NB];
-  __shared__ float nxt_score[MAX_NB];
-  __shared__ float bc_f;
-  __shared__ int bc_i;
+struct SearchSmem {
+  float red_f[SS_THREADS / 32];
+  int red_i[SS_THREADS / 32];
+  float row_lse_max[MAX_NB], row_lse[MAX_NB];
+  float cand_score[MAX_CAND];
+  int cand_idx[MAX_CAND];
+  int nxt_parent[MAX_NB], nxt_word[MAX_NB];
+  float nxt_score[MAX_NB];
+  float bc_f;
+  int bc_i;
+  static constexpr int LIST_CAP = 192;  // candidates at or above the selection threshold (expected: C plus a few)
+  int list_n;
+  float list_s[LIST_CAP];
+  int list_i[LIST_CAP];
+};
 
+// Parts 1 + 2 of a search step for the beam rows [b_begin, b_end) of clip `clip`: log-softmax statistics of every row, then
+// the exact top-C (C = st.cand) of (log_softmax + beam_score) over those rows' V candidates each, ordered by `better`, into
+// sh.cand_score / sh.cand_idx (candidate id = b * V + word).  load(b, i) returns logit i of beam row b.
+// Executed by SS_THREADS threads (tid = 0 .. SS_THREADS-1) that meet in sync().
+// prof (optional, debugging): thread 0 adds the SM cycles of the five sections to prof[0..4].
+template <class Load, class Sync>
+__device__ __forceinline__ void search_topc_rows(const SearchState& st, Load load, int b_begin, int b_end, int clip, int tid, Sync sync,
+                                                 SearchSmem& sh, unsigned long long* prof = nullptr) {
   const int warp = tid >> 5, lane = tid & 31;
-  auto ldx = [](const float* q) { return COHERENT ? __ldcg(q) : *q; };
   const int nb = st.nb, V = st.V, C = st.cand;
-  const int* tok_in = parity ? st.tokens_tmp : st.tokens;
-  int* tok_out = parity ? st.tokens : st.tokens_tmp;
-  const int* anc_in = parity ? st.anc_tmp : st.anc;
-  int* anc_out = parity ? st.anc : st.anc_tmp;
-
+  long long t_prof = (prof != nullptr && tid == 0) ? clock64() : 0;
+  auto section = [&](int k) {
+    if (prof != nullptr && tid == 0) {
+      const long long now = clock64();
+      prof[k] += (unsigned long long)(now - t_prof);
+      t_prof = now;
+    }
+  };
   // ---- 1. log-softmax statistics per beam row: max, then log(sum(exp(x - max)))   (model.py:557)
-  for (int b = 0; b < nb; ++b) {
-    const float* x = logits + (size_t)(clip * nb + b) * st.ldl;
+  for (int b = b_begin; b < b_end; ++b) {
+    // (the loops below fetch 8 logits per thread before using them: the loads are independent, the uses keep their order)
     float m = -INFINITY;
-    for (int i = tid; i < V; i += SS_THREADS) m = fmaxf(m, ldx(x + i));
+    for (int i0 = tid; i0 < V; i0 += 8 * SS_THREADS) {
+      float x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = i0 + j * SS_THREADS < V ? load(b, i0 + j * SS_THREADS) : -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, x8[j]);
+    }
     m = warp_max(m);
-    if (lane == 0) red_f[warp] = m;
+    if (lane == 0) sh.red_f[warp] = m;
     sync();
     if (tid == 0) {
-      float mm = red_f[0];
-      for (int w = 1; w < SS_THREADS / 32; ++w) mm = fmaxf(mm, red_f[w]);
-      bc_f = mm;
+      float mm = sh.red_f[0];
+      for (int w = 1; w < SS_THREADS / 32; ++w) mm = fmaxf(mm, sh.red_f[w]);
+      sh.bc_f = mm;
     }
     sync();
-    m = bc_f;
+    m = sh.bc_f;
     float s = 0.f;
-    for (int i = tid; i < V; i += SS_THREADS) s += expf(ldx(x + i) - m);
+    for (int i0 = tid; i0 < V; i0 += 8 * SS_THREADS) {
+      float x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = i0 + j * SS_THREADS < V ? load(b, i0 + j * SS_THREADS) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j * SS_THREADS < V) s += expf(x8[j] - m);
+    }
     s = warp_sum(s);
     sync();
-    if (lane == 0) red_f[warp] = s;
+    if (lane == 0) sh.red_f[warp] = s;
     sync();
     if (tid == 0) {
       float ss = 0.f;
-      for (int w = 0; w < SS_THREADS / 32; ++w) ss += red_f[w];
-      row_lse_max[b] = m;
-      row_lse[b] = logf(ss);
+      for (int w = 0; w < SS_THREADS / 32; ++w) ss += sh.red_f[w];
+      sh.row_lse_max[b] = m;
+      sh.row_lse[b] = logf(ss);
     }
     sync();
   }
 
-  // ---- 2. top-C of (log_softmax + beam_score) over nb * V candidates               (model.py:561-565)
-  float ls[MAX_CAND];
-  int li[MAX_CAND];
+  section(0);
+  // ---- 2. top-C of (log_softmax + beam_score) over the rows' V candidates each     (model.py:561-565)
+  // Exact selection in three sweeps without per-thread sorted lists (a sorted insertion by ANY lane stalls its whole warp, and
+  // with C = 8 some lane inserts at nearly every element):
+  //   a. every thread's single best candidate, in registers;
+  //   b. C rounds of block-wide argmax over those 256 bests -> T = the C-th of them: at least C candidates are >= T, so the
+  //      top-C all lie at or above T;
+  //   c. every candidate at or above T (a handful) is appended to a shared list; each list entry's rank among the list
+  //      (number of entries that beat it in the total order `better`) places it: ranks 0 .. C-1 are the answer, in order.
+  // The order `better` is total (ids are unique), so the result is THE top-C in THE order: the same as any other exact method.
+  const auto score_of = [&](int b, int i, float m, float l, float bs) { return ((load(b, i) - m) - l) + bs; };
+  float best_s = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int b = b_begin; b < b_end; ++b) {
+    const float m = sh.row_lse_max[b], l = sh.row_lse[b], bs = __ldcg(st.beam_scores + clip * nb + b);
+    for (int i0 = tid; i0 < V; i0 += 8 * SS_THREADS) {
+      float x8[8];
 #pragma unroll
-  for (int j = 0; j < MAX_CAND; ++j) {
-    ls[j] = -INFINITY;
-    li[j] = 0x7fffffff;
-  }
-  for (int b = 0; b < nb; ++b) {
-    const float* x = logits + (size_t)(clip * nb + b) * st.ldl;
-    const float m = row_lse_max[b], l = row_lse[b], bs = st.beam_scores[clip * nb + b];
-    for (int i = tid; i < V; i += SS_THREADS) {
-      const float sc = ((ldx(x + i) - m) - l) + bs;
-      const int id = b * V + i;
-      if (better(sc, id, ls[C - 1], li[C - 1])) {
-        // insertion into the sorted local list (C is tiny)
-        int j = C - 1;
-        while (j > 0 && better(sc, id, ls[j - 1], li[j - 1])) {
-          ls[j] = ls[j - 1];
-          li[j] = li[j - 1];
-          --j;
+      for (int j = 0; j < 8; ++j) x8[j] = i0 + j * SS_THREADS < V ? load(b, i0 + j * SS_THREADS) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * SS_THREADS;
+        if (i < V) {
+          const float sc = ((x8[j] - m) - l) + bs;
+          if (better(sc, b * V + i, best_s, best_i)) {
+            best_s = sc;
+            best_i = b * V + i;
+          }
         }
-        ls[j] = sc;
-        li[j] = id;
       }
     }
   }
-  int head = 0;  // next unconsumed entry of this thread's sorted list
+  section(1);
+  float thr_s = -INFINITY;
+  int thr_i = 0x7fffffff;
   for (int c = 0; c < C; ++c) {
-    float bs_ = head < C ? ls[head] : -INFINITY;
-    int bi_ = head < C ? li[head] : 0x7fffffff;
+    float bs_ = best_s;
+    int bi_ = best_i;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float s2 = __shfl_xor_sync(0xffffffffu, bs_, o);
@@ -108,26 +138,234 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
       }
     }
     if (lane == 0) {
-      red_f[warp] = bs_;
-      red_i[warp] = bi_;
+      sh.red_f[warp] = bs_;
+      sh.red_i[warp] = bi_;
     }
     sync();
     if (tid == 0) {
-      float s = red_f[0];
-      int i = red_i[0];
+      float s = sh.red_f[0];
+      int i = sh.red_i[0];
       for (int w = 1; w < SS_THREADS / 32; ++w)
-        if (better(red_f[w], red_i[w], s, i)) {
-          s = red_f[w];
-          i = red_i[w];
+        if (better(sh.red_f[w], sh.red_i[w], s, i)) {
+          s = sh.red_f[w];
+          i = sh.red_i[w];
         }
-      cand_score[c] = s;
-      cand_idx[c] = i;
-      bc_i = i;
+      sh.bc_f = s;
+      sh.bc_i = i;
     }
     sync();
-    if (head < C && li[head] == bc_i) ++head;  // candidate ids are unique, exactly one thread pops
+    thr_s = sh.bc_f;
+    thr_i = sh.bc_i;
+    if (best_i == thr_i) {  // this thread's best was taken (ids are unique): it leaves the contest
+      best_s = -INFINITY;
+      best_i = 0x7fffffff;
+    }
     sync();
   }
+  section(2);
+  if (tid == 0) sh.list_n = 0;
+  sync();
+  for (int b = b_begin; b < b_end; ++b) {
+    const float m = sh.row_lse_max[b], l = sh.row_lse[b], bs = __ldcg(st.beam_scores + clip * nb + b);
+    for (int i0 = tid; i0 < V; i0 += 8 * SS_THREADS) {
+      float x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = i0 + j * SS_THREADS < V ? load(b, i0 + j * SS_THREADS) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * SS_THREADS;
+        if (i < V) {
+          const float sc = ((x8[j] - m) - l) + bs;
+          if (!better(thr_s, thr_i, sc, b * V + i)) {  // at or above the threshold
+            const int slot = atomicAdd(&sh.list_n, 1);
+            if (slot < SearchSmem::LIST_CAP) {
+              sh.list_s[slot] = sc;
+              sh.list_i[slot] = b * V + i;
+            }
+          }
+        }
+      }
+    }
+  }
+  sync();
+  section(3);
+  const int n_list = sh.list_n;
+  if (n_list <= SearchSmem::LIST_CAP) {
+    for (int e = tid; e < n_list; e += SS_THREADS) {
+      const float se = sh.list_s[e];
+      const int ie = sh.list_i[e];
+      int rank = 0;
+      for (int f = 0; f < n_list; ++f) rank += better(sh.list_s[f], sh.list_i[f], se, ie) ? 1 : 0;
+      if (rank < C) {
+        sh.cand_score[rank] = se;
+        sh.cand_idx[rank] = ie;
+      }
+    }
+  } else {
+    // (never seen: more than LIST_CAP candidates above the C-th best thread maximum)  Exact fallback: C rounds of block-wide
+    // argmax over ALL candidates below the previous pick.
+    float prev_s = INFINITY;
+    int prev_i = -1;
+    for (int c = 0; c < C; ++c) {
+      float bs_ = -INFINITY;
+      int bi_ = 0x7fffffff;
+      for (int b = b_begin; b < b_end; ++b) {
+        const float m = sh.row_lse_max[b], l = sh.row_lse[b], bs = __ldcg(st.beam_scores + clip * nb + b);
+        for (int i = tid; i < V; i += SS_THREADS) {
+          const float sc = score_of(b, i, m, l, bs);
+          const int id = b * V + i;
+          if (better(prev_s, prev_i, sc, id) && better(sc, id, bs_, bi_)) {
+            bs_ = sc;
+            bi_ = id;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, bs_, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi_, o);
+        if (better(s2, i2, bs_, bi_)) {
+          bs_ = s2;
+          bi_ = i2;
+        }
+      }
+      if (lane == 0) {
+        sh.red_f[warp] = bs_;
+        sh.red_i[warp] = bi_;
+      }
+      sync();
+      if (tid == 0) {
+        float s = sh.red_f[0];
+        int i = sh.red_i[0];
+        for (int w = 1; w < SS_THREADS / 32; ++w)
+          if (better(sh.red_f[w], sh.red_i[w], s, i)) {
+            s = sh.red_f[w];
+            i = sh.red_i[w];
+          }
+        sh.cand_score[c] = s;
+        sh.cand_idx[c] = i;
+      }
+      sync();
+      prev_s = sh.cand_score[c];
+      prev_i = sh.cand_idx[c];
+      sync();
+    }
+  }
+  sync();
+  section(4);
+}
+
+// Parts 1 + 2 for ONE beam row whose V logits sit in shared memory (persistent single-clip decode kernel: one CTA per row),
+// executed by ALL n_threads threads of the CTA (n_threads >= SS_THREADS, tid = 0 .. n_threads-1, meeting in sync_all();
+// sync_ss() is a barrier over the first SS_THREADS threads only).  thread_max = the maximum of the logits THIS thread staged.
+// Same results as search_topc_rows over that row, bit for bit:
+//   * the row maximum is exact whatever the order; the sum of exponentials runs on the first SS_THREADS threads in
+//     search_topc_rows' order (thread t adds elements t, t + SS_THREADS, ... in this order, then the same tree);
+//   * selection: x -> ((x - m) - l) + bs is monotone, so with T = the C-th largest of the threads' maxima at least C candidates
+//     score >= score(T), and every member of the top-C does; those few candidates are ranked in the total order `better`.
+template <class SyncAll, class SyncSS>
+__device__ __forceinline__ void search_row_staged(const SearchState& st, const float* xs /* shared: [V] */, float thread_max, int b, int clip,
+                                                  int tid, int n_threads, SyncAll sync_all, SyncSS sync_ss, SearchSmem& sh, float* wred /* shared: [n_threads / 32] */) {
+  const int warp = tid >> 5, lane = tid & 31, n_warps = n_threads >> 5;
+  const int nb = st.nb, V = st.V, C = st.cand;
+  // ---- row maximum, and T = the C-th largest thread maximum (C rounds of block-wide max; the winner leaves the contest)
+  float mine = thread_max, m = 0.f, thr_x = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float v = warp_max(mine);
+    if (lane == 0) wred[warp] = v;
+    sync_all();
+    float top = wred[0];
+    for (int w = 1; w < n_warps; ++w) top = fmaxf(top, wred[w]);
+    if (c == 0) m = top;
+    thr_x = top;
+    // exactly one thread among those holding `top` retires per round (ties: the lowest thread index)
+    const unsigned holders = __ballot_sync(0xffffffffu, mine == top);
+    sync_all();
+    if (holders != 0 && lane == __ffs(holders) - 1) wred[warp] = (float)tid; else if (lane == 0 && holders == 0) wred[warp] = 3.0e38f;
+    sync_all();
+    float first = wred[0];
+    for (int w = 1; w < n_warps; ++w) first = fminf(first, wred[w]);
+    if ((float)tid == first) mine = -INFINITY;
+    sync_all();
+  }
+  // ---- log(sum(exp(x - m))): search_topc_rows' summation order on the first SS_THREADS threads
+  if (tid < SS_THREADS) {
+    float s = 0.f;
+    for (int i0 = tid; i0 < V; i0 += 8 * SS_THREADS) {
+      float x8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x8[j] = i0 + j * SS_THREADS < V ? xs[i0 + j * SS_THREADS] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j * SS_THREADS < V) s += expf(x8[j] - m);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sh.red_f[warp] = s;
+    sync_ss();
+    if (tid == 0) {
+      float ss = 0.f;
+      for (int w = 0; w < SS_THREADS / 32; ++w) ss += sh.red_f[w];
+      sh.row_lse_max[b] = m;
+      sh.row_lse[b] = logf(ss);
+      sh.list_n = 0;
+    }
+  }
+  sync_all();
+  // ---- candidates at or above score(T), then their ranks
+  const float l = sh.row_lse[b], bs = __ldcg(st.beam_scores + clip * nb + b);
+  const float thr_s = ((thr_x - m) - l) + bs;
+  for (int i0 = tid; i0 < V; i0 += 8 * n_threads) {
+    float x8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x8[j] = i0 + j * n_threads < V ? xs[i0 + j * n_threads] : -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sc = ((x8[j] - m) - l) + bs;
+      if (sc >= thr_s && i0 + j * n_threads < V) {
+        const int slot = atomicAdd(&sh.list_n, 1);
+        if (slot < SearchSmem::LIST_CAP) {
+          sh.list_s[slot] = sc;
+          sh.list_i[slot] = b * V + i0 + j * n_threads;
+        }
+      }
+    }
+  }
+  sync_all();
+  const int n_list = sh.list_n;
+  if (n_list <= SearchSmem::LIST_CAP) {
+    for (int e = tid; e < n_list; e += n_threads) {
+      const float se = sh.list_s[e];
+      const int ie = sh.list_i[e];
+      int rank = 0;
+      for (int f = 0; f < n_list; ++f) rank += better(sh.list_s[f], sh.list_i[f], se, ie) ? 1 : 0;
+      if (rank < C) {
+        sh.cand_score[rank] = se;
+        sh.cand_idx[rank] = ie;
+      }
+    }
+    sync_all();
+  } else {
+    // (never seen: a long run of equal logits)  the general routine, on the first SS_THREADS threads
+    if (tid < SS_THREADS) search_topc_rows(st, [xs](int, int i) { return xs[i]; }, b, b + 1, clip, tid, sync_ss, sh);
+    sync_all();
+  }
+}
+
+// Parts 3 + 4 of a search step: the reference's candidate walk over sh.cand_score / sh.cand_idx (the clip's top-C, ordered),
+// then the re-ordering of token rows / the ancestor table.  Same thread / sync contract as above.
+template <class Sync>
+__device__ __forceinline__ void search_walk_reorder(const SearchState& st, int cur_len, int parity, int clip, int tid, Sync sync,
+                                                    SearchSmem& sh) {
+  const int nb = st.nb, V = st.V, C = st.cand;
+  const int* tok_in = parity ? st.tokens_tmp : st.tokens;
+  int* tok_out = parity ? st.tokens : st.tokens_tmp;
+  const int* anc_in = parity ? st.anc_tmp : st.anc;
+  int* anc_out = parity ? st.anc : st.anc_tmp;
+  float* cand_score = sh.cand_score;
+  int* cand_idx = sh.cand_idx;
+  int* nxt_parent = sh.nxt_parent;
+  int* nxt_word = sh.nxt_word;
+  float* nxt_score = sh.nxt_score;
 
   // ---- 3. candidate walk (thread 0), exactly the reference's control flow           (model.py:573-611)
   if (tid == 0) {
@@ -216,5 +454,15 @@ __device__ __forceinline__ void search_step_device(const SearchState& st, const 
   }
 }
 
+// One search step of clip `clip` by one group of SS_THREADS threads (search_step_kernel: one CTA per clip).
+// COHERENT: the logits were written by other CTAs of the same launch.
+template <bool COHERENT, class Sync>
+__device__ __forceinline__ void search_step_device(const SearchState& st, const float* __restrict__ logits, int cur_len, int parity,
+                                                   int clip, int tid, Sync sync, SearchSmem& sh) {
+  const int nb = st.nb, ldl = st.ldl;
+  auto load = [=](int b, int i) { const float* q = logits + (size_t)(clip * nb + b) * ldl + i; return COHERENT ? __ldcg(q) : *q; };
+  search_topc_rows(st, load, 0, nb, clip, tid, sync, sh);
+  search_walk_reorder(st, cur_len, parity, clip, tid, sync, sh);
+}
 
 }  // namespace search_dev
