@@ -856,7 +856,7 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
         ml.vis_kv = c->kv[l].p; ml.txt_kv = c->txt_kv[l].p;
       }
       m.trace = c->mega_trace_on ? c->mega_trace.p : nullptr;
-      m.tq = c->tq.p; m.ta = c->ta.p; m.tb = c->tb.p; m.tf = c->tf.p; m.partial = c->partial.p; m.barrier = c->mega_bar.p;
+      m.tq = c->tq.p; m.ta = c->ta.p; m.tb = c->tb.p; m.tf = c->tf.p; m.partial = c->partial.p; m.barrier = c->mega_bar.p; m.attn_cnt = reinterpret_cast<int*>(c->mega_bar.p + 8);
       m.cand_score = reinterpret_cast<float*>(c->mega_bar.p + 32); m.cand_idx = reinterpret_cast<int*>(c->mega_bar.p + 160);
       CUDA_OK(c, search_init(st, k.sos, s));
       const cudaError_t e = decode_mega(m, s);

@@ -210,19 +210,31 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, const MegaLay
   float* scratch = attn_smem + (size_t)vslot * attn_floats;
   for (int v = b + G * vslot; v < n_vcta; v += G * VCTAS) {
     const int h = v % a.heads, rest = v / a.heads;
-    text_attn_dev::text_attention_body<NB, true>(ta, a.scale_log2, a.kcap, scratch, 0, rest % chunks, h, rest / chunks, vtid,
+    const int chunk = rest % chunks;
+    text_attn_dev::text_attention_body<NB, true>(ta, a.scale_log2, a.kcap, scratch, 0, chunk, h, rest / chunks, vtid,
                                                  [vslot] { named_barrier(1 + vslot, text_attn_dev::TA_THREADS); });
+    if (a.splits > 1) {
+      // The LAST virtual CTA of this (row chunk, head) to finish combines the key splits' partials right here (the launch
+      // path's combine kernel, same arithmetic) and writes the attention output rows -- instead of every CTA of the next phase
+      // combining every (row, head) for itself, which at beam 4 cost more than the projection it fed.
+      __shared__ int s_ticket[VCTAS];
+      __threadfence();  // this thread's partials are visible GPU-wide before the ticket is drawn
+      named_barrier(1 + vslot, text_attn_dev::TA_THREADS);
+      if (vtid == 0) s_ticket[vslot] = atomicAdd(a.attn_cnt + chunk * a.heads + h, 1);
+      named_barrier(1 + vslot, text_attn_dev::TA_THREADS);
+      if (s_ticket[vslot] == a.splits - 1) {
+        __threadfence();
+        const int n_loc = min(NB, M - chunk * NB);
+        for (int r = vtid >> 5; r < n_loc; r += text_attn_dev::TA_THREADS / 32) {
+          const int row = chunk * NB + r;
+          const uint32_t u = text_attn_dev::combine_partials<true>(a.partial + ((size_t)row * a.heads + h) * a.splits * (text_attn_dev::HD + 2),
+                                                                   a.splits, vtid & 31);
+          reinterpret_cast<uint32_t*>(a.ta + (size_t)row * H + h * text_attn_dev::HD)[vtid & 31] = u;
+        }
+        if (vtid == 0) a.attn_cnt[chunk * a.heads + h] = 0;  // ready for the next layer (grid barriers lie in between)
+      }
+    }
     named_barrier(1 + vslot, text_attn_dev::TA_THREADS);  // scratch reuse by the next virtual CTA of this slot
-  }
-}
-
-// ---- phase C prologue: key-split partials of every (row, head) -> the attention output rows in shared memory
-__device__ __forceinline__ void combine_phase(const MegaArgs& a, uint4* as, int M) {
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int task = wid; task < M * a.heads; task += MEGA_WARPS) {
-    const int m = task / a.heads, h = task % a.heads;
-    const uint32_t u = text_attn_dev::combine_partials<true>(a.partial + (size_t)task * a.splits * (text_attn_dev::HD + 2), a.splits, lane);
-    reinterpret_cast<uint32_t*>(as + m * HV)[h * 32 + lane] = u;
   }
 }
 
@@ -274,7 +286,8 @@ __device__ __forceinline__ void search_walk_phase(const MegaArgs& a, int M, int 
   search_dev::search_walk_reorder(a.st, t + 1, parity, 0, tid, [] { named_barrier(6, search_dev::SS_THREADS); }, sh);
 }
 
-__device__ __forceinline__ void preload_qkv(const MegaArgs& a, int l, int gw, int lane, uint4 (&wA)[1][3]) {
+__device__ __forceinline__ void preload_qkv(const MegaArgs& a, int l, int gw, int lane, uint4 (&wA)[1][3], float& bA) {
+  bA = __ldg(a.layer[l].b_qkv + min(gw, 3 * H - 1));
   // UNCONDITIONAL (out-of-range warps re-read the last column): a conditional definition would keep the registers alive
   // around the whole layer loop in the compiler's view
   const bf16* const wr[1] = {a.layer[l].w_qkv + (size_t)min(gw, 3 * H - 1) * H};
@@ -332,9 +345,10 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
 
   // weights of a phase's first columns, fetched before the barrier in front of the phase
   uint4 wA[1][3], wC[1][3], wD[2][3], wE[3][2], wV[4][3];
+  float bA = 0.f, bC = 0.f, bD = 0.f, bE = 0.f, bV = 0.f;  // ... and the bias values this thread's epilogues will add
   const int cols_per_cta = 6, n_cta_cols = (H + cols_per_cta - 1) / cols_per_cta;  // fc2: columns per CTA
   const int vw = wid & 7, cg = wid >> 3;                                             // fc2: K-slice warp, column group
-  preload_qkv(a, 0, gw, lane, wA);
+  preload_qkv(a, 0, gw, lane, wA, bA);
 
   for (int t = 0; t < a.steps; ++t) {
     const int parity = t & 1;
@@ -360,11 +374,12 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
         if (n != gw) {
           const bf16* const wr[1] = {L.w_qkv + (size_t)n * H};
           load768<1>(wr, lane, wA);
+          bA = __ldg(L.b_qkv + n);
         }
         float acc[MT][1];
         fma768<MT, 1>(wA, sm.xs, lane, acc);
         if (lane < M) {
-          const float v = pick<MT, 1>(acc, lane, 0) + L.b_qkv[n];
+          const float v = pick<MT, 1>(acc, lane, 0) + bA;
           const bf16 o = __float2bfloat16(v);
           a.tq[(size_t)lane * 3 * H + n] = o;
           if (n >= H) L.txt_kv[((size_t)t * M + lane) * 2 * H + (n - H)] = o;
@@ -377,16 +392,13 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       {
         const bf16* const wr[1] = {L.w_out + (size_t)min(gw, H - 1) * H};
         load768<1>(wr, lane, wC);
+        bC = __ldg(L.b_out + min(gw, H - 1));
       }
       barrier(1);
 
       // ---------------------------------------------------------------- C: combine + output projection + residual x
       if (b * MEGA_WARPS < H) {
-        if (a.splits > 1) {
-          combine_phase(a, sm.as, M);
-        } else {
-          for (int i = tid; i < M * HV; i += MEGA_THREADS) sm.as[i] = __ldcg(reinterpret_cast<const uint4*>(a.ta) + i);
-        }
+        for (int i = tid; i < M * HV; i += MEGA_THREADS) sm.as[i] = __ldcg(reinterpret_cast<const uint4*>(a.ta) + i);
         if (MT > M)
           for (int i = tid; i < (MT - M) * HV; i += MEGA_THREADS) sm.as[M * HV + i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -394,11 +406,12 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           if (n != gw) {
             const bf16* const wr[1] = {L.w_out + (size_t)n * H};
             load768<1>(wr, lane, wC);
+            bC = __ldg(L.b_out + n);
           }
           float acc[MT][1];
           fma768<MT, 1>(wC, sm.as, lane, acc);
           if (lane < M) {
-            float v = pick<MT, 1>(acc, lane, 0) + L.b_out[n];
+            float v = pick<MT, 1>(acc, lane, 0) + bC;
             v += __bfloat162float(reinterpret_cast<const bf16*>(sm.xs + lane * HV)[n]);
             a.tb[(size_t)lane * H + n] = __float2bfloat16(v);
           }
@@ -407,6 +420,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       {
         const bf16* const wr[2] = {L.w_fc1 + (size_t)min(gw, ffn - 1) * H, L.w_fc1 + (size_t)min(gw + n_gw, ffn - 1) * H};
         load768<2>(wr, lane, wD);
+        bD = __ldg(L.b_fc1 + min(gw + (lane & 1) * n_gw, ffn - 1));  // lane -> (row lane >> 1, column lane & 1)
       }
       barrier(2);
 
@@ -420,15 +434,17 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
         if (n != gw) {
           const bf16* const wr[2] = {L.w_fc1 + (size_t)n * H, n2 < ffn ? L.w_fc1 + (size_t)n2 * H : nullptr};
           load768<2>(wr, lane, wD);
+          bD = __ldg(L.b_fc1 + min(n + (lane & 1) * n_gw, ffn - 1));
         }
         float acc[MT][2];
         fma768<MT, 2>(wD, sm.cs, lane, acc);
         if (lane < 2 * M) {
           const int m = lane >> 1, c = lane & 1, nn = c ? n2 : n;
-          if (nn < ffn) a.tf[(size_t)m * ffn + nn] = __float2bfloat16(gelu_erf(pick<MT, 2>(acc, m, c) + L.b_fc1[nn]));
+          if (nn < ffn) a.tf[(size_t)m * ffn + nn] = __float2bfloat16(gelu_erf(pick<MT, 2>(acc, m, c) + bD));
         }
       }
       load_fc2(L.w_fc2, ffn, min(b, n_cta_cols - 1) * cols_per_cta + cg * 3, vw, lane, wE);
+      bE = __ldg(L.b_fc2 + min(min(b, n_cta_cols - 1) * cols_per_cta + tid % cols_per_cta, H - 1));  // column of the finalising thread
       barrier(3);
 
       // ---------------------------------------------------------------- E: fc2 (split K, fixed-order reduction) + residual c
@@ -437,7 +453,10 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
         // (virtual warp w takes the 256-wide slices w, w + 8, ...; partials added in the order w = 0 .. 7)
         for (int cb = b; cb < n_cta_cols; cb += G) {
           for (int i = tid; i < M * (ffn / 8); i += MEGA_THREADS) sm.tfs[i] = __ldcg(reinterpret_cast<const uint4*>(a.tf) + i);
-          if (cb != b) load_fc2(L.w_fc2, ffn, cb * cols_per_cta + cg * 3, vw, lane, wE);
+          if (cb != b) {
+            load_fc2(L.w_fc2, ffn, cb * cols_per_cta + cg * 3, vw, lane, wE);
+            bE = __ldg(L.b_fc2 + min(cb * cols_per_cta + tid % cols_per_cta, H - 1));
+          }
           __syncthreads();
           float acc[MT][3];
 #pragma unroll
@@ -482,7 +501,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
             if (n < H) {
               float v = 0.f;
               for (int w2 = 0; w2 < 8; ++w2) v += sm.red2[(((j / 3) * 8 + w2) * 4 + m) * 3 + (j % 3)];
-              v += L.b_fc2[n];
+              v += bE;
               v += __bfloat162float(reinterpret_cast<const bf16*>(sm.cs + m * HV)[n]);
               a.tb[(size_t)m * H + n] = __float2bfloat16(v);
             }
@@ -491,7 +510,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
         }
       }
       if (l + 1 < a.n_layers) {
-        preload_qkv(a, l + 1, gw, lane, wA);
+        preload_qkv(a, l + 1, gw, lane, wA, bA);
         barrier(4);
       }
     }
@@ -500,6 +519,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       const bf16* const wrc[4] = {a.w_vocab + (size_t)n * H, a.w_vocab + (size_t)(n + 1) * H, a.w_vocab + (size_t)(n + 2) * H,
                                   a.w_vocab + (size_t)(n + 3) * H};
       load768<4>(wrc, lane, wV);
+      bV = __ldg(a.b_vocab + n + (lane & 3));  // lane -> (row lane >> 2, column lane & 3)
       barrier(4);
     }
 
@@ -516,12 +536,13 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
           const bf16* const wrc[4] = {a.w_vocab + (size_t)n * H, a.w_vocab + (size_t)(n + 1) * H, a.w_vocab + (size_t)(n + 2) * H,
                                       a.w_vocab + (size_t)(n + 3) * H};
           load768<4>(wrc, lane, wV);
+          bV = __ldg(a.b_vocab + n + (lane & 3));
         }
         float acc[MT][4];
         fma768<MT, 4>(wV, sm.xs, lane, acc);
         if (lane < 4 * M) {
           const int m = lane >> 2, c = lane & 3;
-          logits[(size_t)m * a.vocab_pad + n + c] = pick<MT, 4>(acc, m, c) + a.b_vocab[n + c];
+          logits[(size_t)m * a.vocab_pad + n + c] = pick<MT, 4>(acc, m, c) + bV;
         }
       }
       barrier(5);
@@ -560,7 +581,7 @@ __device__ __forceinline__ void mega_body(const MegaArgs& a, const Smem& sm, int
       barrier(6);
       // ---------------------------------------------------------------- part 2 (CTA 0): merge, candidate walk, re-order
       if (b == 0 && tid < search_dev::SS_THREADS) search_walk_phase(a, M, t, parity, sh);
-      preload_qkv(a, 0, gw, lane, wA);  // the next step's first weights
+      preload_qkv(a, 0, gw, lane, wA, bA);  // the next step's first weights
       barrier(7);
     }
     // model.py:640 `if all(done): break`: the clip's search is finished, later steps would not change anything
@@ -638,7 +659,7 @@ cudaError_t decode_mega(const MegaArgs& a, cudaStream_t stream) {
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MEGA_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorNotSupported;
-  e = cudaMemsetAsync(a.barrier, 0, sizeof(unsigned int), stream);
+  e = cudaMemsetAsync(a.barrier, 0, 32 * sizeof(unsigned int), stream);  // [0]: barrier counter; [8, 32): attention tickets (attn_cnt)
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_sm);

@@ -194,7 +194,8 @@ struct MegaArgs {
   long long logits_step_stride;  // floats between the logits of consecutive steps (0: one buffer reused)
   bf16 *tq, *ta, *tb, *tf;  // scratch rows: [rows, 3H], [rows, H], [rows, H], [rows, ffn]
   float* partial;           // key-split partials of the attention
-  unsigned int* barrier;    // grid barrier counter (reset by the launcher)
+  unsigned int* barrier;    // grid barrier counter (reset by the launcher together with attn_cnt: 32 words from here)
+  int* attn_cnt;            // [row chunks * heads <= 24] finished key splits per (row chunk, head): the last one combines
   unsigned long long* trace;  // optional [32]: SM cycles of CTA 0 per phase (0-7: work, 16-23: barrier wait; 15: launches)
   float* cand_score;        // [rows * st.cand] every beam row's own top candidates (search step, part 1 -> part 2)
   int* cand_idx;

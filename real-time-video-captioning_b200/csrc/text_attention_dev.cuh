@@ -247,32 +247,31 @@ __device__ __forceinline__ void text_attention_body(const TextAttnArgs& a, float
 }
 
 // Combine of the key-split partials (m, l, o[HD]) of one (row, head) by one warp: lane -> dims 2 * lane, 2 * lane + 1.
-// splits <= 32.  Lane s fetches (m_s, l_s) once and the warp reads them by shuffle; the o pairs come in batches of 8 loads
-// issued together (one L2 round trip per batch instead of one per split).  Same operations in the same order as the plain loop.
+// splits <= MAX_SPLITS.  Every load is issued before the first use (one L2 round trip): lane s fetches (m_s, l_s) and the warp
+// reads them by shuffle, the o pairs of all splits go to registers.  Same operations in the same order as the plain loop.
+constexpr int MAX_SPLITS = 16;
 template <bool COHERENT>
 __device__ __forceinline__ uint32_t combine_partials(const float* p, int splits, int lane) {
   auto ld = [](const float* q) { return COHERENT ? __ldcg(q) : *q; };
   const float pm_l = lane < splits ? ld(p + lane * (HD + 2)) : -INFINITY;
   const float pl_l = lane < splits ? ld(p + lane * (HD + 2) + 1) : 0.f;
+  float2 po[MAX_SPLITS];
+#pragma unroll
+  for (int j = 0; j < MAX_SPLITS; ++j) {
+    const float2* q = reinterpret_cast<const float2*>(p + j * (HD + 2) + 2) + lane;
+    po[j] = j < splits ? (COHERENT ? __ldcg(q) : *q) : make_float2(0.f, 0.f);
+  }
   float m = -INFINITY;
   for (int s = 0; s < splits; ++s) m = fmaxf(m, __shfl_sync(0xffffffffu, pm_l, s));
   float l = 0.f, o0 = 0.f, o1 = 0.f;
-  for (int s0 = 0; s0 < splits; s0 += 8) {
-    float2 po[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2* q = reinterpret_cast<const float2*>(p + (s0 + j) * (HD + 2) + 2) + lane;
-      po[j] = s0 + j < splits ? (COHERENT ? __ldcg(q) : *q) : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (s0 + j < splits) {  // warp-uniform
-        const float pm = __shfl_sync(0xffffffffu, pm_l, s0 + j);
-        const float c = (pm == -INFINITY) ? 0.f : exp2f(pm - m);
-        l += __shfl_sync(0xffffffffu, pl_l, s0 + j) * c;
-        o0 += po[j].x * c;
-        o1 += po[j].y * c;
-      }
+  for (int j = 0; j < MAX_SPLITS; ++j) {
+    if (j < splits) {  // warp-uniform
+      const float pm = __shfl_sync(0xffffffffu, pm_l, j);
+      const float c = (pm == -INFINITY) ? 0.f : exp2f(pm - m);
+      l += __shfl_sync(0xffffffffu, pl_l, j) * c;
+      o0 += po[j].x * c;
+      o1 += po[j].y * c;
     }
   }
   const float inv = 1.f / l;
