@@ -299,6 +299,13 @@ int gitb200_op_attention_groups(const void* qkv_dev, void* out_dev, int n_groups
 /* the same operator on the warp-level mma.sync path (the kernel the tcgen05 one replaced; kept as a cross-check) */
 int gitb200_op_attention_groups_mma(const void* qkv_dev, void* out_dev, int n_groups, int group_len, int heads,
                                     float scale, void* stream);
+/* Decode-step / text-row attention (the attention of model.py:1056-1075's text rows over the clip's visual keys and
+ * their own text history): q bf16 [n_clips*rows_per_clip, heads*64]; vis_kv bf16 [n_clips*n_vis, 2*heads*64] (K | V);
+ * txt_kv bf16 [n_text][n_clips*rows_per_clip][2*heads*64]; anc int32 [rows, n_text] (slot of the row's ancestor at each text
+ * position, NULL = the row itself); every row sees all n_vis visual keys of its clip and n_text text keys.  splits >= 1 key
+ * splits (partials combined by a second kernel).  out bf16 [rows, heads*64]. */
+int gitb200_op_text_attention(const void* q_dev, const void* vis_kv_dev, const void* txt_kv_dev, const int32_t* anc_dev, int n_clips,
+                              int rows_per_clip, int heads, int n_vis, int n_text, int splits, float scale, void* out_dev, void* stream);
 /* Search on a pre-computed score sequence: logits_dev fp32 [max_steps-1, n_clips*beam, ld]. */
 int gitb200_op_search(const float* logits_dev, int ld, int vocab, int n_clips, int sos, int eos,
                       const gitb200_search_params* sp, int32_t* tokens_dev, float* logprobs_dev, void* stream);

@@ -1866,6 +1866,35 @@ int gitb200_op_attention_groups_mma(const void* qkv, void* out, int n_groups, in
   return GITB200_OK;
 }
 
+int gitb200_op_text_attention(const void* q, const void* vis_kv, const void* txt_kv, const int32_t* anc, int n_clips, int rows_per_clip,
+                              int heads, int n_vis, int n_text, int splits, float scale, void* out, void* stream) {
+  if (!q || !vis_kv || !out || n_clips < 1 || rows_per_clip < 1 || heads < 1 || n_vis < 0 || n_text < 0 || (n_text > 0 && !txt_kv) ||
+      splits < 1 || splits > 16)
+    return fail(nullptr, GITB200_ERR_INVALID, "bad op_text_attention argument");
+  TextAttnArgs a;
+  const int width = heads * 64, rows = n_clips * rows_per_clip;
+  a.q = (const bf16*)q; a.ldq = width;
+  a.n_clips = n_clips; a.rows_per_clip = rows_per_clip; a.heads = heads;
+  a.vis_kv = (const bf16*)vis_kv; a.ld_vis = 2 * width; a.k_off = 0; a.v_off = width; a.Nv = n_vis;
+  a.txt_kv = (const bf16*)txt_kv; a.txt_slots = rows;
+  a.anc = anc; a.anc_ld = n_text;
+  a.n_text_const = n_text; a.max_text = n_text;
+  a.scale = scale;
+  a.out = (bf16*)out; a.ldo = width;
+  a.splits = splits;
+  float* partial = nullptr;
+  if (splits > 1 && cudaMalloc(&partial, text_attention_workspace_floats(rows, heads, splits) * sizeof(float)) != cudaSuccess)
+    return fail(nullptr, GITB200_ERR_CUDA, "op_text_attention: workspace allocation failed");
+  a.partial = partial;
+  cudaError_t e = text_attention(a, (cudaStream_t)stream);
+  if (partial) {
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(partial);
+  }
+  if (e != cudaSuccess) return fail(nullptr, GITB200_ERR_CUDA, "text_attention: %s", cudaGetErrorString(e));
+  return GITB200_OK;
+}
+
 int gitb200_preprocess(const uint8_t* frames, int n_frames, int height, int width, int size, float* out, void* stream) {
   if (!frames || !out) return fail(nullptr, GITB200_ERR_INVALID, "bad preprocess argument");
   cudaError_t e = preprocess_frames_u8(frames, n_frames, height, width, size, out, (cudaStream_t)stream);

@@ -14,6 +14,8 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
+
 #include "text_attention_dev.cuh"
 
 namespace {
@@ -184,12 +186,12 @@ attention_groups_kernel(const bf16* __restrict__ qkv, int ld_qkv, bf16* __restri
 using text_attn_dev::TA_THREADS;
 using text_attn_dev::TA_GROUPS;
 
-template <int NB>
-__global__ void __launch_bounds__(TA_THREADS) text_attention_kernel(TextAttnArgs a, float scale_log2, int kcap) {
+template <int NB, int UT = 2>
+__global__ void __launch_bounds__(TA_THREADS, NB == 1 ? 8 : 6) text_attention_kernel(TextAttnArgs a, float scale_log2, int kcap) {
   extern __shared__ float sm[];
   const int chunks = (a.rows_per_clip + NB - 1) / NB;
-  text_attn_dev::text_attention_body<NB, false>(a, scale_log2, kcap, sm, blockIdx.y / chunks, blockIdx.y % chunks, blockIdx.x, blockIdx.z,
-                                                threadIdx.x, [] { __syncthreads(); });
+  text_attn_dev::text_attention_body<NB, false, UT, 5>(a, scale_log2, kcap, sm, blockIdx.y / chunks, blockIdx.y % chunks, blockIdx.x,
+                                                       blockIdx.z, threadIdx.x, [] { __syncthreads(); });
 }
 
 // combine split partials: one warp per (row, head)
@@ -229,7 +231,7 @@ cudaError_t text_attention(const TextAttnArgs& a, cudaStream_t stream) {
   const int chunks = (a.rows_per_clip + nb - 1) / nb;
   const int per = (a.Nv + a.splits - 1) / a.splits;
   const int kcap = ((per + a.max_text + 3) / 4) * 4;
-  const size_t smem = ((size_t)nb * kcap + (size_t)TA_GROUPS * nb * HD) * sizeof(float);
+  const size_t smem = (size_t)text_attn_dev::ta_smem_floats(nb, kcap) * sizeof(float);
   if (smem > 200 * 1024 || (long)a.n_clips * chunks > 65535) return cudaErrorInvalidValue;  // grid.y limit
   // heads are the FASTEST grid dimension: the CTAs of one clip's heads are resident together and jointly read whole
   // 1.5 KB K (then V) runs of every cache row instead of one 128-byte piece of rows 4.6 KB apart
@@ -240,8 +242,12 @@ cudaError_t text_attention(const TextAttnArgs& a, cudaStream_t stream) {
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) kernel<<<grid, TA_THREADS, smem, stream>>>(a, sl2, kcap);
   };
-  if (nb == 4) launch(text_attention_kernel<4>);
-  else if (nb == 2) launch(text_attention_kernel<2>);
+  // throughput batches: 2 tiles per warp and step; a few clips (key splits, the persistent decode kernel's twin): TA_UT_LATENCY
+  const int ut = a.n_clips * chunks * a.heads >= 2 * 148 ? 2 : text_attn_dev::TA_UT_LATENCY;
+  if (nb == 4 && ut == 2) launch(text_attention_kernel<4, 2>);
+  else if (nb == 4) launch(text_attention_kernel<4, text_attn_dev::TA_UT_LATENCY>);
+  else if (nb == 2 && ut == 2) launch(text_attention_kernel<2, 2>);
+  else if (nb == 2) launch(text_attention_kernel<2, text_attn_dev::TA_UT_LATENCY>);
   else launch(text_attention_kernel<1>);
   if (e != cudaSuccess) return e;
   note_launch();

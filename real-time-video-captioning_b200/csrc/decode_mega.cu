@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 
 size_t mega_smem_bytes(const MegaArgs& a, int* attn_floats) {
   const int nb = a.rows > 2 ? 4 : (a.rows == 2 ? 2 : 1);  // = NB of mega_body<MT> (3 rows share one 4-row virtual CTA: per-row arithmetic does not depend on it)
-  *attn_floats = nb * a.kcap + text_attn_dev::TA_GROUPS * nb * text_attn_dev::HD;
+  *attn_floats = text_attn_dev::ta_smem_floats(nb, a.kcap);
   const size_t layers = (size_t)(3 * 4 * HV + 4 * (a.ffn / 8)) * sizeof(uint4) + (size_t)(2 * 8 * 4 * 3 + VCTAS * *attn_floats) * sizeof(float);
   const size_t search = (size_t)((a.st.V + 3) / 4) * sizeof(float4);  // one staged logits row
   return layers > search ? layers : search;

@@ -406,6 +406,24 @@ def op_attention_groups(qkv: torch.Tensor, n_groups: int, group_len: int, heads:
     return out
 
 
+def op_text_attention(q: torch.Tensor, vis_kv: torch.Tensor, txt_kv, anc, n_clips: int, rows_per_clip: int, heads: int, scale: float,
+                      splits: int = 1):
+    """q bf16 [rows, H]; vis_kv bf16 [n_clips, n_vis, 2H]; txt_kv bf16 [n_text, rows, 2H] or None; anc int32 [rows, n_text] or None."""
+    lib = _lib.load()
+    q, vis_kv = q.contiguous(), vis_kv.contiguous()
+    n_text = 0 if txt_kv is None else txt_kv.shape[0]
+    if txt_kv is not None:
+        txt_kv = txt_kv.contiguous()
+    if anc is not None:
+        anc = anc.contiguous()
+    out = torch.empty(q.shape[0], heads * 64, dtype=torch.bfloat16, device=q.device)
+    s = ctypes.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+    check(lib.gitb200_op_text_attention(_ptr(q), _ptr(vis_kv), _ptr(txt_kv) if txt_kv is not None else None,
+                                        _ptr(anc) if anc is not None else None, n_clips, rows_per_clip, heads, vis_kv.shape[1], n_text,
+                                        splits, scale, _ptr(out), s), None, "gitb200_op_text_attention")
+    return out
+
+
 def op_search(logits: torch.Tensor, vocab: int, n_clips: int, sos: int, eos: int, sp: SearchConfig):
     """logits fp32 [max_steps-1, n_clips*beam, ld] (device) -> tokens [n_clips, keep, max_steps], logprobs."""
     lib = _lib.load()

@@ -141,4 +141,6 @@ def test_persistent_decode_under_cuda_graph_replay_and_streaming(g):
         res.append((tok.cpu(), lp.cpu()))
     eng.set_persistent_decode(True)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-    assert torch.equal(res[0][0], t_ref) and torch.allclose(res[0][1], l_ref, atol=1e-4)
+    # the window's frames were encoded one by one (other GEMM tiles than the 2-frame batch): same tokens, log-probabilities within
+    # the batch-invariance tolerance of test_full_size_properties_bench_geometry
+    assert torch.equal(res[0][0], t_ref) and torch.allclose(res[0][1], l_ref, rtol=2e-2, atol=5e-3)

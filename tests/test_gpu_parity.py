@@ -178,6 +178,54 @@ def test_op_attention_groups(g, n_groups, group_len, heads, legacy):
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max()
 
 
+def _text_attention_reference(q, vis, txt, anc, n_clips, rpc, heads, scale):
+    """Plain fp32 torch: every row attends to its clip's visual keys and to the text keys of its ancestors' slots."""
+    rows, W = q.shape
+    n_text = 0 if txt is None else txt.shape[0]
+    out = torch.empty(rows, W, dtype=torch.float32, device=q.device)
+    for r in range(rows):
+        c = r // rpc
+        k = [vis[c, :, :W].float()]
+        v = [vis[c, :, W:].float()]
+        for s_ in range(n_text):
+            slot = r if (anc is None or s_ == n_text - 1) else int(anc[r, s_])
+            k.append(txt[s_, slot, :W].float()[None])
+            v.append(txt[s_, slot, W:].float()[None])
+        k, v = torch.cat(k), torch.cat(v)
+        qh = q[r].float().view(heads, 1, 64)
+        kh, vh = k.view(-1, heads, 64).transpose(0, 1), v.view(-1, heads, 64).transpose(0, 1)
+        p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+        out[r] = (p @ vh).reshape(W)
+    return out
+
+
+@pytest.mark.parametrize("n_clips,rpc,heads,n_vis,n_text,splits,use_anc", [
+    (3, 1, 12, 1182, 7, 1, False), (3, 4, 12, 1182, 7, 1, True), (2, 4, 12, 1182, 19, 16, True), (2, 2, 12, 394, 3, 6, True),
+    (2, 3, 12, 197, 5, 3, True), (1, 8, 12, 197, 4, 1, True), (2, 4, 16, 1542, 9, 1, True), (1, 4, 16, 6168, 14, 1, True),
+    (2, 4, 12, 33, 1, 1, False), (2, 6, 12, 130, 0, 1, False), (1, 4, 12, 1182, 12, 5, True), (5, 4, 12, 16, 2, 2, True)])
+def test_op_text_attention(g, n_clips, rpc, heads, n_vis, n_text, splits, use_anc):
+    """Decode-step attention (scalar body for one row per clip, mma.sync body for several) vs fp32 torch: tails of every tile
+    size, key splits, ancestor slots, rows_per_clip that is not a multiple of the row chunk."""
+    from importlib import import_module
+    eng = import_module("real-time-video-captioning_b200.engine")
+    gen = torch.Generator(device="cuda").manual_seed(n_vis + rpc)
+    W, rows = heads * 64, n_clips * rpc
+    q = (torch.randn(rows, W, device="cuda", generator=gen) * 1.5).bfloat16()
+    vis = torch.randn(n_clips, n_vis, 2 * W, device="cuda", generator=gen).bfloat16()
+    txt = torch.randn(n_text, rows, 2 * W, device="cuda", generator=gen).bfloat16() if n_text else None
+    anc = None
+    if use_anc and n_text:
+        base = torch.arange(rows, device="cuda").div(rpc, rounding_mode="floor") * rpc
+        anc = (base[:, None] + torch.randint(0, rpc, (rows, n_text), device="cuda", generator=gen)).int()
+    out = eng.op_text_attention(q, vis, txt, anc, n_clips, rpc, heads, 0.125, splits)
+    ref = _text_attention_reference(q, vis, txt, anc, n_clips, rpc, heads, 0.125)
+    err = (out.float() - ref).abs()
+    record("op_text_attention", rpc=rpc, n_vis=n_vis, splits=splits, max_err=err.max().item())
+    assert (err <= 0.01 + 0.008 * ref.abs()).all(), err.max()
+    again = eng.op_text_attention(q, vis, txt, anc, n_clips, rpc, heads, 0.125, splits)
+    assert torch.equal(out, again)
+
+
 @pytest.mark.parametrize("group_len,heads", [(197, 12), (1182, 12), (257, 16), (70, 12)])
 def test_op_attention_deterministic_and_batch_invariant(g, group_len, heads):
     """The kernel must be bit-reproducible run to run and a group's result must not depend on its position in the batch

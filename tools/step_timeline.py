@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_timeline"))
     ap.add_argument("--sweep-rows", type=int, default=-1)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--beam", type=int, default=1)
+    ap.add_argument("--max-steps", type=int, default=15)
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -47,11 +49,11 @@ def main():
     dev = torch.device("cuda", 0)
     eng, model = bench.build_engine(g, gm, torch, {"num_image_with_embedding": 6}, 0)
     del model
-    sp = g.SearchConfig(beam_size=1, max_steps=15)
+    sp = g.SearchConfig(beam_size=args.beam, max_steps=args.max_steps)
     B = args.batch
     if args.sweep_rows >= 0:
         eng.set_sweep_rows(args.sweep_rows)
-    eng.reserve(B, 6, 1, 15)
+    eng.reserve(B, 6, args.beam, args.max_steps)
     if not args.graph:
         eng.set_graph_segments(False)  # the eager timeline: one launch per kernel
     if args.graph:
@@ -59,7 +61,7 @@ def main():
         eng.set_early_exit(0)
         torch.cuda.set_stream(torch.cuda.Stream(dev))
     frames = torch.randn(B, 6, 3, 224, 224, device=dev, generator=torch.Generator(device=dev).manual_seed(100))
-    tok = torch.empty(B, 1, 15, dtype=torch.int32, device=dev)
+    tok = torch.empty(B, 1, args.max_steps, dtype=torch.int32, device=dev)
     lp = torch.empty(B, 1, dtype=torch.float32, device=dev)
     import ctypes
     c = sp.to_c()
@@ -109,8 +111,8 @@ def main():
             prev_end, prev_name = max(prev_end or 0, s + d), n
     idle = wall - busy
     with open(args.out + ".md", "w") as fh:
-        fh.write(f"# Timeline of one {B}-clip step (GIT-base, 6 frames, greedy max 15){' -- CUDA graph replay' if args.graph else ''}\n\n")
-        fh.write(f"`python tools/step_timeline.py --batch {B}{' --graph' if args.graph else ''}` (torch.profiler CUDA activity records = CUPTI kernel timestamps)\n\n")
+        fh.write(f"# Timeline of one {B}-clip step (GIT-base, 6 frames, beam {args.beam} max {args.max_steps}){' -- CUDA graph replay' if args.graph else ''}\n\n")
+        fh.write(f"`python tools/step_timeline.py --batch {B} --beam {args.beam} --max-steps {args.max_steps}{' --graph' if args.graph else ''}` (torch.profiler CUDA activity records = CUPTI kernel timestamps)\n\n")
         fh.write(f"* un-profiled step (CUDA events, mean of 3): **{plain_ms:.2f} ms**\n")
         fh.write(f"* profiled step, first kernel start -> last kernel end: {wall:.2f} ms; {len(ks)} kernel launches\n")
         fh.write(f"* sum of kernel durations: **{busy:.2f} ms = {100 * busy / wall:.1f} %** of the profiled step; in no kernel: {idle:.2f} ms ({100 * idle / wall:.1f} %)\n\n")
