@@ -317,9 +317,10 @@ __device__ __forceinline__ void text_attention_body_mma(const TextAttnArgs& a, f
   // UT: 16-key tiles per warp and block-wide step (4 UT 16-byte loads in flight per thread)
   constexpr int KPB = 4 * UT * 16;       // keys per block-wide step (4 warps)
 
-  // Not kept: software-pipelining the two streaming loops in registers (loads of step i + 1 issued before step i is computed,
-  // first V step before the softmax pass): 128 registers, 4 CTAs per SM, 193-224 us against 178 us for this form at 80 registers
-  // and 6 CTAs per SM (256 clips x 4 beams); 8 CTAs per SM at 64 registers: 187 us (profiles/r02_text_attention_mma.md).
+  // Not kept: the two streaming loops on two register buffers (loop unrolled by two, the loads of step i + 1 issued before step i
+  // is computed, the first V step before the softmax pass): 128 registers / 4 CTAs per SM 212 us, one tile per step at 80 registers
+  // 216 us, against 178-182 us for this form at 80 registers / 6 CTAs per SM (256 clips x 4 beams); this form at 64 registers /
+  // 8 CTAs per SM: 187 us (profiles/r02_text_attention_mma.md).
   const bf16* vp = a.vis_kv + (size_t)clip * a.Nv * a.ld_vis + a.v_off + h * HD + g * 8;
   auto load_v = [&](uint4 (&vv)[UT][4], int base) {
 #pragma unroll
@@ -355,9 +356,7 @@ __device__ __forceinline__ void text_attention_body_mma(const TextAttnArgs& a, f
 #pragma unroll
       for (int i = 0; i < 8; ++i) qb[i] = 0u;
     }
-    for (int base = base0; base < k_end; base += KPB) {
-      uint4 kv[UT][4];
-      load_k(kv, base);
+    auto scores = [&](const uint4 (&kv)[UT][4], int base) {
 #pragma unroll
       for (int u = 0; u < UT; ++u) {
         const uint32_t wa[8] = {kv[u][0].x, kv[u][0].y, kv[u][0].z, kv[u][0].w, kv[u][1].x, kv[u][1].y, kv[u][1].z, kv[u][1].w};
@@ -379,6 +378,11 @@ __device__ __forceinline__ void text_attention_body_mma(const TextAttnArgs& a, f
           if (kb < k_end) sc[(2 * t + 1) * kcap + (kb - k_begin)] = s4[3] * scale_log2;
         }
       }
+    };
+    for (int base = base0; base < k_end; base += KPB) {
+      uint4 kv[UT][4];
+      load_k(kv, base);
+      scores(kv, base);
     }
   }
   // ---- phase 1b: text-key scores
@@ -477,9 +481,7 @@ __device__ __forceinline__ void text_attention_body_mma(const TextAttnArgs& a, f
   {
     const float* pr = sc + min(g, NB - 1) * kcap - k_begin;
     const bool live = g < n_loc;
-    for (int base = base0; base < k_end; base += KPB) {
-      uint4 vv[UT][4];
-      load_v(vv, base);
+    auto values = [&](const uint4 (&vv)[UT][4], int base) {
 #pragma unroll
       for (int u = 0; u < UT; ++u) {
         const int k0 = base + u * 16 + 2 * t;
@@ -504,6 +506,11 @@ __device__ __forceinline__ void text_attention_body_mma(const TextAttnArgs& a, f
           ptx::mma_bf16_16816(o[j], af, pl0, pl1);
         }
       }
+    };
+    for (int base = base0; base < k_end; base += KPB) {
+      uint4 vv[UT][4];
+      load_v(vv, base);
+      values(vv, base);
     }
   }
   // this warp's visual partial -> red[warp][beam][dim], on top of the text share
