@@ -794,10 +794,11 @@ int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unuse
   if (nb < 1 || nb > 8 || sp.per_node_beam_size < 1 || nb * sp.per_node_beam_size > 16 || nk < 1 || nk > 15 || ml < 2)
     return fail(c, GITB200_ERR_INVALID, "unsupported search parameters (beam %d, per-node %d, keep %d, max_steps %d)", nb,
                 sp.per_node_beam_size, nk, ml);
-  const size_t n_int = (size_t)rows * ml * 4 + (size_t)n_clips * 2 + 1 + rows + (size_t)n_clips * (nk + 1) * (1 + ml);
+  const int cand = nb * sp.per_node_beam_size;
+  const size_t n_int = (size_t)rows * ml * 4 + (size_t)n_clips * 2 + 1 + rows + (size_t)n_clips * (nk + 1) * (1 + ml) + (size_t)rows * cand;
   ENSURE(c, c->ibuf, n_int);
   ENSURE(c, c->dbuf, (size_t)n_clips * (nk + 2));
-  ENSURE(c, c->fbuf, (size_t)rows);
+  ENSURE(c, c->fbuf, (size_t)rows * (1 + cand));
   int* ip = c->ibuf.p;
   st->n_clips = n_clips; st->nb = nb; st->cand = nb * sp.per_node_beam_size; st->V = V; st->ldl = ldl; st->max_len = ml;
   st->eos = eos; st->n_keep = nk; st->length_penalty = sp.length_penalty; st->reorder_cache = sp.reorder_cache;
@@ -810,7 +811,9 @@ int make_search_state(gitb200_ctx* c, int n_clips, int V, int ldl, int sos_unuse
   st->done_count = ip; ip += 1;
   st->cur_tok = ip; ip += rows;
   st->hyp_len = ip; ip += (size_t)n_clips * (nk + 1);
-  st->hyp_tok = ip;
+  st->hyp_tok = ip; ip += (size_t)n_clips * (nk + 1) * ml;
+  st->row_cand_idx = ip;
+  st->row_cand_score = c->fbuf.p + rows;
   st->hyp_score = c->dbuf.p;
   st->worst = c->dbuf.p + (size_t)n_clips * (nk + 1);
   st->beam_scores = c->fbuf.p;

@@ -165,6 +165,10 @@ struct SearchState {
   int* hyp_count;     // [n_clips]
   double* worst;      // [n_clips]
   int reorder_cache;  // 0 = reference behaviour (cache rows never re-indexed), 1 = re-index by parent
+  // beam search: every row's own top `cand` candidates [n_rows, cand] (search_step: one CTA per ROW selects, one per clip merges
+  // and walks); null = one CTA per clip does both
+  float* row_cand_score = nullptr;
+  int* row_cand_idx = nullptr;
 };
 // One search step: log-softmax over logits [n_rows, ldl] (fp32), + beam score, top-(cand) per clip,
 // then the reference's candidate walk; cur_len = current caption length before this step.

@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 def short(name):
     for k in ("gemm2_kernel", "gemm_tcgen05_kernel", "gemv_skinny", "attention_tc_kernel", "text_attention_kernel", "text_attention_combine",
-              "layernorm_kernel", "search_step_kernel", "im2col_kernel", "store_text_kv_kernel", "embed_text_kernel", "cls_rows_kernel",
+              "layernorm_kernel", "search_step_kernel", "search_rows_kernel", "search_merge_walk_kernel", "im2col_kernel", "store_text_kv_kernel", "embed_text_kernel", "cls_rows_kernel",
               "search_finalize_kernel", "search_init_kernel", "cast_", "preprocess_kernel"):
         if k in name:
             if k == "attention_tc_kernel":
