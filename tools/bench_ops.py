@@ -42,7 +42,36 @@ def layernorm(rows=605184):
         print(f"layernorm rows={rows} cols={cols}: {ms:.3f} ms  {2 * rows * cols * 2 / ms / 1e9:.2f} TB/s")
 
 
+def decode_gemms():
+    """Decode-step GEMM shapes (rows = clips x beams) per tile choice: kernel durations from CUPTI records (the launches are a
+    few microseconds: host launch cost would dominate CUDA-event timing of eager calls)."""
+    from torch.profiler import ProfilerActivity, profile
+    for M in (512, 1024, 2048):
+        for N, K in ((2304, 768), (768, 768), (3072, 768), (768, 3072)):
+            a = torch.randn(M, K, device="cuda").bfloat16()
+            w = torch.randn(N, K, device="cuda").bfloat16()
+            bias = torch.zeros(N, device="cuda")
+            res = torch.randn(M, N, device="cuda").bfloat16()
+            line = f"M={M:5d} N={N:5d} K={K:5d}:"
+            for tile in (0, 128, 256):
+                for _ in range(3):
+                    eng.op_gemm(a, w, bias, res, 0, False, tile)
+                torch.cuda.synchronize()
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for _ in range(10):
+                        eng.op_gemm(a, w, bias, res, 0, False, tile)
+                    torch.cuda.synchronize()
+                ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "gemm" in e.name]
+                us = sum(e.time_range.end - e.time_range.start for e in ev) / max(1, len(ev))
+                name = ev[0].name.split("(")[0][-28:] if ev else "?"
+                line += f"  tile {tile:3d}: {us:6.1f} us [{name}]"
+            print(line, flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "decode_gemms":
+        decode_gemms()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "ln":
         layernorm(int(sys.argv[1]) * 6 * 197)
     else:
