@@ -168,7 +168,7 @@ def run_search(ref, name, clips, nb, pn, keep, max_steps, vocab, boost, lp):
     decoded, logprobs, saved = dec.search(start, step, num_keep_best=keep)
     return dict(logits=logits.numpy(), decoded=decoded.reshape(clips, keep, max_steps).numpy(), logprobs=logprobs.numpy(),
                 steps_run=np.int64(len(calls)), last_input_ids=calls[-1].numpy(),
-                spec=np.array([clips, nb, pn, keep, max_steps, vocab, eos, sos], dtype=np.int64), length_penalty=np.float32(lp))
+                spec=np.array([clips, nb, pn, keep, max_steps, vocab, eos, sos], dtype=np.int64), length_penalty=np.float64(lp))
 
 
 # ------------------------------------------------------------------ GIT glue (a4 / a6 / a7)
