@@ -5,11 +5,16 @@ Plain PyTorch fp32 restatement of the arithmetic the reference reaches through
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this module; the product
 package never does (it fails loudly when the CUDA library is missing).
 
-PARITY STATUS: *unpinned by the reference*.  The reference's layer arithmetic lives in the
-un-vendored, un-pinned dependency ``generativeimage2text`` (microsoft/GenerativeImage2Text,
-``/root/reference/requirements.txt:19``) and the reference's only test
-(``/root/reference/tests/test_metrics.py:7-22``) pins no number on this path, so there are no golden
-vectors to inherit.  What anchors this restatement instead:
+PARITY STATUS: two halves.
+(1) The GLUE the reference wrote itself -- ``forward_one_custom`` (frame features + temporal embeddings in zip order,
+truncation, concat, hidden-state stacking) and ``infer`` -- is PINNED TO THE REFERENCE'S OWN CODE: oracle/make_reference_golden.py
+imports /root/reference/src/models/model.py unmodified and runs those methods around THIS file's layers;
+tests/test_reference_golden.py replays the frozen outputs (tests/golden/ref_git_glue.npz) through ``forward_one_custom`` /
+``search_oracle.infer`` here.
+(2) The LAYER ARITHMETIC is *unpinned by the reference*: it lives in the un-vendored, un-pinned dependency
+``generativeimage2text`` (microsoft/GenerativeImage2Text, ``/root/reference/requirements.txt:19``), absent from this image, and
+the reference's only test (``/root/reference/tests/test_metrics.py:7-22``) pins no number on this path, so there are no golden
+vectors to inherit.  What anchors the layers instead:
 
   * the in-tree call sites and hyper-parameters: ``model.py:681-718`` (get_git_model),
     ``:371-424`` (forward_one_custom), ``:426-462`` (infer), ``:479-678`` (search, restated in

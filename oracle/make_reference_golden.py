@@ -10,6 +10,7 @@ import stubs for the missing packages into sys.modules, imports /root/reference/
   * ``GenerativeImageTextModel.forward_one_custom`` (model.py:372-428: frame features + temporal embeddings, concat, a4/a6)
   * ``GenerativeImageTextModel.infer``              (model.py:430-463: start tokens, search call, result dict, a7)
   * ``StudentCandidateV1.forward_decoder / greedy_decode / beam_search`` (model.py:135-316, rank f3)
+  * ``DistillationTrainer.training_step``           (model.py:880-1004: KL + CE loss; gradients by its ``loss.backward()``)
   * ``PositionalEncoding`` (model.py:320-341), ``create_padding_mask`` / ``create_casual_mask`` (src/utils/masking.py)
 
 on seeded inputs, and freezes inputs + outputs as small fixtures.  `tests/test_reference_golden.py` replays them through the
@@ -256,6 +257,62 @@ def run_student(ref):
                 spec=np.array([d_model, n_head, d_ffn, layers, vocab], dtype=np.int64), **{"sd." + k: v for k, v in sd.items()})
 
 
+# ------------------------------------------------------------------ distillation step (model.py:880-1004, configs[4])
+def run_training_step(ref):
+    """``DistillationTrainer.training_step`` executed on a duck-typed trainer: the constructor wires Lightning, hooks into the
+    teacher's layers and a log file (out of scope); the step itself needs only the attributes set below.  Student = the
+    reference's StudentCandidateV1 (TinyViT replaced by fixed feature maps), teacher = given logits.  Returns the loss the
+    reference computed AND the gradients its ``loss.backward()`` leaves on the decoder-side parameters."""
+    torch.manual_seed(51)
+    d_model, n_head, d_ffn, layers, vocab, B, Fr, Lc = 64, 4, 96, 2, 101, 3, 6, 7
+    m = ref.StudentCandidateV1("unused", d_model, n_head, d_ffn, 0.0, layers, vocab, cls_token_id=vocab - 2, sep_token_id=vocab - 1)
+    m.train()  # Lightning trains in train mode; dropout is 0.0 here so the step is deterministic
+    g = torch.Generator().manual_seed(52)
+    fmaps = [torch.randn(B * Fr, c, 2, 2, generator=g) for c in (8, 16, 32, d_model)]
+    memory = torch.mean(fmaps[-1], dim=[2, 3]).view(B, Fr, -1)
+
+    class FeatureMaps(nn.Module):
+        def forward(self, x):
+            return fmaps
+
+    m.image_encoder = FeatureMaps()
+    y = torch.randint(1, vocab - 2, (B, Lc), generator=g)
+    y[:, 0] = vocab - 2
+    y[1, 5:] = 0
+    teacher_logits = torch.randn(B, Lc, vocab, generator=g) * 2.0
+
+    class Teacher:
+        def eval(self):
+            return self
+
+        def forward_output_logits(self, x, yy):
+            return [t[None] for t in teacher_logits], None, None
+
+    class Self:
+        pass
+
+    me = Self()
+    me.teacher, me.student = Teacher(), m
+    me.fmap_distill_loss = nn.MSELoss()
+    me.kl_div_loss = nn.KLDivLoss(reduction="batchmean")   # model.py:819
+    me.ce_loss = nn.CrossEntropyLoss(ignore_index=0)       # model.py:821
+    me.student_decoder_activations = {0: [torch.zeros(1, 1)]}
+    me.teacher_encoder_activations = {i: [torch.randn(3, B * Fr, 1024, generator=g)] for i in range(4)}
+    me.teacher_decoder_activations = {}
+    logged = {}
+    me.log = lambda name, value, **kw: logged.__setitem__(name, float(value))
+    batch = {"frames": torch.zeros(B, Fr, 3, 8, 8), "caption": y, "caption-id": None, "vid-id": None}
+    loss = ref.DistillationTrainer.training_step(me, batch, 0)
+    loss.backward()
+    grads = {k: p.grad.numpy() for k, p in m.named_parameters()
+             if p.grad is not None and k.startswith(("decoder.", "embed.", "linear."))}
+    sd = {k: v.detach().numpy() for k, v in m.state_dict().items() if k.startswith(("decoder.", "embed.", "linear."))}
+    return dict(memory=memory.numpy(), y=y.numpy(), teacher_logits=teacher_logits.numpy(), loss=np.float64(loss.item()),
+                kl=np.float64(logged["train_kl_loss"]), ce=np.float64(logged["ce_loss"]),
+                spec=np.array([d_model, n_head, d_ffn, layers, vocab], dtype=np.int64),
+                **{"sd." + k: v for k, v in sd.items()}, **{"grad." + k: v for k, v in grads.items()})
+
+
 def main():
     ref = import_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -270,7 +327,8 @@ def main():
             glue[f"{name}.{k}"] = v
     np.savez_compressed(os.path.join(OUT, "ref_git_glue.npz"), **glue)
     np.savez_compressed(os.path.join(OUT, "ref_student.npz"), **run_student(ref))
-    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_student.npz"):
+    np.savez_compressed(os.path.join(OUT, "ref_training_step.npz"), **run_training_step(ref))
+    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_student.npz", "ref_training_step.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

@@ -5,9 +5,14 @@ greedy-beam branch the reference uses (do_sample=False), the sampling branch (:5
 ``top_k_top_p_filtering`` (:537), and the upstream ``BeamHypotheses`` helper it constructs at model.py:503 (legacy HuggingFace beam hypotheses container; recalled -- SURVEY 3.3).
 Plus ``infer`` (model.py:426-462) and the teacher's caption / logit post-processing (model.py:762-793).
 
-PARITY STATUS: unpinned by the reference (no test in /root/reference pins search output).  Anchors:
-the in-tree loop itself (followed statement by statement below) and the hand-worked cases in
-tests/test_search_oracle.py.
+PARITY STATUS: ``search`` and ``infer`` are PINNED TO THE REFERENCE'S OWN CODE: oracle/make_reference_golden.py imports
+/root/reference/src/models/model.py unmodified (import stubs for the packages this image lacks) and runs its
+``GeneratorWithBeamSearchV2.search`` / ``GenerativeImageTextModel.infer`` on seeded inputs; tests/test_reference_golden.py
+replays the frozen outputs (tests/golden/ref_search.npz, ref_git_glue.npz) through this file: tokens, log-probabilities (bit
+for bit), the step at which the loop breaks and the re-ordered beam histories agree.  The reference holds no test of its own
+for search output.  NOT pinned that way: ``BeamHypotheses`` and ``top_k_top_p_filtering`` (upstream generativeimage2text code,
+absent here: the published legacy-HuggingFace algorithm, exercised by the hand-worked cases in tests/test_cpu_oracle_and_host.py;
+the reference's search ran ON TOP of these restatements when the fixtures were made).
 """
 from __future__ import annotations
 

@@ -3,7 +3,11 @@
 Restates the decoder half of ``StudentCandidateV1`` (/root/reference/src/models/model.py:50-187), SURVEY 8(f) rank 3:
 ``forward_decoder`` (:135-154) and ``greedy_decode`` (:156-187) on a given ``memory`` tensor.
 
-PARITY STATUS: **pinned by PyTorch itself.**  The reference builds this decoder from stock ``torch.nn`` modules
+PARITY STATUS: **pinned to the reference's own code and by PyTorch itself.**  oracle/make_reference_golden.py imports
+/root/reference/src/models/model.py unmodified and runs its ``StudentCandidateV1.forward_decoder / greedy_decode / beam_search``,
+``PositionalEncoding``, the masking helpers and ``DistillationTrainer.training_step`` (loss + ``loss.backward()`` gradients) on
+seeded inputs; tests/test_reference_golden.py replays the frozen outputs (tests/golden/ref_student.npz, ref_training_step.npz)
+through this file.  Besides, the reference builds this decoder from stock ``torch.nn`` modules
 (``nn.TransformerDecoderLayer(d_model, nhead, dim_feedforward, dropout, batch_first=True)`` stacked by
 ``nn.TransformerDecoder`` :73-76, ``nn.Embedding`` :78, ``nn.Linear`` :80) and this file instantiates exactly those
 modules with the same arguments -- the layer arithmetic below IS the reference's arithmetic, not a recollection of it.

@@ -132,17 +132,17 @@ def test_cuda_path_equals_the_reference_glue(name):
                                  layers=cfg.num_layers), 0)
     eng.load_state_dict(sd)
     S = mk.SUB
-    vf = eng.encode(frames[None].cuda()).cpu()
+    tokens = torch.from_numpy(want["tokens"])
+    logits, vf, hidden = eng.forward_logits(frames[None].cuda(), tokens.cuda())      # forward_one_custom, batched form
+    vf, logits, hidden = vf.cpu(), logits.cpu(), hidden.cpu()
     ref_vf = torch.from_numpy(want["visual_features"])
     assert list(vf.shape) == list(want["visual_features_shape"])          # 3 frames, 2 temporal embeddings -> 2 frames
     assert ((vf[:, ::S, ::S] - ref_vf).norm() / ref_vf.norm()).item() < 2e-2
-    tokens = torch.from_numpy(want["tokens"])
-    logits, hidden = eng.forward_logits(tokens.int().cuda(), return_hidden=True)
     ref_logits = torch.from_numpy(want["logits"])
-    err = (logits[..., : cfg.vocab_size].cpu()[..., ::S] - ref_logits).abs()
+    err = (logits[..., ::S] - ref_logits).abs()
     assert err.max().item() < 0.15 * ref_logits.std().item() and err.mean().item() < 0.03 * ref_logits.std().item()
     ref_h = torch.from_numpy(want["hidden_states"])
-    h = hidden.cpu().reshape(want["hidden_states_shape"].tolist())
+    h = hidden.reshape(want["hidden_states_shape"].tolist())              # [1, 3, Nv+L, H] -> the reference's [3, Nv+L, H]
     assert ((h[:, ::S, ::S] - ref_h).norm() / ref_h.norm()).item() < 3e-2
     sp = g.SearchConfig(beam_size=beam, max_steps=max_steps, length_penalty=cfg.length_penalty, per_node_beam_size=cfg.per_node_beam_size)
     tok, lp, _ = eng.caption(frames[None].cuda(), sp)
@@ -227,3 +227,50 @@ def test_cuda_student_decoder_equals_the_reference_student():
     else:  # up to the first near-tie the runs must agree
         first = int((~clear).float().argmax(dim=1).min().item())
         assert torch.equal(got[:, : first + 1], ref_greedy[:, : first + 1])
+
+
+# ------------------------------------------------------------------------------------------ distillation step (model.py:880-1004)
+def training_case():
+    z = load("ref_training_step.npz")
+    d_model, n_head, d_ffn, layers, vocab = (int(v) for v in z["spec"])
+    cfg = sto.StudentConfig(d_model=d_model, n_head=n_head, d_ffn=d_ffn, dropout=0.0, num_decoder_layers=layers, vocab_length=vocab,
+                            cls_token_id=vocab - 2, sep_token_id=vocab - 1)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad.")}
+    return z, cfg, sd, grads
+
+
+def test_oracle_distillation_step_equals_the_reference_training_step():
+    """KL(batchmean) * T^2 + CE(ignore_index=0) and the gradients of `loss.backward()`, as the reference's own
+    DistillationTrainer.training_step computed them, against the oracle's restatement (the checker of the CUDA training step)."""
+    z, cfg, sd, want = training_case()
+    m = sto.StudentDecoderOracle(cfg)
+    m.load_state_dict(sd, strict=False)
+    y, memory, teacher = torch.from_numpy(z["y"]), torch.from_numpy(z["memory"]), torch.from_numpy(z["teacher_logits"])
+    info, grads, _ = sto.distillation_step(m, y, memory, teacher, 1.0)
+    assert abs(info["loss"] - float(z["loss"])) < 1e-5 and abs(info["kl"] - float(z["kl"])) < 1e-5 and abs(info["ce"] - float(z["ce"])) < 1e-5
+    assert set(grads) == set(want)
+    for k, ref in want.items():
+        assert torch.allclose(grads[k], ref, atol=1e-6, rtol=1e-4), k
+
+
+@pytest.mark.gpu
+def test_cuda_distillation_step_equals_the_reference_training_step():
+    g = importlib.import_module("real-time-video-captioning_b200")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    z, cfg, sd, want = training_case()
+    s = g.StudentCandidateV1(None, cfg.d_model, cfg.n_head, cfg.d_ffn, 0.0, cfg.num_decoder_layers, cfg.vocab_length, cfg.cls_token_id,
+                             cfg.sep_token_id)
+    s.load_state_dict(sd)
+    s = s.to("cuda")
+    s.enable_training(lr=1e-4)
+    y, memory, teacher = torch.from_numpy(z["y"]), torch.from_numpy(z["memory"]), torch.from_numpy(z["teacher_logits"])
+    out = s.distillation_step(y, memory, teacher, temperature=1.0, apply=False)
+    kl, ce = out["kl"].item(), out["ce"].item()
+    assert abs(kl - float(z["kl"])) < 2e-2 * float(z["kl"]) and abs(ce - float(z["ce"])) < 2e-2 * float(z["ce"]), (kl, ce)
+    grads = {k: v.cpu() for k, v in s.gradients().items()}
+    assert set(grads) == set(want)
+    num = sum((grads[k].double() - want[k].double()).pow(2).sum().item() for k in want)
+    den = sum(want[k].double().pow(2).sum().item() for k in want)
+    assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
