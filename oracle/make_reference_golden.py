@@ -9,6 +9,7 @@ import stubs for the missing packages into sys.modules, imports /root/reference/
   * ``GeneratorWithBeamSearchV2.search``            (model.py:479-678: the whole caption search loop, a9)
   * ``GenerativeImageTextModel.forward_one_custom`` (model.py:372-428: frame features + temporal embeddings, concat, a4/a6)
   * ``GenerativeImageTextModel.infer``              (model.py:430-463: start tokens, search call, result dict, a7)
+  * ``GenerativeImageTextTeacher.forward / forward_output_logits`` (model.py:747-793: per-clip loop, caption, 'output', a11)
   * ``StudentCandidateV1.forward_decoder / greedy_decode / beam_search`` (model.py:135-316, rank f3)
   * ``DistillationTrainer.training_step``           (model.py:880-1004: KL + CE loss; gradients by its ``loss.backward()``)
   * ``PositionalEncoding`` (model.py:320-341), ``create_padding_mask`` / ``create_casual_mask`` (src/utils/masking.py)
@@ -102,6 +103,14 @@ class _CaptioningModel(nn.Module):
         if num_image_with_embedding:
             self.img_temperal_embedding = nn.ParameterList(
                 nn.Parameter(torch.zeros(1, 1, textual.visual_feature_size)) for _ in range(num_image_with_embedding))
+
+    def forward(self, batch):
+        # upstream CaptioningModel.forward in eval mode (not in /root/reference): features through the reference's own glue
+        # (forward_one_custom's first half, a dummy caption feeds its text-head call), then the reference's infer with the
+        # default search parameters
+        dummy = torch.full((1, 1), self.sos_index, dtype=torch.long)
+        _, visual_features, _ = self.forward_one_custom({"image": batch["image"], "caption_tokens": dummy})
+        return self.infer(batch, visual_features, None, search_param=None)
 
     def decoding_step(self, visual_features, visual_features_valid, bi_valid_mask_caption, partial_captions):
         # upstream code, not in /root/reference: the oracle's restatement (hidden-state history, visual features
@@ -226,6 +235,51 @@ def run_glue(ref, n_frames, n_embed):
                 spec=np.array([n_frames, n_embed, 2, 2, 6, 2], dtype=np.int64))
 
 
+# ------------------------------------------------------------------ teacher wrapper (a11, model.py:747-793)
+def detok(ids, skip_special_tokens=True, sos=101, eos=102):
+    """Stand-in for BertTokenizer.decode (bert-base-uncased is not in this image): one pseudo-word per non-special id."""
+    return " ".join(f"w{i}" for i in ids if not (skip_special_tokens and i in (0, sos, eos)))
+
+
+def run_teacher(ref):
+    n_frames = 2
+    cfg = go.GitConfig(num_image_with_embedding=n_frames, num_layers=2, tie_output=False)
+    sd = go.init_state_dict(cfg, seed=GLUE_SEEDS["weights"] + 1, temporal_std=0.02, perturb=True)
+    x = torch.randn(2, n_frames, 3, 224, 224, generator=torch.Generator().manual_seed(GLUE_SEEDS["frames"] + 1))
+
+    class Tok:
+        cls_token_id, sep_token_id = cfg.sos_index, cfg.eos_index
+        decode = staticmethod(detok)
+
+    dec = ref.GeneratorWithBeamSearchV2(cfg.eos_index, 7, 4, per_node_beam_size=cfg.per_node_beam_size, length_penalty=cfg.length_penalty)
+    m = ref.GenerativeImageTextModel(_OracleImageEncoder(sd, cfg), _OracleTextHead(sd, cfg), dec, Tok, {"num_image_with_embedding": n_frames})
+    with torch.no_grad():
+        for i, p in enumerate(m.img_temperal_embedding):
+            p.copy_(sd[f"img_temperal_embedding.{i}"])
+    m.eval()
+
+    class Self:
+        model, tokenizer = m, Tok
+
+    out = ref.GenerativeImageTextTeacher.forward(Self(), x)
+    y = torch.tensor([[cfg.sos_index, 2023, 2003, 1037], [cfg.sos_index, 1996, 4937, 102]], dtype=torch.long)
+    with torch.no_grad():
+        logits, vfs, hiddens = ref.GenerativeImageTextTeacher.forward_output_logits(Self(), x, y)
+    d = dict(spec=np.array([n_frames, 2, 7, 4], dtype=np.int64), y=y.numpy(), n_clips=np.int64(len(out)))
+    for i, o in enumerate(out):
+        d[f"clip{i}.predictions"] = o["predictions"].numpy()
+        d[f"clip{i}.logprobs"] = o["logprobs"].numpy()
+        d[f"clip{i}.cap"] = np.array(o["cap"])
+        d[f"clip{i}.output"] = o["output"][..., ::SUB].numpy()
+        d[f"clip{i}.output_shape"] = np.array(o["output"].shape)
+        d[f"clip{i}.n_saved_steps"] = np.int64(len(o["logits_dict"]))
+        d[f"clip{i}.fol_logits"] = logits[i][..., ::SUB].numpy()
+        d[f"clip{i}.fol_visual_features"] = vfs[i][:, ::SUB, ::SUB].numpy()
+        d[f"clip{i}.fol_hidden_states"] = hiddens[i][:, ::SUB, ::SUB].numpy()
+    d["result_keys"] = np.array(sorted(out[0].keys()))
+    return d
+
+
 # ------------------------------------------------------------------ student (f3)
 def run_student(ref):
     torch.manual_seed(41)
@@ -326,9 +380,10 @@ def main():
         for k, v in run_glue(ref, n_frames, n_embed).items():
             glue[f"{name}.{k}"] = v
     np.savez_compressed(os.path.join(OUT, "ref_git_glue.npz"), **glue)
+    np.savez_compressed(os.path.join(OUT, "ref_teacher.npz"), **run_teacher(ref))
     np.savez_compressed(os.path.join(OUT, "ref_student.npz"), **run_student(ref))
     np.savez_compressed(os.path.join(OUT, "ref_training_step.npz"), **run_training_step(ref))
-    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_student.npz", "ref_training_step.npz"):
+    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_teacher.npz", "ref_student.npz", "ref_training_step.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

@@ -274,3 +274,33 @@ def test_cuda_distillation_step_equals_the_reference_training_step():
     num = sum((grads[k].double() - want[k].double()).pow(2).sum().item() for k in want)
     den = sum(want[k].double().pow(2).sum().item() for k in want)
     assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
+
+
+# ------------------------------------------------------------------------------------------ teacher wrapper (model.py:747-793)
+def test_oracle_teacher_wrapper_equals_the_reference_teacher():
+    """GenerativeImageTextTeacher.forward (per-clip loop, caption, n = min(words, saved steps), beam pick by the word's logit,
+    'output') and forward_output_logits, executed by the reference, against the oracle's restatement (teacher_postprocess is the
+    checker of the package's batched teacher in tests/test_gpu_baseline_geometry.py)."""
+    z = load("ref_teacher.npz")
+    n_frames, layers, max_steps, beam = (int(v) for v in z["spec"])
+    cfg = go.GitConfig(num_image_with_embedding=n_frames, num_layers=layers, tie_output=False)
+    sd = go.init_state_dict(cfg, seed=mk.GLUE_SEEDS["weights"] + 1, temporal_std=0.02, perturb=True)
+    x = torch.randn(2, n_frames, 3, 224, 224, generator=torch.Generator().manual_seed(mk.GLUE_SEEDS["frames"] + 1))
+    y = torch.from_numpy(z["y"])
+    S = mk.SUB
+    assert list(z["result_keys"]) == ["cap", "logits_dict", "logprobs", "output", "predictions", "visual_features"]
+    for i in range(int(z["n_clips"])):
+        with torch.no_grad():
+            vf = go.encode_clip(sd, cfg, x[i])
+            res = so.infer(sd, cfg, vf, beam_size=beam, max_steps=max_steps)
+            post = so.teacher_postprocess(res, mk.detok, num_beams=beam)
+            logits, vf2, hidden = go.forward_one_custom(sd, cfg, x[i], y[i:i + 1])
+        assert torch.equal(post["predictions"], torch.from_numpy(z[f"clip{i}.predictions"]))
+        assert torch.allclose(post["logprobs"], torch.from_numpy(z[f"clip{i}.logprobs"]), atol=1e-5)
+        assert post["cap"] == str(z[f"clip{i}.cap"]) and len(post["cap"]) > 0
+        assert len(res["logits_dict"]) == int(z[f"clip{i}.n_saved_steps"])
+        assert list(post["output"].shape) == list(z[f"clip{i}.output_shape"])
+        assert torch.allclose(post["output"][..., ::S], torch.from_numpy(z[f"clip{i}.output"]), atol=2e-4, rtol=1e-4)
+        assert torch.allclose(logits[..., ::S], torch.from_numpy(z[f"clip{i}.fol_logits"]), atol=2e-4, rtol=1e-4)
+        assert torch.allclose(vf2[:, ::S, ::S], torch.from_numpy(z[f"clip{i}.fol_visual_features"]), atol=1e-5, rtol=1e-5)
+        assert torch.allclose(hidden[:, ::S, ::S], torch.from_numpy(z[f"clip{i}.fol_hidden_states"]), atol=2e-4, rtol=1e-4)
