@@ -9,6 +9,7 @@ import stubs for the missing packages into sys.modules, imports /root/reference/
   * ``GeneratorWithBeamSearchV2.search``            (model.py:479-678: the whole caption search loop, a9)
   * ``GenerativeImageTextModel.forward_one_custom`` (model.py:372-428: frame features + temporal embeddings, concat, a4/a6)
   * ``GenerativeImageTextModel.infer``              (model.py:430-463: start tokens, search call, result dict, a7)
+  * ``get_git_model`` / ``GenerativeImageTextModel.__init__`` (model.py:681-718, :350-369: the hyper-parameters it passes, a1/a2)
   * ``GenerativeImageTextTeacher.forward / forward_output_logits`` (model.py:747-793: per-clip loop, caption, 'output', a11)
   * ``StudentCandidateV1.forward_decoder / greedy_decode / beam_search`` (model.py:135-316, rank f3)
   * ``DistillationTrainer.training_step``           (model.py:880-1004: KL + CE loss; gradients by its ``loss.backward()``)
@@ -235,6 +236,49 @@ def run_glue(ref, n_frames, n_embed):
                 spec=np.array([n_frames, n_embed, 2, 2, 6, 2], dtype=np.int64))
 
 
+# ------------------------------------------------------------------ get_git_model (a1 / a2, model.py:681-718, :350-369)
+def run_get_git_model(ref):
+    """The reference's own get_git_model with recording stand-ins for the two upstream constructors: which hyper-parameters the
+    REFERENCE passes (they size every kernel of the path), for the default and for the shipped GIT-large parameter dict."""
+    import json
+    rec = {}
+
+    class Enc(nn.Module):
+        pass
+
+    class Head(nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+            rec["text_decoder"] = dict(kw)
+            self.visual_feature_size = kw["visual_feature_size"]
+
+    def get_image_encoder(name, **kw):
+        rec["image_encoder"] = dict(name=name, **kw)
+        return Enc()
+
+    ref.get_image_encoder, ref.TransformerDecoderTextualHead = get_image_encoder, Head
+
+    class Tok:
+        cls_token_id, sep_token_id = 101, 102
+
+    out = {}
+    for label, param in (("default", {"num_image_with_embedding": 6}),
+                         ("large", {"image_encoder_type": "CLIPViT_L_14", "test_crop_size": 224, "visual_feature_size": 1024,
+                                    "num_image_with_embedding": 6})):
+        rec.clear()
+        m = ref.get_git_model(Tok, param)
+        d = m.decoder
+        out[label] = dict(image_encoder=rec["image_encoder"], text_decoder=rec["text_decoder"],
+                          decoder=dict(eos_index=d._eos_index, max_steps=d.max_steps, beam_size=d.beam_size, length_penalty=d.length_penalty,
+                                       per_node_beam_size=d.per_node_beam_size, repetition_penalty=d.repetition_penalty,
+                                       temperature=d.temperature),
+                          model=dict(sos_index=m.sos_index, eos_index=m.eos_index, use_history_for_infer=m.use_history_for_infer,
+                                     num_image_with_embedding=m.num_image_with_embedding,
+                                     n_temporal_embeddings=len(m.img_temperal_embedding),
+                                     temporal_embedding_shape=list(m.img_temperal_embedding[0].shape)))
+    return dict(json=np.array(json.dumps(out, sort_keys=True)))
+
+
 # ------------------------------------------------------------------ teacher wrapper (a11, model.py:747-793)
 def detok(ids, skip_special_tokens=True, sos=101, eos=102):
     """Stand-in for BertTokenizer.decode (bert-base-uncased is not in this image): one pseudo-word per non-special id."""
@@ -381,9 +425,10 @@ def main():
             glue[f"{name}.{k}"] = v
     np.savez_compressed(os.path.join(OUT, "ref_git_glue.npz"), **glue)
     np.savez_compressed(os.path.join(OUT, "ref_teacher.npz"), **run_teacher(ref))
+    np.savez_compressed(os.path.join(OUT, "ref_get_git_model.npz"), **run_get_git_model(ref))
     np.savez_compressed(os.path.join(OUT, "ref_student.npz"), **run_student(ref))
     np.savez_compressed(os.path.join(OUT, "ref_training_step.npz"), **run_training_step(ref))
-    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_teacher.npz", "ref_student.npz", "ref_training_step.npz"):
+    for f in ("ref_search.npz", "ref_git_glue.npz", "ref_teacher.npz", "ref_get_git_model.npz", "ref_student.npz", "ref_training_step.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 

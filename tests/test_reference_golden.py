@@ -304,3 +304,37 @@ def test_oracle_teacher_wrapper_equals_the_reference_teacher():
         assert torch.allclose(logits[..., ::S], torch.from_numpy(z[f"clip{i}.fol_logits"]), atol=2e-4, rtol=1e-4)
         assert torch.allclose(vf2[:, ::S, ::S], torch.from_numpy(z[f"clip{i}.fol_visual_features"]), atol=1e-5, rtol=1e-5)
         assert torch.allclose(hidden[:, ::S, ::S], torch.from_numpy(z[f"clip{i}.fol_hidden_states"]), atol=2e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ get_git_model (model.py:681-718)
+@pytest.mark.parametrize("label,param", [("default", {"num_image_with_embedding": 6}),
+                                         ("large", {"image_encoder_type": "CLIPViT_L_14", "test_crop_size": 224,
+                                                    "visual_feature_size": 1024, "num_image_with_embedding": 6})])
+def test_hyper_parameters_equal_what_the_reference_get_git_model_passes(label, param):
+    """What the reference's OWN get_git_model handed to its constructors (recorded by the fixture generator) sizes every kernel:
+    the oracle's GitConfig and the package's get_git_model must carry the same numbers."""
+    import json
+    want = json.loads(str(load("ref_get_git_model.npz")["json"]))[label]
+    td, dec, mod, enc = want["text_decoder"], want["decoder"], want["model"], want["image_encoder"]
+    cfg = go.GitConfig.from_param(param)
+    assert (cfg.image_encoder_type, cfg.resolution) == (enc["name"], enc["input_resolution"])
+    assert (cfg.visual_feature_size, cfg.vocab_size, cfg.hidden_size, cfg.num_layers, cfg.attention_heads, cfg.feedforward_size,
+            cfg.max_caption_length) == (td["visual_feature_size"], td["vocab_size"], td["hidden_size"], td["num_layers"],
+                                        td["attention_heads"], td["feedforward_size"], td["max_caption_length"])
+    assert (cfg.beam_size, cfg.max_steps, cfg.length_penalty, cfg.eos_index, cfg.sos_index) == \
+        (dec["beam_size"], dec["max_steps"], dec["length_penalty"], dec["eos_index"], mod["sos_index"])
+    assert cfg.num_image_with_embedding == mod["num_image_with_embedding"] == mod["n_temporal_embeddings"]
+    gm = importlib.import_module("real-time-video-captioning_b200.model")
+    m = gm.get_git_model(gm.SyntheticTokenizer(), param)
+    d = m.decoder
+    assert (d._eos_index, d.max_steps, d.beam_size, d.length_penalty, d.repetition_penalty, d.temperature) == \
+        (dec["eos_index"], dec["max_steps"], dec["beam_size"], dec["length_penalty"], dec["repetition_penalty"], dec["temperature"])
+    assert (m.sos_index, m.eos_index) == (mod["sos_index"], mod["eos_index"])
+    assert len(m.img_temperal_embedding) == mod["n_temporal_embeddings"]
+    assert list(m.img_temperal_embedding[0].shape) == mod["temporal_embedding_shape"]
+    sd = m.state_dict()
+    assert sd["textual.embedding.words.weight"].shape == (td["vocab_size"], td["hidden_size"])
+    assert sd["textual.visual_projection.0.weight"].shape == (td["hidden_size"], td["visual_feature_size"])
+    assert f"textual.transformer.encoder.layer.{td['num_layers'] - 1}.output.dense.weight" in sd
+    assert f"textual.transformer.encoder.layer.{td['num_layers']}.output.dense.weight" not in sd
+    assert sd["textual.transformer.encoder.layer.0.intermediate.dense.weight"].shape == (td["feedforward_size"], td["hidden_size"])
