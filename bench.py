@@ -254,7 +254,9 @@ def teacher_forward_leg(g, gm, torch, dist, param, B, world, rank, dev, steps=3)
     x = torch.randn(B, FRAMES, 3, RES, RES, generator=torch.Generator().manual_seed(70 + rank)).pin_memory()
 
     def wall(fn):
-        fn()  # warm-up
+        for _ in range(3):  # warm-up: sizing call, CUDA-graph capture call, first replay
+            r = fn()
+            del r
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
