@@ -257,7 +257,7 @@ __device__ __forceinline__ uint4 ld16_line(const bf16* p) {
 
 // Several query rows per clip (NB >= 2: the beams of a clip, or the text rows of a teacher-forced pass).  The scalar body
 // above spends NB x 16 FMAs + the transposing butterflies per loaded 16 bytes: at NB = 4 it ran at a third of the HBM rate
-// (399 us per 0.93 GB launch at 256 clips x 4 beams, profiles/r02_timeline_beam4.md).  Here the visual keys go through the
+// (399 us per 0.93 GB launch at 256 clips x 4 beams, profiles/r02_timeline_beam4_before.md).  Here the visual keys go through the
 // warp-level tensor path (mma.sync m16n8k16 bf16, fp32 accumulate; the work is HBM bound, tcgen05's 64-row minimum would
 // compute 16x padding) with fragments assembled in registers straight from 16-byte global loads -- no shared-memory staging:
 //   scores  S^T[16 keys x 8 beams] = K[16 keys x 64 dims] . Q^T : thread (g, t) of a warp loads 2 x 16 bytes of key rows g and
