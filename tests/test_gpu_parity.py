@@ -202,7 +202,8 @@ def _text_attention_reference(q, vis, txt, anc, n_clips, rpc, heads, scale):
 @pytest.mark.parametrize("n_clips,rpc,heads,n_vis,n_text,splits,use_anc", [
     (3, 1, 12, 1182, 7, 1, False), (3, 4, 12, 1182, 7, 1, True), (2, 4, 12, 1182, 19, 16, True), (2, 2, 12, 394, 3, 6, True),
     (2, 3, 12, 197, 5, 3, True), (1, 8, 12, 197, 4, 1, True), (2, 4, 16, 1542, 9, 1, True), (1, 4, 16, 6168, 14, 1, True),
-    (2, 4, 12, 33, 1, 1, False), (2, 6, 12, 130, 0, 1, False), (1, 4, 12, 1182, 12, 5, True), (5, 4, 12, 16, 2, 2, True)])
+    (2, 4, 12, 33, 1, 1, False), (2, 6, 12, 130, 0, 1, False), (1, 4, 12, 1182, 12, 5, True), (5, 4, 12, 16, 2, 2, True),
+    (2, 4, 12, 300, 30, 1, True), (1, 2, 12, 100, 45, 1, True), (40, 4, 12, 197, 27, 1, True)])  # more text keys than the register prefetch holds
 def test_op_text_attention(g, n_clips, rpc, heads, n_vis, n_text, splits, use_anc):
     """Decode-step attention (scalar body for one row per clip, mma.sync body for several) vs fp32 torch: tails of every tile
     size, key splits, ancestor slots, rows_per_clip that is not a multiple of the row chunk."""
