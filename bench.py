@@ -229,6 +229,24 @@ def config_leg(g, gm, torch, dist, name, param, B, frames_n, sp, steps, warmup, 
     sustained, burst, hbm, _ = peaks
     out["path_frac"] = out["path_tflops_algorithmic"] / sustained
     out["model_frac"] = (B * steps / (ms * 1e-3)) / roofline_model_clips_per_s(gflop, kv_mb, B, sp.max_steps, sustained, hbm)
+    if sp.beam_size > 1:
+        # roofline of the leg's HBM-bound kernel (decode-step attention, several beam rows per clip: the warp-level tensor body):
+        # one more step with per-launch CUDA events on the launching stream (eager launches), as in the headline's profiled pass
+        import ctypes
+        eng.lib.gitb200_profile_gemm(1)
+        eng.caption(sets[0], sp)
+        torch.cuda.synchronize(dev)
+        a_ms, a_by, a_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        eng.lib.gitb200_profile_decode_attention_read(ctypes.byref(a_ms), ctypes.byref(a_by), ctypes.byref(a_n))
+        eng.lib.gitb200_profile_gemm(0)
+        if a_n.value > 0 and a_ms.value > 0:
+            gbs = a_by.value / (a_ms.value * 1e-3) / 1e9
+            out["roofline_decode"] = {"bound": "hbm", "kernel": "text_attention_kernel<4, 2> (decode-step attention, mma.sync body: the clip's beams share every K/V byte)",
+                                      "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "launches_timed": int(a_n.value),
+                                      "algorithmic_bytes_per_launch": a_by.value / a_n.value, "us_per_launch": 1e3 * a_ms.value / a_n.value,
+                                      "share_of_step": a_ms.value / (ms / steps),
+                                      "traffic": 962918400.0,
+                                      "traffic_note": "dram read+write bytes of one launch at 256 clips x 4 beams, ncu --set full of the kernel alone (profiles/r02_text_attention_mma_raw.csv: 955.1 MB read + 7.8 MB written for 961 MB algorithmic)"}
     if name.startswith("large") and sp.max_steps > 2:
         # BASELINE.json configs[3] is an encode-heavy PREFILL sweep: encode + projection + the first decode step only
         sp2 = g.SearchConfig(beam_size=1, max_steps=2, length_penalty=0.6, per_node_beam_size=2, num_keep_best=1)
