@@ -641,7 +641,7 @@ def main():
     gemm_tflops = (g_fl.value / (g_ms.value * 1e-3) / 1e12) if g_ms.value > 0 else None
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_gemm2_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm2_traffic.json")) as fh:
             traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
     except Exception:
         pass
@@ -651,7 +651,7 @@ def main():
     roofline = {"bound": "tensor", "kernel": "gemm2_kernel (2-CTA tcgen05) + gemm_tcgen05_kernel<128> (decode rows)",
                 "achieved": gemm_tflops, "peak": sustained,
                 "unit": "TFLOP/s", "frac": (gemm_tflops / sustained) if gemm_tflops else None, "traffic": traffic,
-                "traffic_note": "avg DRAM read+write bytes per launch of the 4 ViT-layer GEMMs at M=151296 (one 128-clip sub-batch of the 512-clip step; algorithmic average 1.049 GB; profiles/r01_gemm2_traffic.json)",
+                "traffic_note": "avg DRAM read+write bytes per launch of the 4 ViT-layer GEMMs at M=151296 (one 128-clip sub-batch of the 512-clip step; algorithmic average 1.049 GB; profiles/r02_gemm2_traffic.json)",
                 "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_timed": g_n.value, "gemm_share_of_step": g_ms.value / ms_prof if ms_prof > 0 else None,
                 "timed_in": "a second pass of the same K steps with per-launch CUDA events on the launching stream (eager launches)",
@@ -667,14 +667,14 @@ def main():
     dec_gbs = (a_by.value / (a_ms.value * 1e-3) / 1e9) if a_ms.value > 0 else None
     dec_traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_text_attention_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_text_attention_traffic.json")) as fh:
             dec_traffic = json.load(fh)["traffic_bytes_per_launch_avg"]
     except Exception:
         pass
     roofline_decode = {"bound": "hbm", "kernel": "text_attention_kernel (decode-step attention, visual K/V shared by a clip's beams)",
                        "achieved": dec_gbs, "peak": hbm, "unit": "GB/s", "frac": (dec_gbs / hbm) if (dec_gbs and hbm) else None,
                        "traffic": dec_traffic,
-                       "traffic_note": "dram read+write bytes per launch, ncu capture of the first decode step's 6 launches at 512 clips (profiles/r01_text_attention_traffic.json)",
+                       "traffic_note": "dram read+write bytes per launch, ncu capture of the first decode step's 6 launches at 512 clips (profiles/r02_text_attention_traffic.json)",
                        "peak_source": f"{src} hbm_gbs (copy bandwidth)", "launches_timed": a_n.value,
                        "algorithmic_bytes_per_launch": (a_by.value / a_n.value) if a_n.value else None,
                        "share_of_step": (a_ms.value / ms_prof) if ms_prof > 0 else None}
