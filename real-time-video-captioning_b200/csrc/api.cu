@@ -886,13 +886,15 @@ int run_decode(gitb200_ctx* c, const gitb200_search_params& sp, int32_t* tokens_
   const int steps = sp.max_steps - 1;  // model.py:518: while cur_len < max_length, cur_len = t + 1
   // The loop runs in segments of `early_exit_every` steps (all steps when polling is off).  A segment touches only
   // context-owned buffers, so it is captured into a CUDA graph on its second occurrence and replayed from then on; the
-  // poll of the finished-clip count sits between segments.  Saved logits go to a caller buffer: eager.
+  // poll of the finished-clip count sits between segments.  Saved logits go to a caller buffer: its address is part of the
+  // graph key (a caller that hands in the same buffer again -- torch's caching allocator does -- replays; another buffer is
+  // another graph, and the cache is bounded).
   const int seg = (poll_done && c->early_exit_every < steps) ? c->early_exit_every : steps;
-  const bool graphable = c->graph_segments && logits_out == nullptr && B > c->graph_max_clips;
+  const bool graphable = c->graph_segments && B > c->graph_max_clips;
   for (int t0 = 0; t0 < steps; t0 += seg) {
     const int n = steps - t0 < seg ? steps - t0 : seg;
     gitb200_ctx::GraphKey key;
-    key.kind = 5; key.i0 = B; key.i1 = t0; key.i2 = n; key.i3 = c->cur_nv; key.sp = sp;
+    key.kind = 5; key.i0 = B; key.i1 = t0; key.i2 = n; key.i3 = c->cur_nv; key.sp = sp; key.p0 = logits_out;
     const int r = run_graphed(c, key, s, graphable, [&]() -> int {
       if (t0 == 0) CUDA_OK(c, search_init(st, k.sos, s));
       for (int t = t0; t < t0 + n; ++t) {

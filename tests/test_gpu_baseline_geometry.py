@@ -524,3 +524,21 @@ def test_large_batch_graph_segments_equal_eager(g):
         assert (replays > 20) if mode == "graphs" else (replays == 0), (mode, replays)
     for (te, le), (tg, lg) in zip(results["eager"], results["graphs"]):
         assert torch.equal(te, tg) and torch.equal(le, lg)
+    # saved per-step logits (the teacher wrapper's path): the caller's logits buffer is part of the graph key -- the same buffer
+    # again replays, and tokens, scores AND the saved logits equal the eager launches bit for bit
+    sp = g.SearchConfig(beam_size=4, max_steps=9)
+    saved = {}
+    for mode in ("eager", "graphs"):
+        eng.set_graph_segments(mode == "graphs")
+        before = eng.lib.gitb200_graph_launches(eng.h)
+        host = a.cpu().pin_memory()
+        for _ in range(4):
+            tok, lp, logits, _ = eng.caption_from_host(host, sp, chunk_clips=5, save_logits=True)
+            torch.cuda.synchronize()
+            keep = (tok.cpu().clone(), lp.cpu().clone(), logits[: eng.last_decode_steps()].cpu().clone())
+            del tok, lp, logits     # torch's caching allocator hands the same blocks to the next call
+        saved[mode] = keep
+        replays = eng.lib.gitb200_graph_launches(eng.h) - before
+        assert (replays > 0) if mode == "graphs" else (replays == 0), (mode, replays)
+    for x, y in zip(saved["eager"], saved["graphs"]):
+        assert torch.equal(x, y)
