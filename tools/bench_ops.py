@@ -68,7 +68,33 @@ def decode_gemms():
             print(line, flush=True)
 
 
+def vocab_gemm():
+    """Vocabulary head (fp32 logits, N = 30720 padded columns, K = 768) per tile width: CUPTI kernel durations."""
+    from torch.profiler import ProfilerActivity, profile
+    N, K = 30720, 768
+    w = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.zeros(N, device="cuda")
+    for M in (512, 1024, 2048):
+        a = torch.randn(M, K, device="cuda").bfloat16()
+        line = f"M={M:5d} N={N} K={K} fp32 out:"
+        for tile in (0, 128, 256):
+            for _ in range(3):
+                eng.op_gemm(a, w, bias, None, 0, True, tile)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(10):
+                    eng.op_gemm(a, w, bias, None, 0, True, tile)
+                torch.cuda.synchronize()
+            ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "gemm" in e.name]
+            us = sum(e.time_range.end - e.time_range.start for e in ev) / max(1, len(ev))
+            line += f"  tile {tile:3d}: {us:6.1f} us = {2.0 * M * N * K / us / 1e6:6.0f} TFLOP/s"
+        print(line, flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vocab_gemm":
+        vocab_gemm()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "decode_gemms":
         decode_gemms()
         sys.exit(0)
