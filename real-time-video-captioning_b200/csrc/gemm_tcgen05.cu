@@ -39,7 +39,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;  // 4 for BN=256, 6 for BN=128
   static constexpr int TMEM_COLS = 2 * BN;                  // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int F32_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // fp32 output: one 32 x 32 transpose slice per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + F32_STAGE_BYTES;
 };
 
 struct Epilogue {
@@ -69,6 +70,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  float* const f32_stage = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + C::STAGES * C::STAGE_BYTES + 256);
   auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + C::A_BYTES; };
 
@@ -189,11 +191,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c, v);
         ptx::tmem_ld_wait();
-        if (row_ok) {
-          const int col = n0 + c;
-          float f[32];
+        const int col = n0 + c;
+        float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (row_ok) {
           if (ep.bias != nullptr) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col);
 #pragma unroll
@@ -243,11 +245,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               o4[i] = u;
             }
           }
-          if (ep.out_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(ep.out_f32 + (size_t)orow * ep.ldo32 + col);
+        }
+        if (ep.out_f32 != nullptr) {  // warp-uniform
+          // A lane holds 32 consecutive columns of ONE row: stored directly, every instruction would touch 32 rows with 16 bytes
+          // each (half-written sectors: the vocabulary head ran at 1.1 TB/s of logits).  The 32 x 32 block goes through this warp's
+          // shared-memory slice (16-byte chunk index XOR row: conflict-free both ways) and leaves as whole 128-byte row segments,
+          // four rows per instruction.
+          float* st = f32_stage + (warp - 2) * 1024;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(st + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = j * 4 + (lane >> 3), ch = lane & 7;
+            const float4 val = *reinterpret_cast<const float4*>(st + rr * 32 + ((ch ^ (rr & 7)) << 2));
+            const int r2 = m0 + quarter * 32 + rr;
+            if (r2 < M) {
+              const int o2 = ep.gin > 0 ? (r2 / ep.gin) * ep.gout + (r2 % ep.gin) + ep.goff : r2;
+              *reinterpret_cast<float4*>(ep.out_f32 + (size_t)o2 * ep.ldo32 + col + ch * 4) = val;
+            }
           }
+          __syncwarp();
         }
       }
       ptx::tc_fence_before();
